@@ -1,0 +1,307 @@
+// agg_kernels.cuh -- the neighbour-aggregation kernel family (GCN SpMM and fused GAT), sm_100a.
+//
+// Replaces the reference kernels aggr_gcn / aggr_gcn_target (include/aggr_gcn.h:5-36,78-114) and
+// aggr_gat / aggr_gat_fine (include/aggr_gat.h:116-205).  Not a port: the reference maps one warp
+// to one row (or one neighbour group), F/32 y-warps re-read idx/val, every lane issues scalar
+// 4-byte gathers and split rows are combined with float atomics.  Here:
+//
+//   * EDGE-BALANCED ITEMS.  The edge array is cut into fixed-size items; a "virtual warp" of
+//     LPR = F/4 lanes (8/16/32) owns one item and walks the rows that intersect it.  A hub row
+//     of 10^5..10^6 edges is therefore spread over thousands of virtual warps and a warp never
+//     idles on a short row.  One 32-lane warp always stages 512 consecutive edges.
+//   * TMA STAGING.  The 512 idx (and val) entries of a warp are brought into shared memory by
+//     two 1-D bulk copies (cp.async.bulk -> UBLKCP) completing on an mbarrier; the walk then
+//     reads them as conflict-free broadcasts instead of 2 SHFL per edge-lane.
+//   * 128-BIT GATHERS, U-DEEP.  Each lane gathers float4 of the source row; U (8) independent
+//     gathers are issued before the first FMA so every warp keeps 4 KB in flight.
+//   * DETERMINISTIC SPLIT ROWS.  A row that crosses item boundaries leaves per-item partials in
+//     a carry buffer; a small fix-up kernel adds them in item order (no float atomics, results
+//     are run-to-run reproducible).  Only the scheduled mode -- whose group order is
+//     arbitrary (locality slices) -- combines with 128-bit RED.ADD, like the reference.
+//   * 64-bit addressing of X/Y (the reference overflows int at idx*F, aggr_gcn.h:23).
+#pragma once
+#include <climits>
+
+#include "common.cuh"
+
+namespace gnnagg {
+
+struct AggParams {
+    // CSR (or scheduled group list): ptr has num_rows+1 entries, idx/val num_edges entries
+    const int *__restrict__ ptr;
+    const int *__restrict__ idx;
+    const float *__restrict__ val;       // GCN edge values; unused for GAT
+    const int *__restrict__ target;      // scheduled mode: output row of every group
+    const int *__restrict__ item_row;    // row containing edge k*kFineItem
+    const float *__restrict__ X;         // [*, F]
+    const float *__restrict__ att;       // GAT attention table [n,2]
+    float *__restrict__ Y;               // [n, F]
+    float *__restrict__ carry;           // [num_items, F] partials of rows entering an item
+    float *__restrict__ den_row;         // GAT: [n] denominator of rows that start in an item and leave it
+    float *__restrict__ carry_den;       // GAT: [num_items]
+    float *__restrict__ newval;          // GAT scheduled: un-normalised edge weights (aggr_gat.h:192)
+    int num_rows;
+    int num_edges;
+    int F;
+    float slope;
+    int bulk_ok;                         // idx/val 16-byte aligned -> TMA staging allowed
+};
+
+enum { kModeGCN = 0, kModeGAT = 1 };
+
+template <int LPR, int NV, int MODE, bool SCHED>
+__global__ void __launch_bounds__(kCtaThreads) agg_kernel(const AggParams p)
+{
+    constexpr int VPW = 32 / LPR;             // virtual warps per warp
+    constexpr int EB = kWarpEdges / VPW;      // edges per item
+    constexpr int U = (NV == 1) ? 8 : 4;      // gathers in flight per lane = U*NV float4
+    constexpr int CHUNK = LPR * 4 * NV;       // feature columns covered per pass
+    static_assert(LPR >= 8 && U <= LPR && EB % kFineItem == 0, "virtual warp narrower than 8 lanes is not supported");
+
+    __shared__ __align__(16) int s_idx[kCtaWarps][kWarpEdges];
+    __shared__ __align__(16) float s_val[kCtaWarps][kWarpEdges];
+    __shared__ __align__(8) uint64_t s_bar[kCtaWarps];
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = (int64_t)blockIdx.x * kCtaWarps + warp;
+    const int64_t wbase64 = gwarp * kWarpEdges;
+    if (wbase64 >= p.num_edges) return;  // whole warp idle (warp-uniform)
+    const int wbase = (int)wbase64;
+    const int wcnt = min(kWarpEdges, p.num_edges - wbase);
+
+    // ---------------- stage idx (+val) of this warp's 512 edges ----------------
+    int *my_idx = s_idx[warp];
+    float *my_val = s_val[warp];
+    {
+        const int nb = p.bulk_ok ? (wcnt & ~3) : 0;  // bulk copies need 16-byte multiples
+        const uint32_t bar = smem_u32(&s_bar[warp]);
+        if (nb > 0) {
+            if (lane == 0) {
+                mbar_init(bar, 1);
+                fence_proxy_async();  // init visible to the async proxy; CTA scope (no L1 invalidate)
+                const uint32_t bytes = (uint32_t)nb * 4u;
+                mbar_expect_tx(bar, (MODE == kModeGCN) ? 2u * bytes : bytes);
+                bulk_g2s(smem_u32(my_idx), p.idx + wbase, bytes, bar);
+                if (MODE == kModeGCN) bulk_g2s(smem_u32(my_val), p.val + wbase, bytes, bar);
+            }
+        }
+        for (int i = nb + lane; i < wcnt; i += 32) {
+            my_idx[i] = __ldg(p.idx + wbase + i);
+            if (MODE == kModeGCN) my_val[i] = __ldg(p.val + wbase + i);
+        }
+        __syncwarp();
+        if (nb > 0) mbar_wait(bar, 0);
+        if (MODE == kModeGAT) {
+            // source half of the attention logit, gathered once per edge: att[2u+1] (aggr_gat.h:138)
+#pragma unroll 4
+            for (int i = lane; i < wcnt; i += 32) my_val[i] = __ldg(p.att + 2 * (size_t)my_idx[i] + 1);
+            __syncwarp();
+        }
+    }
+
+    // ---------------- the walk: one virtual warp per item ----------------
+    const int vw = lane / LPR;
+    const int vl = lane % LPR;
+    const int e0 = wbase + vw * EB;
+    if (e0 >= p.num_edges) return;  // no *_sync below this point
+    const int e1 = min(p.num_edges, e0 + EB);
+    const int64_t item = gwarp * VPW + vw;
+    const int F = p.F;
+
+    for (int cb = 0; cb < F; cb += CHUNK) {
+        const int col = cb + vl * 4;
+        const bool act0 = col < F;
+        const bool act1 = (NV > 1) && (col + LPR * 4 < F);
+
+        int row = (e0 == 0) ? 0 : __ldg(p.item_row + e0 / kFineItem);
+        int row_end = __ldg(p.ptr + row + 1);
+        bool carry_in = SCHED ? false : (__ldg(p.ptr + row) < e0);
+        float a_dst = 0.f;
+        if (MODE == kModeGAT) a_dst = __ldg(p.att + 2 * (size_t)(SCHED ? __ldg(p.target + row) : row));
+
+        float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+        float den = 0.f;
+
+        // closes `row`: writes / accumulates its result and moves to the next row
+        auto flush = [&](bool at_item_end) {
+            if (SCHED) {
+                const int t = __ldg(p.target + row);
+                const bool merge = !at_item_end && (row + 1 < p.num_rows) && (__ldg(p.target + row + 1) == t);
+                if (!merge) {  // consecutive groups of one target are summed in registers first
+                    float *y = p.Y + (size_t)t * F + col;
+                    if (act0) red_add_f4(y, acc0);
+                    if (act1) red_add_f4(y + LPR * 4, acc1);
+                    if (MODE == kModeGAT && vl == 0 && cb == 0) atomicAdd(p.den_row + t, den);
+                    acc0 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    acc1 = acc0;
+                    den = 0.f;
+                }
+            } else if (carry_in) {
+                float *c = p.carry + (size_t)item * F + col;
+                if (act0) stg_f4(c, acc0);
+                if (act1) stg_f4(c + LPR * 4, acc1);
+                if (MODE == kModeGAT && vl == 0 && cb == 0) p.carry_den[item] = den;
+                carry_in = false;
+            } else {
+                float *y = p.Y + (size_t)row * F + col;
+                if (MODE == kModeGAT) {
+                    // complete row: normalise here (aggr_gat.h:163); empty row -> 0 (documented)
+                    const float inv = (den != 0.f) ? __fdividef(1.f, den) : 0.f;
+                    acc0 = make_float4(acc0.x * inv, acc0.y * inv, acc0.z * inv, acc0.w * inv);
+                    acc1 = make_float4(acc1.x * inv, acc1.y * inv, acc1.z * inv, acc1.w * inv);
+                }
+                if (act0) stg_f4(y, acc0);
+                if (act1) stg_f4(y + LPR * 4, acc1);
+            }
+            if (!SCHED) {
+                acc0 = make_float4(0.f, 0.f, 0.f, 0.f);
+                acc1 = acc0;
+                den = 0.f;
+            }
+            ++row;
+            if (row < p.num_rows) {
+                row_end = __ldg(p.ptr + row + 1);
+                if (MODE == kModeGAT) a_dst = __ldg(p.att + 2 * (size_t)(SCHED ? __ldg(p.target + row) : row));
+            } else {
+                row_end = INT_MAX;
+            }
+        };
+
+        int e = e0;
+        while (row_end == e) flush(false);  // leading empty rows (only item 0 can see any)
+
+        while (e < e1) {
+            const int nb = min(U, e1 - e);
+            int src[U];
+            float w[U];
+            float4 v0[U], v1[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int k = min(e + u, e1 - 1) - wbase;
+                src[u] = my_idx[k];
+                w[u] = my_val[k];
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const float *x = p.X + (size_t)src[u] * F + col;
+                v0[u] = act0 ? ldg_f4(x) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (NV > 1) v1[u] = act1 ? ldg_f4(x + LPR * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            float wout = 0.f;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (u < nb) {
+                    while (row_end == e + u) flush(false);
+                    float wu = w[u];
+                    if (MODE == kModeGAT) {
+                        const float s = a_dst + wu;
+                        wu = __expf(fmaxf(s, s * p.slope));  // aggr_gat.h:143
+                        den += wu;
+                        if (SCHED && vl == u % LPR) wout = wu;
+                    }
+                    fma4(acc0, wu, v0[u]);
+                    if (NV > 1) fma4(acc1, wu, v1[u]);
+                }
+            }
+            if (MODE == kModeGAT && SCHED && cb == 0 && p.newval != nullptr) {
+                // one coalesced store per batch instead of one per edge (U <= LPR always holds)
+                if (vl < nb) p.newval[e + vl] = wout;
+            }
+            e += nb;
+        }
+
+        // item end
+        if (row_end == e1) {
+            while (row < p.num_rows && row_end == e1) flush(true);  // row closes here (+ trailing empty rows)
+        } else if (SCHED) {
+            flush(true);
+        } else if (carry_in) {
+            float *c = p.carry + (size_t)item * F + col;  // row spans the whole item
+            if (act0) stg_f4(c, acc0);
+            if (act1) stg_f4(c + LPR * 4, acc1);
+            if (MODE == kModeGAT && vl == 0 && cb == 0) p.carry_den[item] = den;
+        } else {
+            float *y = p.Y + (size_t)row * F + col;  // row starts here and continues: raw partial
+            if (act0) stg_f4(y, acc0);
+            if (act1) stg_f4(y + LPR * 4, acc1);
+            if (MODE == kModeGAT && vl == 0 && cb == 0) p.den_row[row] = den;
+        }
+    }
+}
+
+// Adds the carried partials of rows that cross item boundaries, in item order.
+// One warp per item; only the first carry item of a row does the work for that row.
+template <int MODE>
+__global__ void __launch_bounds__(256) agg_fixup_kernel(const AggParams p, int EB, int64_t num_items)
+{
+    const int64_t item = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (item < 1 || item >= num_items) return;
+    const int e0 = (int)(item * EB);
+    const int row = __ldg(p.item_row + e0 / kFineItem);
+    const int rs = __ldg(p.ptr + row);
+    if (rs >= e0) return;                  // no row enters this item
+    if (item != (int64_t)(rs / EB) + 1) return;  // not the first carry item of that row
+    const int re = __ldg(p.ptr + row + 1);
+    const int64_t last = (int64_t)(re - 1) / EB;  // item holding the row's last edge
+    const int F = p.F;
+    float dsum = 0.f;
+    if (MODE == kModeGAT) {
+        dsum = p.den_row[row];
+        for (int64_t b = item; b <= last; ++b) dsum += p.carry_den[b];
+    }
+    const float inv = (MODE == kModeGAT) ? ((dsum != 0.f) ? __fdividef(1.f, dsum) : 0.f) : 1.f;
+    for (int col = lane * 4; col < F; col += 128) {
+        float *y = p.Y + (size_t)row * F + col;
+        float4 acc = *reinterpret_cast<const float4 *>(y);
+        int64_t b = item;
+        for (; b + 4 <= last + 1; b += 4) {
+            const float4 c0 = *reinterpret_cast<const float4 *>(p.carry + (size_t)b * F + col);
+            const float4 c1 = *reinterpret_cast<const float4 *>(p.carry + (size_t)(b + 1) * F + col);
+            const float4 c2 = *reinterpret_cast<const float4 *>(p.carry + (size_t)(b + 2) * F + col);
+            const float4 c3 = *reinterpret_cast<const float4 *>(p.carry + (size_t)(b + 3) * F + col);
+            acc = add4(add4(add4(add4(acc, c0), c1), c2), c3);
+        }
+        for (; b <= last; ++b) acc = add4(acc, *reinterpret_cast<const float4 *>(p.carry + (size_t)b * F + col));
+        if (MODE == kModeGAT) acc = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+        stg_f4(y, acc);
+    }
+}
+
+// scheduled GAT epilogue: Y[v,:] /= den[v] when den != 0  (scaleArray, aggr_gat.h:207-213)
+__global__ void __launch_bounds__(256) gat_scale_kernel(float *__restrict__ Y, const float *__restrict__ den, int F,
+                                                        int64_t total4)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const int64_t row = (i * 4) / F;
+    const float d = __ldg(den + row);
+    if (d != 0.f) {
+        float4 v = reinterpret_cast<float4 *>(Y)[i];
+        const float inv = __fdividef(1.f, d);
+        v = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
+        reinterpret_cast<float4 *>(Y)[i] = v;
+    }
+}
+
+// row containing edge k*kFineItem, for every k (one thread each)
+__global__ void __launch_bounds__(256) item_row_kernel(const int *__restrict__ ptr, int num_rows, int num_edges,
+                                                       int *__restrict__ item_row, int num_items)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= num_items) return;
+    const int64_t e64 = (int64_t)k * kFineItem;
+    const int e = (int)(e64 < num_edges ? e64 : num_edges - 1);
+    int lo = 0, hi = num_rows - 1;  // last r with ptr[r] <= e
+    while (lo < hi) {
+        const int mid = (int)(((int64_t)lo + hi + 1) >> 1);
+        if (__ldg(ptr + mid) <= e)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    item_row[k] = lo;
+}
+
+}  // namespace gnnagg

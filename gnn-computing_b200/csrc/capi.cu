@@ -1,0 +1,678 @@
+// capi.cu -- the C ABI of libgnnagg.so (include/gnnagg.h): aggregator object, launch logic.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "agg_kernels.cuh"
+#include "edge_kernels.cuh"
+#include "gnnagg.h"
+#include "internal.h"
+
+namespace gnnagg {
+
+static thread_local std::string g_error;
+
+int set_error(int code, const char *msg)
+{
+    g_error = msg ? msg : "";
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            char _buf[512];                                                                  \
+            snprintf(_buf, sizeof _buf, "%s:%d %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return set_error(GNNAGG_ERR_CUDA, _buf);                                         \
+        }                                                                                    \
+    } while (0)
+
+#define LAUNCH_CHECK(a)                   \
+    do {                                  \
+        CUDA_TRY(cudaPeekAtLastError()); \
+        ++(a)->launches;                  \
+    } while (0)
+
+template <class T>
+static int ensure(T *&p, size_t &cap, size_t need)
+{
+    if (need <= cap && p) return GNNAGG_OK;
+    if (p) CUDA_TRY(cudaFree(p));
+    p = nullptr;
+    cap = 0;
+    CUDA_TRY(cudaMalloc((void **)&p, (need ? need : 1) * sizeof(T)));
+    cap = need;
+    return GNNAGG_OK;
+}
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace gnnagg
+
+using namespace gnnagg;
+
+struct gnnagg_aggregator {
+    // borrowed graph
+    const int *d_ptr = nullptr, *d_idx = nullptr;
+    const int *h_ptr_user = nullptr, *h_idx_user = nullptr;
+    std::vector<int> h_ptr, h_idx;  // lazily mirrored (aggregator.h:30-39)
+    int n = 0, m = 0;
+    const float *d_val = nullptr;
+    // derived
+    int *d_item_row = nullptr;
+    int num_items = 0;  // ceil(m / kFineItem)
+    // scratch (owned)
+    float *carry = nullptr;
+    size_t carry_cap = 0;
+    float *den_row = nullptr;
+    size_t den_row_cap = 0;
+    float *carry_den = nullptr;
+    size_t carry_den_cap = 0;
+    float *newval = nullptr;
+    size_t newval_cap = 0;
+    float *ax = nullptr;
+    size_t ax_cap = 0;
+    // host-buffer entry points: device staging
+    float *st_in = nullptr, *st_out = nullptr, *st_w = nullptr, *st_att = nullptr;
+    size_t st_in_cap = 0, st_out_cap = 0, st_w_cap = 0, st_att_cap = 0;
+    // schedule (owned device copies)
+    int sched_kind = GNNAGG_SCHED_NOP;
+    int num_target = 0, sched_edges = 0, sched_items = 0;
+    int neighbor_group_size = 0, locality_partition_num = 0;
+    int *s_ptr = nullptr, *s_idx = nullptr, *s_target = nullptr, *s_perm = nullptr, *s_item_row = nullptr;
+    float *s_val = nullptr;  // owned only when s_perm != nullptr (locality kinds); NG aliases d_val
+    int64_t launches = 0;
+};
+
+namespace gnnagg {
+
+static EdgeParams edge_params(const gnnagg_aggregator *a)
+{
+    EdgeParams g;
+    g.ptr = a->d_ptr;
+    g.idx = a->d_idx;
+    g.item_row = a->d_item_row;
+    g.num_rows = a->n;
+    g.num_edges = a->m;
+    g.num_items = a->num_items;
+    return g;
+}
+
+static EdgeParams edge_params_sched(const gnnagg_aggregator *a)
+{
+    EdgeParams g;
+    g.ptr = a->s_ptr;
+    g.idx = a->s_idx;
+    g.item_row = a->s_item_row;
+    g.num_rows = a->num_target;
+    g.num_edges = a->sched_edges;
+    g.num_items = a->sched_items;
+    return g;
+}
+
+static int build_item_rows(gnnagg_aggregator *a, const int *d_ptr, int rows, int edges, int **out, int *items,
+                           cudaStream_t st)
+{
+    *items = (int)cdiv(edges, kFineItem);
+    if (*out) CUDA_TRY(cudaFree(*out));
+    *out = nullptr;
+    CUDA_TRY(cudaMalloc((void **)out, (size_t)(*items ? *items : 1) * sizeof(int)));
+    if (*items > 0) {
+        item_row_kernel<<<(unsigned)cdiv(*items, 256), 256, 0, st>>>(d_ptr, rows, edges, *out, *items);
+        LAUNCH_CHECK(a);
+    }
+    return GNNAGG_OK;
+}
+
+static void free_schedule(gnnagg_aggregator *a)
+{
+    cudaFree(a->s_ptr);
+    cudaFree(a->s_idx);
+    cudaFree(a->s_target);
+    cudaFree(a->s_item_row);
+    if (a->s_perm) cudaFree(a->s_val);
+    cudaFree(a->s_perm);
+    a->s_ptr = a->s_idx = a->s_target = a->s_item_row = a->s_perm = nullptr;
+    a->s_val = nullptr;
+    a->num_target = a->sched_edges = a->sched_items = 0;
+    a->sched_kind = GNNAGG_SCHED_NOP;
+}
+
+__global__ void gather_val_kernel(const float *__restrict__ val, const int *__restrict__ perm, float *__restrict__ out,
+                                  int count)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = __ldg(val + __ldg(perm + i));
+}
+
+static int check_feat(int F)
+{
+    if (F < 4 || F > 1024 || (F & 3)) return set_error(GNNAGG_ERR_ARG, "feat must be a multiple of 4 in [4,1024]");
+    return GNNAGG_OK;
+}
+
+// lanes per virtual warp for a feature width
+static inline int lpr_for(int F) { return F <= 32 ? 8 : (F <= 64 ? 16 : 32); }
+
+template <int MODE, bool SCHED>
+static int launch_agg(gnnagg_aggregator *a, const AggParams &p, cudaStream_t st)
+{
+    const int F = p.F;
+    const unsigned grid = (unsigned)cdiv(p.num_edges, (int64_t)kWarpEdges * kCtaWarps);
+    if (F <= 32)
+        agg_kernel<8, 1, MODE, SCHED><<<grid, kCtaThreads, 0, st>>>(p);
+    else if (F <= 64)
+        agg_kernel<16, 1, MODE, SCHED><<<grid, kCtaThreads, 0, st>>>(p);
+    else if (F <= 128)
+        agg_kernel<32, 1, MODE, SCHED><<<grid, kCtaThreads, 0, st>>>(p);
+    else
+        agg_kernel<32, 2, MODE, SCHED><<<grid, kCtaThreads, 0, st>>>(p);
+    LAUNCH_CHECK(a);
+    if (!SCHED) {
+        const int EB = kWarpEdges / (32 / lpr_for(F));
+        const int64_t items = cdiv(p.num_edges, EB);
+        if (items > 1) {
+            agg_fixup_kernel<MODE><<<(unsigned)cdiv(items, 8), 256, 0, st>>>(p, EB, items);
+            LAUNCH_CHECK(a);
+        }
+    }
+    return GNNAGG_OK;
+}
+
+static int aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static int gcn_run_impl(gnnagg_aggregator *a, const float *X, float *Y, int F, int scheduled, cudaStream_t st)
+{
+    if (!a || !X || !Y) return set_error(GNNAGG_ERR_ARG, "gnnagg_gcn_run: NULL argument");
+    if (int rc = check_feat(F)) return rc;
+    if (!aligned16(X) || !aligned16(Y)) return set_error(GNNAGG_ERR_ARG, "X and Y must be 16-byte aligned");
+    if (!a->d_val) return set_error(GNNAGG_ERR_STATE, "gnnagg_gcn_run: edge values not set (gnnagg_set_val)");
+    AggParams p{};
+    p.X = X;
+    p.Y = Y;
+    p.F = F;
+    if (scheduled) {
+        if (a->sched_kind == GNNAGG_SCHED_NOP) return set_error(GNNAGG_ERR_STATE, "scheduled run before schedule");
+        CUDA_TRY(cudaMemsetAsync(Y, 0, (size_t)a->n * F * sizeof(float), st));  // aggr_gcn.h:393
+        if (a->sched_edges == 0) return GNNAGG_OK;
+        p.ptr = a->s_ptr;
+        p.idx = a->s_idx;
+        p.val = a->s_val;
+        p.target = a->s_target;
+        p.item_row = a->s_item_row;
+        p.num_rows = a->num_target;
+        p.num_edges = a->sched_edges;
+        p.bulk_ok = aligned16(p.idx) && aligned16(p.val);
+        return launch_agg<kModeGCN, true>(a, p, st);
+    }
+    if (a->m == 0) {
+        CUDA_TRY(cudaMemsetAsync(Y, 0, (size_t)a->n * F * sizeof(float), st));
+        return GNNAGG_OK;
+    }
+    const int EB = kWarpEdges / (32 / lpr_for(F));
+    if (int rc = ensure(a->carry, a->carry_cap, (size_t)cdiv(a->m, EB) * F)) return rc;
+    p.ptr = a->d_ptr;
+    p.idx = a->d_idx;
+    p.val = a->d_val;
+    p.item_row = a->d_item_row;
+    p.carry = a->carry;
+    p.num_rows = a->n;
+    p.num_edges = a->m;
+    p.bulk_ok = aligned16(p.idx) && aligned16(p.val);
+    return launch_agg<kModeGCN, false>(a, p, st);
+}
+
+static int gat_run_impl(gnnagg_aggregator *a, const float *X, const float *att, float *Y, int F, float slope,
+                        int scheduled, cudaStream_t st)
+{
+    if (!a || !X || !Y || !att) return set_error(GNNAGG_ERR_ARG, "gnnagg_gat_run: NULL argument");
+    if (int rc = check_feat(F)) return rc;
+    if (!aligned16(X) || !aligned16(Y)) return set_error(GNNAGG_ERR_ARG, "X and Y must be 16-byte aligned");
+    if (int rc = ensure(a->den_row, a->den_row_cap, (size_t)a->n)) return rc;
+    AggParams p{};
+    p.X = X;
+    p.Y = Y;
+    p.att = att;
+    p.F = F;
+    p.slope = slope;
+    p.den_row = a->den_row;
+    if (scheduled) {
+        if (a->sched_kind == GNNAGG_SCHED_NOP) return set_error(GNNAGG_ERR_STATE, "scheduled run before schedule");
+        CUDA_TRY(cudaMemsetAsync(Y, 0, (size_t)a->n * F * sizeof(float), st));
+        if (a->sched_edges == 0) return GNNAGG_OK;
+        CUDA_TRY(cudaMemsetAsync(a->den_row, 0, (size_t)a->n * sizeof(float), st));
+        if (int rc = ensure(a->newval, a->newval_cap, (size_t)a->sched_edges)) return rc;
+        p.ptr = a->s_ptr;
+        p.idx = a->s_idx;
+        p.target = a->s_target;
+        p.item_row = a->s_item_row;
+        p.newval = a->newval;
+        p.num_rows = a->num_target;
+        p.num_edges = a->sched_edges;
+        p.bulk_ok = aligned16(p.idx);
+        if (int rc = launch_agg<kModeGAT, true>(a, p, st)) return rc;
+        const int64_t total4 = (int64_t)a->n * F / 4;
+        gat_scale_kernel<<<(unsigned)cdiv(total4, 256), 256, 0, st>>>(Y, a->den_row, F, total4);
+        LAUNCH_CHECK(a);
+        return GNNAGG_OK;
+    }
+    if (a->m == 0) {
+        CUDA_TRY(cudaMemsetAsync(Y, 0, (size_t)a->n * F * sizeof(float), st));
+        return GNNAGG_OK;
+    }
+    const int EB = kWarpEdges / (32 / lpr_for(F));
+    if (int rc = ensure(a->carry, a->carry_cap, (size_t)cdiv(a->m, EB) * F)) return rc;
+    if (int rc = ensure(a->carry_den, a->carry_den_cap, (size_t)a->num_items)) return rc;
+    p.ptr = a->d_ptr;
+    p.idx = a->d_idx;
+    p.item_row = a->d_item_row;
+    p.carry = a->carry;
+    p.carry_den = a->carry_den;
+    p.num_rows = a->n;
+    p.num_edges = a->m;
+    p.bulk_ok = aligned16(p.idx);
+    return launch_agg<kModeGAT, false>(a, p, st);
+}
+
+// out[v] = sum over row v of in[e]; deterministic
+static int rowsum_impl(gnnagg_aggregator *a, const float *in, float *out, cudaStream_t st)
+{
+    if (a->m == 0) {
+        CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)a->n * sizeof(float), st));
+        return GNNAGG_OK;
+    }
+    if (int rc = ensure(a->carry_den, a->carry_den_cap, (size_t)a->num_items)) return rc;
+    const EdgeParams g = edge_params(a);
+    const unsigned grid = (unsigned)cdiv(a->num_items, 256);
+    rowsum_kernel<<<grid, 256, 0, st>>>(g, in, out, a->carry_den);
+    LAUNCH_CHECK(a);
+    if (a->num_items > 1) {
+        rowsum_fixup_kernel<<<grid, 256, 0, st>>>(g, out, a->carry_den);
+        LAUNCH_CHECK(a);
+    }
+    return GNNAGG_OK;
+}
+
+}  // namespace gnnagg
+
+extern "C" {
+
+int gnnagg_version(void) { return 100; }
+const char *gnnagg_last_error(void) { return g_error.c_str(); }
+
+int gnnagg_device_info(int *sm_count, int *cc_major, int *cc_minor, char *name, int name_len)
+{
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (name && name_len > 0) {
+        strncpy(name, prop.name, (size_t)name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    return GNNAGG_OK;
+}
+
+int gnnagg_create(const int *d_ptr, const int *d_idx, const int *h_ptr, const int *h_idx, int num_v, int num_e,
+                  gnnagg_aggregator **out)
+{
+    if (!out || !d_ptr || (num_e > 0 && !d_idx) || num_v < 0 || num_e < 0)
+        return set_error(GNNAGG_ERR_ARG, "gnnagg_create: bad argument");
+    gnnagg_aggregator *a = new gnnagg_aggregator();
+    a->d_ptr = d_ptr;
+    a->d_idx = d_idx;
+    a->h_ptr_user = h_ptr;
+    a->h_idx_user = h_idx;
+    a->n = num_v;
+    a->m = num_e;
+    const int rc = build_item_rows(a, d_ptr, num_v, num_e, &a->d_item_row, &a->num_items, 0);
+    if (rc != GNNAGG_OK) {
+        delete a;
+        return rc;
+    }
+    *out = a;
+    return GNNAGG_OK;
+}
+
+int gnnagg_destroy(gnnagg_aggregator *a)
+{
+    if (!a) return GNNAGG_OK;
+    free_schedule(a);
+    cudaFree(a->d_item_row);
+    cudaFree(a->carry);
+    cudaFree(a->den_row);
+    cudaFree(a->carry_den);
+    cudaFree(a->newval);
+    cudaFree(a->ax);
+    cudaFree(a->st_in);
+    cudaFree(a->st_out);
+    cudaFree(a->st_w);
+    cudaFree(a->st_att);
+    delete a;
+    return GNNAGG_OK;
+}
+
+int gnnagg_set_val(gnnagg_aggregator *a, const float *d_val)
+{
+    if (!a) return set_error(GNNAGG_ERR_ARG, "gnnagg_set_val: NULL aggregator");
+    a->d_val = d_val;
+    if (a->sched_kind == GNNAGG_SCHED_NOP) return GNNAGG_OK;
+    if (a->s_perm) {  // locality kinds keep a permuted copy (aggr_gcn.h:522-537)
+        if (!a->s_val) CUDA_TRY(cudaMalloc((void **)&a->s_val, (size_t)(a->sched_edges ? a->sched_edges : 1) * sizeof(float)));
+        if (d_val && a->sched_edges > 0) {
+            gather_val_kernel<<<(unsigned)cdiv(a->sched_edges, 256), 256>>>(d_val, a->s_perm, a->s_val, a->sched_edges);
+            LAUNCH_CHECK(a);
+        }
+    } else {
+        a->s_val = const_cast<float *>(d_val);  // d_val_scheduled = d_val (aggr_gcn.h:506,542)
+    }
+    return GNNAGG_OK;
+}
+
+int gnnagg_schedule_apply(gnnagg_aggregator *a, int kind, const int *params, int nparams, int total_num_v)
+{
+    if (!a || !params || nparams < 1) return set_error(GNNAGG_ERR_ARG, "gnnagg_schedule_apply: bad argument");
+    if (kind == GNNAGG_SCHED_LOCALITY_NEIGHBOR_GROUPING && nparams < 2)
+        return set_error(GNNAGG_ERR_ARG, "locality_neighbor_grouping needs {par_num, neighbor_num}");
+    // host mirror of the CSR
+    const int *hp = a->h_ptr_user, *hi = a->h_idx_user;
+    if (!hp) {
+        if (a->h_ptr.empty()) {
+            a->h_ptr.resize((size_t)a->n + 1);
+            CUDA_TRY(cudaMemcpy(a->h_ptr.data(), a->d_ptr, a->h_ptr.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        }
+        hp = a->h_ptr.data();
+    }
+    if (!hi) {
+        if (a->h_idx.empty() && a->m > 0) {
+            a->h_idx.resize((size_t)a->m);
+            CUDA_TRY(cudaMemcpy(a->h_idx.data(), a->d_idx, a->h_idx.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        }
+        hi = a->h_idx.data();
+    }
+    int par = 0, ng = 0;
+    if (kind == GNNAGG_SCHED_NEIGHBOR_GROUPING)
+        ng = params[0];
+    else if (kind == GNNAGG_SCHED_LOCALITY)
+        par = params[0];
+    else if (kind == GNNAGG_SCHED_LOCALITY_NEIGHBOR_GROUPING)
+        par = params[0], ng = params[1];
+    else
+        return set_error(GNNAGG_ERR_ARG, "gnnagg_schedule_apply: unknown kind");
+
+    gnnagg_schedule s;
+    const bool permuting = (kind != GNNAGG_SCHED_NEIGHBOR_GROUPING);
+    s.want_perm = permuting;  // edge values are permuted on the device from this (aggr_gcn.h:522-537)
+    if (int rc = schedule_build(kind, hp, hi, nullptr, a->n, a->m, par, ng, total_num_v, &s)) return rc;
+
+    free_schedule(a);
+    a->sched_kind = kind;
+    a->neighbor_group_size = ng;
+    a->locality_partition_num = par;
+    a->num_target = (int)s.target.size();
+    a->sched_edges = (int)s.idx.size();
+    auto upload = [&](int **dst, const void *src, size_t count) -> int {
+        CUDA_TRY(cudaMalloc((void **)dst, (count ? count : 1) * sizeof(int)));
+        if (count) CUDA_TRY(cudaMemcpy(*dst, src, count * sizeof(int), cudaMemcpyHostToDevice));
+        return GNNAGG_OK;
+    };
+    if (int rc = upload(&a->s_ptr, s.ptr.data(), s.ptr.size())) return rc;
+    if (int rc = upload(&a->s_idx, s.idx.data(), s.idx.size())) return rc;
+    if (int rc = upload(&a->s_target, s.target.data(), s.target.size())) return rc;
+    if (permuting)
+        if (int rc = upload(&a->s_perm, s.perm.data(), s.perm.size())) return rc;
+    if (int rc = build_item_rows(a, a->s_ptr, a->num_target, a->sched_edges, &a->s_item_row, &a->sched_items, 0))
+        return rc;
+    if (int rc = gnnagg_set_val(a, a->d_val)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(0));
+    return GNNAGG_OK;
+}
+
+int gnnagg_num_target(const gnnagg_aggregator *a) { return a ? a->num_target : 0; }
+const int *gnnagg_sched_dev_ptr(const gnnagg_aggregator *a) { return a ? a->s_ptr : nullptr; }
+const int *gnnagg_sched_dev_idx(const gnnagg_aggregator *a) { return a ? a->s_idx : nullptr; }
+const int *gnnagg_sched_dev_target(const gnnagg_aggregator *a) { return a ? a->s_target : nullptr; }
+const float *gnnagg_sched_dev_val(const gnnagg_aggregator *a) { return a ? a->s_val : nullptr; }
+const float *gnnagg_gat_edge_weights(const gnnagg_aggregator *a) { return a ? a->newval : nullptr; }
+int64_t gnnagg_launch_count(const gnnagg_aggregator *a) { return a ? a->launches : 0; }
+
+int gnnagg_memcpy_d2h(void *h_dst, const void *d_src, uint64_t bytes)
+{
+    if (bytes == 0) return GNNAGG_OK;
+    if (!h_dst || !d_src) return set_error(GNNAGG_ERR_ARG, "gnnagg_memcpy_d2h: NULL argument");
+    CUDA_TRY(cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost));
+    return GNNAGG_OK;
+}
+
+int gnnagg_gcn_run(gnnagg_aggregator *a, const float *X, float *Y, int feat, int scheduled, void *stream)
+{
+    return gcn_run_impl(a, X, Y, feat, scheduled, (cudaStream_t)stream);
+}
+
+int gnnagg_gat_run(gnnagg_aggregator *a, const float *X, const float *att, float *Y, int feat, float slope,
+                   int scheduled, void *stream)
+{
+    return gat_run_impl(a, X, att, Y, feat, slope, scheduled, (cudaStream_t)stream);
+}
+
+int gnnagg_dense_nn(const float *A, const float *B, float *C, int64_t M, int N, int K, void *stream)
+{
+    if (!A || !B || !C || M < 0) return set_error(GNNAGG_ERR_ARG, "gnnagg_dense_nn: bad argument");
+    if (M == 0) return GNNAGG_OK;
+    return dense_nn_launch(A, B, C, M, N, K, stream);
+}
+
+int gnnagg_gcn_layer(gnnagg_aggregator *a, const float *X, const float *W, float *H, float *AX, int feat_in,
+                     int feat_out, int scheduled, void *stream)
+{
+    if (!a || !X || !W || !H) return set_error(GNNAGG_ERR_ARG, "gnnagg_gcn_layer: NULL argument");
+    float *ax = AX;
+    if (!ax) {
+        if (int rc = ensure(a->ax, a->ax_cap, (size_t)a->n * feat_in)) return rc;
+        ax = a->ax;
+    }
+    if (int rc = gcn_run_impl(a, X, ax, feat_in, scheduled, (cudaStream_t)stream)) return rc;
+    if (a->n == 0) return GNNAGG_OK;
+    if (int rc = dense_nn_launch(ax, W, H, a->n, feat_out, feat_in, stream)) return rc;
+    ++a->launches;
+    return GNNAGG_OK;
+}
+
+int gnnagg_gcn_run_edgewise(gnnagg_aggregator *a, const float *X, float *Y, int feat, void *stream)
+{
+    if (!a || !X || !Y) return set_error(GNNAGG_ERR_ARG, "gnnagg_gcn_run_edgewise: NULL argument");
+    if (int rc = check_feat(feat)) return rc;
+    if (!a->d_val) return set_error(GNNAGG_ERR_STATE, "edge values not set");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(Y, 0, (size_t)a->n * feat * sizeof(float), st));  // aggr_gcn.h:447
+    if (a->m == 0) return GNNAGG_OK;
+    const EdgeParams g = edge_params(a);
+    const int lpr = lpr_for(feat);
+    const unsigned grid = (unsigned)cdiv(cdiv(a->m, 32 / lpr), 8);
+    if (lpr == 8)
+        gcn_edgewise_kernel<8><<<grid, 256, 0, st>>>(g, a->d_val, X, Y, feat);
+    else if (lpr == 16)
+        gcn_edgewise_kernel<16><<<grid, 256, 0, st>>>(g, a->d_val, X, Y, feat);
+    else
+        gcn_edgewise_kernel<32><<<grid, 256, 0, st>>>(g, a->d_val, X, Y, feat);
+    LAUNCH_CHECK(a);
+    return GNNAGG_OK;
+}
+
+int gnnagg_csr2edgelist(gnnagg_aggregator *a, int *d_edgelist, void *stream)
+{
+    if (!a || (!d_edgelist && a->m > 0)) return set_error(GNNAGG_ERR_ARG, "gnnagg_csr2edgelist: NULL argument");
+    if (a->m == 0) return GNNAGG_OK;
+    csr2edgelist_kernel<<<(unsigned)cdiv(a->m, 256), 256, 0, (cudaStream_t)stream>>>(edge_params(a), d_edgelist);
+    LAUNCH_CHECK(a);
+    return GNNAGG_OK;
+}
+
+int gnnagg_u_add_v(gnnagg_aggregator *a, const float *att, float *out_val, void *stream)
+{
+    if (!a || !att || (!out_val && a->m > 0)) return set_error(GNNAGG_ERR_ARG, "gnnagg_u_add_v: NULL argument");
+    if (a->m == 0) return GNNAGG_OK;
+    edge_map_kernel<kEdgeUAddV><<<(unsigned)cdiv(a->m, 256), 256, 0, (cudaStream_t)stream>>>(edge_params(a), att, out_val, 0.f);
+    LAUNCH_CHECK(a);
+    return GNNAGG_OK;
+}
+
+int gnnagg_add_to_center(gnnagg_aggregator *a, const float *in_val, float *out_center, void *stream)
+{
+    if (!a || !out_center || (!in_val && a->m > 0)) return set_error(GNNAGG_ERR_ARG, "gnnagg_add_to_center: NULL argument");
+    return rowsum_impl(a, in_val, out_center, (cudaStream_t)stream);
+}
+
+int gnnagg_each_div(gnnagg_aggregator *a, const float *in_center, float *inout_val, void *stream)
+{
+    if (!a || !in_center || (!inout_val && a->m > 0)) return set_error(GNNAGG_ERR_ARG, "gnnagg_each_div: NULL argument");
+    if (a->m == 0) return GNNAGG_OK;
+    edge_map_kernel<kEdgeDiv><<<(unsigned)cdiv(a->m, 256), 256, 0, (cudaStream_t)stream>>>(edge_params(a), in_center, inout_val, 0.f);
+    LAUNCH_CHECK(a);
+    return GNNAGG_OK;
+}
+
+int gnnagg_edge_softmax(gnnagg_aggregator *a, const float *att, float *out_val, float slope, void *stream)
+{
+    if (!a || !att || (!out_val && a->m > 0)) return set_error(GNNAGG_ERR_ARG, "gnnagg_edge_softmax: NULL argument");
+    if (a->m == 0) return GNNAGG_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = ensure(a->den_row, a->den_row_cap, (size_t)a->n)) return rc;
+    const EdgeParams g = edge_params(a);
+    edge_map_kernel<kEdgeWeight><<<(unsigned)cdiv(a->m, 256), 256, 0, st>>>(g, att, out_val, slope);
+    LAUNCH_CHECK(a);
+    if (int rc = rowsum_impl(a, out_val, a->den_row, st)) return rc;
+    edge_map_kernel<kEdgeDiv><<<(unsigned)cdiv(a->m, 256), 256, 0, st>>>(g, a->den_row, out_val, 0.f);
+    LAUNCH_CHECK(a);
+    return GNNAGG_OK;
+}
+
+int gnnagg_sddmm(gnnagg_aggregator *a, const float *X1, const float *X2, float *out_val, int feat, int scheduled,
+                 void *stream)
+{
+    if (!a || !X1 || !X2 || (!out_val && a->m > 0)) return set_error(GNNAGG_ERR_ARG, "gnnagg_sddmm: NULL argument");
+    if (int rc = check_feat(feat)) return rc;
+    if (!aligned16(X1) || !aligned16(X2)) return set_error(GNNAGG_ERR_ARG, "X1 and X2 must be 16-byte aligned");
+    EdgeParams g = edge_params(a);
+    const int *target = nullptr;
+    if (scheduled) {
+        if (a->sched_kind != GNNAGG_SCHED_NEIGHBOR_GROUPING)  // aggr_sddmm.h:100
+            return set_error(GNNAGG_ERR_STATE, "scheduled SDDMM needs a neighbor_grouping schedule");
+        g = edge_params_sched(a);
+        target = a->s_target;
+    }
+    if (g.num_edges == 0) return GNNAGG_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int lpr = lpr_for(feat);
+    const unsigned grid = (unsigned)cdiv(cdiv(g.num_items, 32 / lpr), 8);
+    if (lpr == 8)
+        sddmm_kernel<8><<<grid, 256, 0, st>>>(g, target, X1, X2, out_val, feat);
+    else if (lpr == 16)
+        sddmm_kernel<16><<<grid, 256, 0, st>>>(g, target, X1, X2, out_val, feat);
+    else
+        sddmm_kernel<32><<<grid, 256, 0, st>>>(g, target, X1, X2, out_val, feat);
+    LAUNCH_CHECK(a);
+    return GNNAGG_OK;
+}
+
+int gnnagg_spmm_naive(int num_v, const int *d_ptr, const int *d_idx, const float *d_val, const float *X, float *Y,
+                      int feat, void *stream)
+{
+    if (!d_ptr || !X || !Y) return set_error(GNNAGG_ERR_ARG, "gnnagg_spmm_naive: NULL argument");
+    if (int rc = check_feat(feat)) return rc;
+    if (num_v == 0) return GNNAGG_OK;
+    spmm_naive_kernel<<<(unsigned)cdiv(num_v, 128), 128, 0, (cudaStream_t)stream>>>(num_v, d_ptr, d_idx, d_val, X, Y, feat);
+    CUDA_TRY(cudaPeekAtLastError());
+    return GNNAGG_OK;
+}
+
+static int count_diff(int *diffnum, cudaStream_t st, int *d_cnt)
+{
+    CUDA_TRY(cudaPeekAtLastError());
+    CUDA_TRY(cudaMemcpyAsync(diffnum, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaFree(d_cnt));
+    return GNNAGG_OK;
+}
+
+int gnnagg_validate(const float *d_ref, const float *d_ans, int64_t num, int *diffnum, void *stream)
+{
+    if (!d_ref || !d_ans || !diffnum) return set_error(GNNAGG_ERR_ARG, "gnnagg_validate: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    int *d_cnt = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&d_cnt, sizeof(int)));
+    CUDA_TRY(cudaMemsetAsync(d_cnt, 0, sizeof(int), st));
+    if (num > 0) validate_kernel<<<(unsigned)cdiv(num, 128), 128, 0, st>>>(d_ref, d_ans, num, d_cnt);
+    return count_diff(diffnum, st, d_cnt);
+}
+
+int gnnagg_validate_reordered(const float *d_ref, const float *d_ans, const int *d_map, int num_v, int feat,
+                              int *diffnum, void *stream)
+{
+    if (!d_ref || !d_ans || !diffnum) return set_error(GNNAGG_ERR_ARG, "gnnagg_validate_reordered: NULL argument");
+    if (!d_map) return gnnagg_validate(d_ref, d_ans, (int64_t)num_v * feat, diffnum, stream);  // spmm.h:73-74
+    cudaStream_t st = (cudaStream_t)stream;
+    int *d_cnt = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&d_cnt, sizeof(int)));
+    CUDA_TRY(cudaMemsetAsync(d_cnt, 0, sizeof(int), st));
+    const int64_t num = (int64_t)num_v * feat;
+    if (num > 0) validate_reordered_kernel<<<(unsigned)cdiv(num, 128), 128, 0, st>>>(d_ref, d_ans, d_map, num_v, feat, d_cnt);
+    return count_diff(diffnum, st, d_cnt);
+}
+
+// ------------------------------------------------------------------ host-buffer entry points
+int gnnagg_gcn_run_host(gnnagg_aggregator *a, const float *h_X, float *h_Y, int feat, int scheduled, void *stream)
+{
+    if (!a || !h_X || !h_Y) return set_error(GNNAGG_ERR_ARG, "gnnagg_gcn_run_host: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t cnt = (size_t)a->n * feat;
+    if (int rc = ensure(a->st_in, a->st_in_cap, cnt)) return rc;
+    if (int rc = ensure(a->st_out, a->st_out_cap, cnt)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(a->st_in, h_X, cnt * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (int rc = gcn_run_impl(a, a->st_in, a->st_out, feat, scheduled, st)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h_Y, a->st_out, cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return GNNAGG_OK;
+}
+
+int gnnagg_gcn_layer_host(gnnagg_aggregator *a, const float *h_X, const float *h_W, float *h_H, int feat_in,
+                          int feat_out, int scheduled, void *stream)
+{
+    if (!a || !h_X || !h_W || !h_H) return set_error(GNNAGG_ERR_ARG, "gnnagg_gcn_layer_host: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t cin = (size_t)a->n * feat_in, cout = (size_t)a->n * feat_out, cw = (size_t)feat_in * feat_out;
+    if (int rc = ensure(a->st_in, a->st_in_cap, cin)) return rc;
+    if (int rc = ensure(a->st_out, a->st_out_cap, cout)) return rc;
+    if (int rc = ensure(a->st_w, a->st_w_cap, cw)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(a->st_in, h_X, cin * sizeof(float), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(a->st_w, h_W, cw * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (int rc = gnnagg_gcn_layer(a, a->st_in, a->st_w, a->st_out, nullptr, feat_in, feat_out, scheduled, stream)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h_H, a->st_out, cout * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return GNNAGG_OK;
+}
+
+int gnnagg_gat_run_host(gnnagg_aggregator *a, const float *h_X, const float *h_att, float *h_Y, int feat,
+                        float slope, int scheduled, void *stream)
+{
+    if (!a || !h_X || !h_att || !h_Y) return set_error(GNNAGG_ERR_ARG, "gnnagg_gat_run_host: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t cnt = (size_t)a->n * feat;
+    if (int rc = ensure(a->st_in, a->st_in_cap, cnt)) return rc;
+    if (int rc = ensure(a->st_out, a->st_out_cap, cnt)) return rc;
+    if (int rc = ensure(a->st_att, a->st_att_cap, (size_t)a->n * 2)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(a->st_in, h_X, cnt * sizeof(float), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(a->st_att, h_att, (size_t)a->n * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (int rc = gat_run_impl(a, a->st_in, a->st_att, a->st_out, feat, slope, scheduled, st)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h_Y, a->st_out, cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return GNNAGG_OK;
+}
+}

@@ -1,0 +1,232 @@
+// edge_kernels.cuh -- edge-parallel kernels: un-fused GAT pieces, SDDMM, edge-wise GCN,
+// CSR->edge list, the naive SpMM and the validators of include/spmm.h.
+//
+// The reference runs all of these warp-per-row (aggr_gat.h:5-92, aggr_sddmm.h:5-83,
+// aggregator.h:11-23), which serialises hub rows on one warp.  Here every kernel is parallel
+// over EDGES: the row of an edge is recovered with a short binary search bounded by the
+// precomputed item_row table (common.cuh: row_of_edge), so work is balanced whatever the degree
+// distribution, and row sums use the same item/carry scheme as the aggregation kernels
+// (deterministic, no float atomics).
+#pragma once
+#include "common.cuh"
+
+namespace gnnagg {
+
+struct EdgeParams {
+    const int *__restrict__ ptr;
+    const int *__restrict__ idx;
+    const int *__restrict__ item_row;
+    int num_rows;
+    int num_edges;
+    int num_items;  // ceil(num_edges / kFineItem)
+};
+
+enum { kEdgeUAddV = 0, kEdgeWeight = 1, kEdgeDiv = 2 };
+
+// OP = kEdgeUAddV : out[e] = att[2v] + att[2u+1]                      (u_add_v, aggr_gat.h:45)
+// OP = kEdgeWeight: out[e] = exp(max(s, slope*s)), s as above          (attGat pass 1, aggr_gat.h:16-18)
+// OP = kEdgeDiv   : out[e] = out[e] / center[v]                        (each_div :89 / attGat pass 2 :28)
+template <int OP>
+__global__ void __launch_bounds__(256) edge_map_kernel(const EdgeParams g, const float *__restrict__ a,
+                                                       float *__restrict__ out, float slope)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= g.num_edges) return;
+    const int v = row_of_edge(g.ptr, g.item_row, g.num_items, g.num_rows, e);
+    if (OP == kEdgeDiv) {
+        out[e] = out[e] / __ldg(a + v);
+    } else {
+        const float s = __ldg(a + 2 * (size_t)v) + __ldg(a + 2 * (size_t)__ldg(g.idx + e) + 1);
+        out[e] = (OP == kEdgeUAddV) ? s : __expf(fmaxf(s, s * slope));
+    }
+}
+
+// out[v] = sum of in[e] over the edges of row v (add_to_center, aggr_gat.h:50-74; the row-sum
+// half of attGat, :19-25).  One thread walks one kFineItem-edge item; rows crossing item
+// boundaries leave a partial in carry[item] that rowsum_fixup_kernel adds in item order.
+__global__ void __launch_bounds__(256) rowsum_kernel(const EdgeParams g, const float *__restrict__ in,
+                                                     float *__restrict__ out, float *__restrict__ carry)
+{
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= g.num_items) return;
+    const int e0 = item * kFineItem;
+    const int e1 = min(g.num_edges, e0 + kFineItem);
+    int row = (item == 0) ? 0 : __ldg(g.item_row + item);
+    int row_end = __ldg(g.ptr + row + 1);
+    bool carry_in = __ldg(g.ptr + row) < e0;
+    float acc = 0.f;
+    auto flush = [&]() {
+        if (carry_in) {
+            carry[item] = acc;
+            carry_in = false;
+        } else {
+            out[row] = acc;
+        }
+        acc = 0.f;
+        ++row;
+        row_end = (row < g.num_rows) ? __ldg(g.ptr + row + 1) : INT_MAX;
+    };
+    int e = e0;
+    while (row_end == e) flush();
+    const bool vec = ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
+    while (e < e1) {
+        float v[4];
+        const int nb = min(4, e1 - e);
+        if (vec && nb == 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(in + e));
+            v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = (u < nb) ? __ldg(in + e + u) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (u < nb) {
+                while (row_end == e + u) flush();
+                acc += v[u];
+            }
+        }
+        e += nb;
+    }
+    if (row_end == e1) {
+        while (row < g.num_rows && row_end == e1) flush();
+    } else if (carry_in) {
+        carry[item] = acc;
+    } else {
+        out[row] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256) rowsum_fixup_kernel(const EdgeParams g, float *__restrict__ out,
+                                                           const float *__restrict__ carry)
+{
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item < 1 || item >= g.num_items) return;
+    const int e0 = item * kFineItem;
+    const int row = __ldg(g.item_row + item);
+    const int rs = __ldg(g.ptr + row);
+    if (rs >= e0 || item != rs / kFineItem + 1) return;
+    const int last = (__ldg(g.ptr + row + 1) - 1) / kFineItem;
+    float acc = out[row];
+    for (int b = item; b <= last; ++b) acc += carry[b];
+    out[row] = acc;
+}
+
+// SDDMM: out[e] = <X1[idx[e], 0:F], X2[row(e), 0:F]>   (aggr_sddmm.h:17-41; target variant :45-83)
+// A virtual warp of LPR lanes walks one item; float4 per lane per 4*LPR columns, xor-shuffle
+// reduction, 4 edges in flight.  `target` (nullable) maps a group to its row (scheduled mode).
+template <int LPR>
+__global__ void __launch_bounds__(256) sddmm_kernel(const EdgeParams g, const int *__restrict__ target,
+                                                    const float *__restrict__ X1, const float *__restrict__ X2,
+                                                    float *__restrict__ out, int F)
+{
+    constexpr int VPW = 32 / LPR;
+    constexpr int U = 4;
+    const int lane = threadIdx.x & 31;
+    const int vw = lane / LPR, vl = lane % LPR;
+    const int64_t item = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * VPW + vw;
+    // every lane of the warp runs the same number of batches (shuffles below use the full mask)
+    const int64_t e0_64 = item * kFineItem;
+    const bool live = e0_64 < g.num_edges;
+    const int e0 = live ? (int)e0_64 : 0;
+    const int e1 = live ? min(g.num_edges, e0 + kFineItem) : 0;
+    int row = 0, row_end = 0;
+    if (live) {
+        row = (e0 == 0) ? 0 : __ldg(g.item_row + item);
+        row_end = __ldg(g.ptr + row + 1);
+    }
+    for (int e = e0; e < e0 + kFineItem; e += U) {
+        float d[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            d[u] = 0.f;
+            const int ee = e + u;
+            if (ee < e1) {
+                while (row_end <= ee) {
+                    ++row;
+                    row_end = __ldg(g.ptr + row + 1);
+                }
+                const int dst = target ? __ldg(target + row) : row;
+                const float *a = X1 + (size_t)__ldg(g.idx + ee) * F;
+                const float *b = X2 + (size_t)dst * F;
+                for (int col = vl * 4; col < F; col += LPR * 4) {
+                    const float4 x = ldg_f4(a + col), y = ldg_f4(b + col);
+                    d[u] = fmaf(x.x, y.x, fmaf(x.y, y.y, fmaf(x.z, y.z, fmaf(x.w, y.w, d[u]))));
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int k = LPR / 2; k > 0; k >>= 1) d[u] += __shfl_xor_sync(0xffffffffu, d[u], k);
+        if (vl < U && e + vl < e1) {
+            const float r = (vl == 0) ? d[0] : (vl == 1) ? d[1] : (vl == 2) ? d[2] : d[3];
+            out[e + vl] = r;
+        }
+    }
+}
+
+// edge-wise GCN aggregation: Y[dst] += X[src]*val[e], one virtual warp per edge and 128-bit
+// reductions (aggr_gcn_edgewise, aggr_gcn.h:291-302: warp per edge, F=32 only, scalar atomics)
+template <int LPR>
+__global__ void __launch_bounds__(256) gcn_edgewise_kernel(const EdgeParams g, const float *__restrict__ val,
+                                                           const float *__restrict__ X, float *__restrict__ Y, int F)
+{
+    constexpr int VPW = 32 / LPR;
+    const int lane = threadIdx.x & 31;
+    const int64_t e64 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * VPW + lane / LPR;
+    if (e64 >= g.num_edges) return;
+    const int e = (int)e64;
+    const int dst = row_of_edge(g.ptr, g.item_row, g.num_items, g.num_rows, e);
+    const int src = __ldg(g.idx + e);
+    const float w = __ldg(val + e);
+    for (int col = (lane % LPR) * 4; col < F; col += LPR * 4) {
+        const float4 x = ldg_f4(X + (size_t)src * F + col);
+        red_add_f4(Y + (size_t)dst * F + col, make_float4(x.x * w, x.y * w, x.z * w, x.w * w));
+    }
+}
+
+// (src, dst) pairs, edgelist[2e] = idx[e], edgelist[2e+1] = row(e)   (aggregator.h:11-23)
+__global__ void __launch_bounds__(256) csr2edgelist_kernel(const EdgeParams g, int *__restrict__ edgelist)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= g.num_edges) return;
+    const int v = row_of_edge(g.ptr, g.item_row, g.num_items, g.num_rows, e);
+    reinterpret_cast<int2 *>(edgelist)[e] = make_int2(__ldg(g.idx + e), v);
+}
+
+// thread-per-row SpMM of include/spmm.h:223-265 (kept for API completeness; rows without edges
+// are left untouched exactly as there, :236-237)
+__global__ void __launch_bounds__(128) spmm_naive_kernel(int num_v, const int *__restrict__ ptr,
+                                                         const int *__restrict__ idx, const float *__restrict__ val,
+                                                         const float *__restrict__ X, float *__restrict__ Y, int F)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= num_v) return;
+    const int begin = ptr[r], end = ptr[r + 1];
+    if (begin == end) return;
+    for (int c = 0; c < F; c += 4) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int e = begin; e < end; ++e) fma4(acc, __ldg(val + e), ldg_f4(X + (size_t)__ldg(idx + e) * F + c));
+        stg_f4(Y + (size_t)r * F + c, acc);
+    }
+}
+
+// mismatch counters (spmm.h:11-33)
+__global__ void __launch_bounds__(128) validate_kernel(const float *__restrict__ ref, const float *__restrict__ ans,
+                                                       int64_t num, int *diffnum)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < num && fabsf((ref[t] - ans[t]) / ref[t]) > 1e-2f) atomicAdd(diffnum, 1);
+}
+
+__global__ void __launch_bounds__(128) validate_reordered_kernel(const float *__restrict__ ref,
+                                                                 const float *__restrict__ ans,
+                                                                 const int *__restrict__ map, int num_v, int F,
+                                                                 int *diffnum)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < (int64_t)num_v * F && fabsf(ref[t] - ans[(size_t)map[t / F] * F + t % F]) > 1e-2f) atomicAdd(diffnum, 1);
+}
+
+}  // namespace gnnagg

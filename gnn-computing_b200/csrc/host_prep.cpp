@@ -1,0 +1,352 @@
+// host_prep.cpp -- host-side preprocessing behind the C ABI: the three load-balance / locality
+// schedules, reorder application and the .config/.graph/.ptrdump/.edgedump/.reorder file formats.
+//
+// Outputs are bit-exact with the reference (include/graph_schedule.h, src/data.cu); the
+// algorithms are not the reference's: every schedule is built by a count pass, a prefix sum and
+// a fill pass into exactly-sized arrays (no push_back growth), and the locality schedules make
+// ONE pass over the edges instead of the reference's par_num passes (graph_schedule.h:24-63
+// rescans all m edges per slice).
+#include <sys/stat.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "gnnagg.h"
+#include "internal.h"
+
+namespace gnnagg {
+
+// slice of a source id for the locality schedules: slice p covers [p*w, (p+1)*w) with
+// w = floor(total/par), the last slice runs to `total` (graph_schedule.h:26-29); ids outside
+// [0,total) belong to no slice and are dropped, as in the reference's range test (:37).
+static inline int slice_of(int src, int w, int par_num, int total)
+{
+    if (src < 0 || src >= total) return -1;
+    if (w == 0) return par_num - 1;  // every slice but the last is empty
+    const int p = src / w;
+    return p < par_num ? p : par_num - 1;
+}
+
+static int build_neighbor_grouping(const int *ptr, const int *idx, int num_v, int num_e, int ng, gnnagg_schedule *s)
+{
+    // groups of row i: ceil(deg/ng)   (graph_schedule.h:100-120)
+    int64_t total = 0;
+    for (int i = 0; i < num_v; ++i) total += ((int64_t)ptr[i + 1] - ptr[i] + ng - 1) / ng;
+    s->ptr.resize((size_t)total + 1);
+    s->target.resize((size_t)total);
+    s->idx.assign(idx, idx + num_e);  // verbatim copy (:123-124)
+    int64_t g = 0;
+    s->ptr[0] = 0;
+    for (int i = 0; i < num_v; ++i) {
+        const int end = ptr[i + 1];
+        for (int b = ptr[i]; b < end; b += ng) {
+            s->ptr[g + 1] = (b + ng < end) ? b + ng : end;
+            s->target[g] = i;
+            ++g;
+        }
+    }
+    return GNNAGG_OK;
+}
+
+static int build_locality(const int *ptr, const int *idx, const float *val, int num_v, int par_num, int ng,
+                          int total_num_v, gnnagg_schedule *s)
+{
+    const int w = total_num_v / par_num;
+    // pass 1: edges and groups per slice
+    std::vector<int64_t> slice_edges(par_num, 0), slice_groups(par_num, 0);
+    std::vector<int> cnt(par_num);
+    for (int i = 0; i < num_v; ++i) {
+        std::fill(cnt.begin(), cnt.end(), 0);
+        for (int j = ptr[i]; j < ptr[i + 1]; ++j) {
+            const int p = slice_of(idx[j], w, par_num, total_num_v);
+            if (p >= 0) ++cnt[p];
+        }
+        for (int p = 0; p < par_num; ++p) {
+            slice_edges[p] += cnt[p];
+            // one group per (slice,row) with a hit (:54-57); with neighbour grouping a group closes
+            // every ng hits and the remainder is flushed (:182-190, :202-209)
+            slice_groups[p] += (ng > 0) ? (cnt[p] + ng - 1) / ng : (cnt[p] > 0);
+        }
+    }
+    std::vector<int64_t> edge_cur(par_num), group_cur(par_num);
+    int64_t te = 0, tg = 0;
+    for (int p = 0; p < par_num; ++p) {
+        edge_cur[p] = te;
+        group_cur[p] = tg;
+        te += slice_edges[p];
+        tg += slice_groups[p];
+    }
+    s->ptr.resize((size_t)tg + 1);
+    s->target.resize((size_t)tg);
+    s->idx.resize((size_t)te);
+    if (val) s->val.resize((size_t)te);
+    if (s->want_perm) s->perm.resize((size_t)te);
+    s->has_val = val != nullptr;
+    s->ptr[0] = 0;
+    // pass 2: scatter edges to their slice (stable), then close this row's groups in every slice
+    std::vector<int64_t> row_begin(par_num);
+    for (int i = 0; i < num_v; ++i) {
+        for (int p = 0; p < par_num; ++p) row_begin[p] = edge_cur[p];
+        for (int j = ptr[i]; j < ptr[i + 1]; ++j) {
+            const int p = slice_of(idx[j], w, par_num, total_num_v);
+            if (p < 0) continue;
+            s->idx[edge_cur[p]] = idx[j];
+            if (val) s->val[edge_cur[p]] = val[j];
+            if (s->want_perm) s->perm[edge_cur[p]] = j;
+            ++edge_cur[p];
+        }
+        for (int p = 0; p < par_num; ++p) {
+            const int64_t b = row_begin[p], e = edge_cur[p];
+            if (b == e) continue;
+            const int64_t step = (ng > 0) ? ng : (e - b);
+            for (int64_t q = b; q < e; q += step) {
+                const int64_t g = group_cur[p]++;
+                s->ptr[g + 1] = (int)((q + step < e) ? q + step : e);
+                s->target[g] = i;
+            }
+        }
+    }
+    return GNNAGG_OK;
+}
+
+int schedule_build(int kind, const int *ptr, const int *idx, const float *val, int num_v, int num_e, int par_num,
+                   int neighbor_num, int total_num_v, gnnagg_schedule *s)
+{
+    s->kind = kind;
+    s->has_val = false;
+    switch (kind) {
+        case GNNAGG_SCHED_NEIGHBOR_GROUPING:
+            if (neighbor_num <= 0) return set_error(GNNAGG_ERR_ARG, "neighbor_num must be > 0");
+            return build_neighbor_grouping(ptr, idx, num_v, num_e, neighbor_num, s);
+        case GNNAGG_SCHED_LOCALITY:
+            if (par_num <= 0) return set_error(GNNAGG_ERR_ARG, "par_num must be > 0");
+            return build_locality(ptr, idx, val, num_v, par_num, 0, total_num_v, s);
+        case GNNAGG_SCHED_LOCALITY_NEIGHBOR_GROUPING:
+            if (par_num <= 0 || neighbor_num <= 0) return set_error(GNNAGG_ERR_ARG, "par_num, neighbor_num must be > 0");
+            return build_locality(ptr, idx, val, num_v, par_num, neighbor_num, total_num_v, s);
+        default:
+            return set_error(GNNAGG_ERR_ARG, "unknown schedule kind");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// file formats
+// ---------------------------------------------------------------------------------------------
+static bool fexists(const std::string &p)
+{
+    struct stat st;
+    return stat(p.c_str(), &st) == 0;
+}
+
+static bool slurp(const std::string &path, std::vector<char> &buf)
+{
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    const long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    buf.resize((size_t)sz + 1);
+    const size_t got = fread(buf.data(), 1, (size_t)sz, f);
+    fclose(f);
+    buf[got] = 0;
+    buf.resize(got + 1);
+    return true;
+}
+
+// next whitespace-separated integer of a text buffer (what fscanf("%d") accepts)
+static bool next_int(const char *&p, const char *end, int &out)
+{
+    while (p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) ++p;
+    if (p >= end) return false;
+    bool neg = false;
+    if (*p == '-' || *p == '+') neg = (*p++ == '-');
+    if (p >= end || *p < '0' || *p > '9') return false;
+    long long v = 0;
+    while (p < end && *p >= '0' && *p <= '9') v = v * 10 + (*p++ - '0');
+    out = (int)(neg ? -v : v);
+    return true;
+}
+
+static bool read_raw(const std::string &path, int *dst, size_t count)
+{
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    const size_t got = fread(dst, sizeof(int), count, f);
+    fclose(f);
+    return got == count;
+}
+
+static bool write_raw(const std::string &path, const int *src, size_t count)
+{
+    FILE *f = fopen(path.c_str(), "wb");
+    if (!f) return false;
+    const size_t put = fwrite(src, sizeof(int), count, f);
+    fclose(f);
+    return put == count;
+}
+
+}  // namespace gnnagg
+
+using namespace gnnagg;
+
+extern "C" {
+
+int gnnagg_schedule_build(int kind, const int *ptr, const int *idx, const float *val, int num_v, int num_e,
+                          int par_num, int neighbor_num, int total_num_v, gnnagg_schedule **out)
+{
+    if (!ptr || (!idx && num_e > 0) || !out || num_v < 0 || num_e < 0)
+        return set_error(GNNAGG_ERR_ARG, "gnnagg_schedule_build: bad argument");
+    gnnagg_schedule *s = new gnnagg_schedule();
+    const int rc = schedule_build(kind, ptr, idx, val, num_v, num_e, par_num, neighbor_num, total_num_v, s);
+    if (rc != GNNAGG_OK) {
+        delete s;
+        return rc;
+    }
+    *out = s;
+    return GNNAGG_OK;
+}
+int64_t gnnagg_schedule_num_target(const gnnagg_schedule *s) { return s ? (int64_t)s->target.size() : 0; }
+int64_t gnnagg_schedule_num_edges(const gnnagg_schedule *s) { return s ? (int64_t)s->idx.size() : 0; }
+const int *gnnagg_schedule_ptr(const gnnagg_schedule *s) { return s ? s->ptr.data() : nullptr; }
+const int *gnnagg_schedule_idx(const gnnagg_schedule *s) { return s ? s->idx.data() : nullptr; }
+const int *gnnagg_schedule_target(const gnnagg_schedule *s) { return s ? s->target.data() : nullptr; }
+const float *gnnagg_schedule_val(const gnnagg_schedule *s) { return (s && s->has_val) ? s->val.data() : nullptr; }
+void gnnagg_schedule_free(gnnagg_schedule *s) { delete s; }
+
+int gnnagg_reorder_csr(const int *ptr, const int *idx, const int *map, const int *reverse_map, int num_v, int num_e,
+                       int *newptr, int *newidx)
+{
+    if (!ptr || !map || !reverse_map || !newptr || (num_e > 0 && (!idx || !newidx)))
+        return set_error(GNNAGG_ERR_ARG, "gnnagg_reorder_csr: bad argument");
+    // new row i is old row map[i]; its neighbours keep their old order and are relabelled through
+    // reverse_map (src/data.cu:15-27).  Row lengths first, then an offset scan, then the copy.
+    newptr[0] = 0;
+    for (int i = 0; i < num_v; ++i) newptr[i + 1] = newptr[i] + (ptr[map[i] + 1] - ptr[map[i]]);
+    if (newptr[num_v] != num_e) return set_error(GNNAGG_ERR_ARG, "gnnagg_reorder_csr: map is not a permutation");
+    for (int i = 0; i < num_v; ++i) {
+        const int *src = idx + ptr[map[i]];
+        int *dst = newidx + newptr[i];
+        const int len = newptr[i + 1] - newptr[i];
+        for (int j = 0; j < len; ++j) dst[j] = reverse_map[src[j]];
+    }
+    return GNNAGG_OK;
+}
+
+int gnnagg_graph_config(const char *datadir, const char *dset, int *num_v, int *num_e)
+{
+    if (!datadir || !dset || !num_v || !num_e) return set_error(GNNAGG_ERR_ARG, "gnnagg_graph_config: bad argument");
+    std::vector<char> buf;
+    const std::string path = std::string(datadir) + dset + ".config";
+    if (!slurp(path, buf)) return set_error(GNNAGG_ERR_IO, ("cannot open " + path).c_str());
+    const char *p = buf.data(), *end = buf.data() + buf.size() - 1;
+    if (!next_int(p, end, *num_v) || !next_int(p, end, *num_e))
+        return set_error(GNNAGG_ERR_IO, ("malformed " + path).c_str());
+    return GNNAGG_OK;
+}
+
+int gnnagg_graph_load(const char *datadir, const char *dset, const char *reorder_path, int num_v, int num_e,
+                      int *indptr, int *indices, int *rows, int *reverse_rows, int *reordered)
+{
+    if (!datadir || !dset || !indptr || (num_e > 0 && !indices))
+        return set_error(GNNAGG_ERR_ARG, "gnnagg_graph_load: bad argument");
+    if (reordered) *reordered = 0;
+    const std::string graph = std::string(datadir) + dset + ".graph";
+    const std::string ptrdump = graph + ".ptrdump", edgedump = graph + ".edgedump";
+    const bool have_ptr = fexists(ptrdump), have_edge = fexists(edgedump);
+    std::vector<char> text;
+    const char *p = nullptr, *end = nullptr;
+    if (!have_ptr || !have_edge) {
+        if (!slurp(graph, text)) return set_error(GNNAGG_ERR_IO, ("cannot open " + graph).c_str());
+        p = text.data();
+        end = text.data() + text.size() - 1;
+    }
+    // row pointers: cache if present, else the first num_v+1 tokens of the text (and write the cache)
+    if (have_ptr) {
+        if (!read_raw(ptrdump, indptr, (size_t)num_v + 1)) return set_error(GNNAGG_ERR_IO, ("short " + ptrdump).c_str());
+        if (p) {  // the text is only needed for the indices: skip its pointer line
+            int skip;
+            for (int i = 0; i <= num_v; ++i)
+                if (!next_int(p, end, skip)) return set_error(GNNAGG_ERR_IO, ("malformed " + graph).c_str());
+        }
+    } else {
+        for (int i = 0; i <= num_v; ++i)
+            if (!next_int(p, end, indptr[i])) return set_error(GNNAGG_ERR_IO, ("malformed " + graph).c_str());
+        if (!write_raw(ptrdump, indptr, (size_t)num_v + 1)) return set_error(GNNAGG_ERR_IO, ("cannot write " + ptrdump).c_str());
+    }
+    if (indptr[num_v] != num_e) return set_error(GNNAGG_ERR_IO, "indptr[num_v] != num_e (src/data.cu:69-74)");
+    if (have_edge) {
+        if (!read_raw(edgedump, indices, (size_t)num_e)) return set_error(GNNAGG_ERR_IO, ("short " + edgedump).c_str());
+    } else {
+        for (int i = 0; i < num_e; ++i)
+            if (!next_int(p, end, indices[i])) return set_error(GNNAGG_ERR_IO, ("malformed " + graph).c_str());
+        if (!write_raw(edgedump, indices, (size_t)num_e)) return set_error(GNNAGG_ERR_IO, ("cannot write " + edgedump).c_str());
+    }
+    // optional reorder (src/data.cu:96-133): entry k of the file = old id placed at new position k
+    if (reorder_path && reorder_path[0] && fexists(reorder_path)) {
+        if (!rows || !reverse_rows) return set_error(GNNAGG_ERR_ARG, "gnnagg_graph_load: rows/reverse_rows required");
+        std::vector<char> rb;
+        if (!slurp(reorder_path, rb)) return set_error(GNNAGG_ERR_IO, "cannot open reorder file");
+        const char *q = rb.data(), *qe = rb.data() + rb.size() - 1;
+        std::vector<char> seen((size_t)num_v, 0);
+        for (int i = 0; i < num_v; ++i) {
+            int r;
+            if (!next_int(q, qe, r) || r < 0 || r >= num_v || seen[r])
+                return set_error(GNNAGG_ERR_IO, "reorder file is not a permutation of 0..num_v-1");
+            seen[r] = 1;
+            rows[i] = r;
+            reverse_rows[r] = i;
+        }
+        std::vector<int> np((size_t)num_v + 1), ni((size_t)num_e);
+        const int rc = gnnagg_reorder_csr(indptr, indices, rows, reverse_rows, num_v, num_e, np.data(), ni.data());
+        if (rc != GNNAGG_OK) return rc;
+        memcpy(indptr, np.data(), np.size() * sizeof(int));
+        if (num_e) memcpy(indices, ni.data(), ni.size() * sizeof(int));
+        if (reordered) *reordered = 1;
+    }
+    return GNNAGG_OK;
+}
+
+static bool write_ints_line(FILE *f, const int *a, size_t count)
+{
+    std::string line;
+    line.reserve(count * 8 + 2);
+    char tmp[16];
+    for (size_t i = 0; i < count; ++i) {
+        const int len = snprintf(tmp, sizeof tmp, i ? " %d" : "%d", a[i]);
+        line.append(tmp, (size_t)len);
+    }
+    line.push_back('\n');
+    return fwrite(line.data(), 1, line.size(), f) == line.size();
+}
+
+int gnnagg_graph_write(const char *datadir, const char *dset, int num_v, int num_e, const int *indptr,
+                       const int *indices)
+{
+    if (!datadir || !dset || !indptr || (num_e > 0 && !indices))
+        return set_error(GNNAGG_ERR_ARG, "gnnagg_graph_write: bad argument");
+    const std::string base = std::string(datadir) + dset;
+    FILE *f = fopen((base + ".config").c_str(), "w");
+    if (!f) return set_error(GNNAGG_ERR_IO, ("cannot write " + base + ".config").c_str());
+    fprintf(f, "%d %d", num_v, num_e);
+    fclose(f);
+    f = fopen((base + ".graph").c_str(), "w");
+    if (!f) return set_error(GNNAGG_ERR_IO, ("cannot write " + base + ".graph").c_str());
+    const bool ok = write_ints_line(f, indptr, (size_t)num_v + 1) && write_ints_line(f, indices, (size_t)num_e);
+    fclose(f);
+    return ok ? GNNAGG_OK : set_error(GNNAGG_ERR_IO, "short write");
+}
+
+int gnnagg_reorder_write(const char *path, const int *rows, int num_v)
+{
+    if (!path || !rows) return set_error(GNNAGG_ERR_ARG, "gnnagg_reorder_write: bad argument");
+    FILE *f = fopen(path, "w");
+    if (!f) return set_error(GNNAGG_ERR_IO, "cannot write reorder file");
+    // every id followed by one space, no newline (script/cluster2.py:168-171)
+    for (int i = 0; i < num_v; ++i) fprintf(f, "%d ", rows[i]);
+    fclose(f);
+    return GNNAGG_OK;
+}
+}

@@ -1,0 +1,221 @@
+/*
+ * gnnagg.h -- C ABI of the B200-native neighbour-aggregation library (libgnnagg.so).
+ *
+ * Drop-in boundary for the aggregation hot path of xxcclong/GNN-Computing.  Every entry point
+ * names the reference interface it replaces (paths relative to the reference tree).  The
+ * existing flat boundary of the reference is Figure7/kernel_generated.cu:15-74
+ * (GCN_init_impl / GCN_run_impl / GCN_schedule_impl / GAT_*_impl: plain device pointers, ints
+ * and an int64 handle); this header keeps that shape and adds what the C++ aggregator classes
+ * (include/aggregator.h, aggr_gcn.h, aggr_gat.h, aggr_sddmm.h) expose beyond it.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  Return value: 0 = ok, <0 = error;
+ *     gnnagg_last_error() returns a thread-local message.  Nothing aborts the process (the
+ *     reference calls exit(1) + cudaDeviceReset(), include/util.h:82-104; the C++ shim headers
+ *     in include/ reproduce that on top of this ABI).
+ *   - CSR row = destination vertex, idx = source ids, int32 indices, fp32 values, dense
+ *     matrices row-major [rows, feat]; feat must be a multiple of 4 (the reference requires a
+ *     multiple of 32, aggr_gcn.h:386) and at most 1024.
+ *   - All `d_*`/device arguments are DEVICE pointers on the current device and are BORROWED:
+ *     the library frees only what it allocated (the reference aggregator cudaFree()s its
+ *     inputs, aggregator.h:58-66; the shim emulates that where a driver relies on it).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream, which is what
+ *     every reference launch uses).  Calls are asynchronous unless stated otherwise.
+ *   - There is no CPU fallback: device entry points fail with GNNAGG_ERR_CUDA when no GPU is
+ *     present.  Host entry points (schedules, reorder, loader) never touch the GPU.
+ */
+#ifndef GNNAGG_H
+#define GNNAGG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNNAGG_OK 0
+#define GNNAGG_ERR_ARG (-1)   /* bad argument (NULL, feat not supported, schedule missing ...) */
+#define GNNAGG_ERR_CUDA (-2)  /* a CUDA runtime call or launch failed */
+#define GNNAGG_ERR_IO (-3)    /* file missing / malformed */
+#define GNNAGG_ERR_STATE (-4) /* call order (e.g. scheduled run before schedule) */
+
+/* enum Schedule of include/graph_schedule.h:8-14, same numeric values */
+#define GNNAGG_SCHED_LOCALITY 0
+#define GNNAGG_SCHED_NEIGHBOR_GROUPING 1
+#define GNNAGG_SCHED_LOCALITY_NEIGHBOR_GROUPING 2
+#define GNNAGG_SCHED_NOP 3
+
+typedef struct gnnagg_aggregator gnnagg_aggregator; /* opaque; replaces `Aggregator*` cast to int64 */
+typedef struct gnnagg_schedule gnnagg_schedule;     /* opaque host-side schedule result */
+
+int gnnagg_version(void);
+const char *gnnagg_last_error(void);
+/* number of SMs / device name of the current device; GNNAGG_ERR_CUDA without a GPU */
+int gnnagg_device_info(int *sm_count, int *cc_major, int *cc_minor, char *name, int name_len);
+
+/* ------------------------------------------------------------------------------------------
+ * Host preprocessing -- bit-exact with the reference, no GPU involved
+ * ------------------------------------------------------------------------------------------ */
+
+/* Builds one of the three schedules on host arrays.
+ *   kind GNNAGG_SCHED_NEIGHBOR_GROUPING           replaces neighbor_grouping_schedule  (graph_schedule.h:91-154)
+ *   kind GNNAGG_SCHED_LOCALITY                    replaces locality_schedule            (graph_schedule.h:17-89)
+ *   kind GNNAGG_SCHED_LOCALITY_NEIGHBOR_GROUPING  replaces localityNeighborGrouping     (graph_schedule.h:156-243)
+ * val may be NULL (then no val vector is produced; neighbor grouping never produces one).
+ * total_num_v is the source-id range the locality slices divide (the reference passes the
+ * global `n`, aggregator.h:79,87). */
+int gnnagg_schedule_build(int kind, const int *ptr, const int *idx, const float *val, int num_v, int num_e,
+                          int par_num, int neighbor_num, int total_num_v, gnnagg_schedule **out);
+int64_t gnnagg_schedule_num_target(const gnnagg_schedule *s); /* == target_vec.size(), aggregator.h:94 */
+int64_t gnnagg_schedule_num_edges(const gnnagg_schedule *s);  /* == idx_vec.size() */
+const int *gnnagg_schedule_ptr(const gnnagg_schedule *s);     /* num_target+1 entries */
+const int *gnnagg_schedule_idx(const gnnagg_schedule *s);
+const int *gnnagg_schedule_target(const gnnagg_schedule *s);
+const float *gnnagg_schedule_val(const gnnagg_schedule *s);   /* NULL when no val vector */
+void gnnagg_schedule_free(gnnagg_schedule *s);
+
+/* replaces reorderCSR (src/data.cu:4-29): map[i] = old id placed at new position i,
+ * reverse_map[old] = new; newptr[num_v+1] and newidx[num_e] are caller-allocated. */
+int gnnagg_reorder_csr(const int *ptr, const int *idx, const int *map, const int *reverse_map, int num_v, int num_e,
+                       int *newptr, int *newidx);
+
+/* replaces load_graph (src/data.cu:31-139), split in the two steps a C caller needs:
+ *   gnnagg_graph_config : reads "<datadir><dset>.config"                       (:38-44)
+ *   gnnagg_graph_load   : fills indptr[num_v+1] / indices[num_e] from the .ptrdump/.edgedump
+ *                         caches or the text .graph (writing the caches)       (:46-93);
+ *                         if reorder_path is non-NULL/non-empty and exists the permutation is
+ *                         read into rows/reverse_rows (caller-allocated, num_v each) and
+ *                         applied (:96-133); *reordered tells whether that happened.
+ * datadir must end with '/' (the reference hard-codes "../data/", :34). */
+int gnnagg_graph_config(const char *datadir, const char *dset, int *num_v, int *num_e);
+int gnnagg_graph_load(const char *datadir, const char *dset, const char *reorder_path, int num_v, int num_e,
+                      int *indptr, int *indices, int *rows, int *reverse_rows, int *reordered);
+/* writes <datadir><dset>.config and .graph in the reference's text format (test/bench helper,
+ * the reference only reads these files: README.md:45-54) */
+int gnnagg_graph_write(const char *datadir, const char *dset, int num_v, int num_e, const int *indptr,
+                       const int *indices);
+
+/* locality-aware reordering: deterministic re-statement of script/cluster2.py (MinHash-LSH
+ * candidates -> exact Jaccard -> greedy size-capped union-find clustering).  Writes the
+ * permutation rows[num_v] (entry k = old id placed at new position k) -- the content of a
+ * <dset>.reorder<suffix> file.  num_perm/bands/rows_per_band/cap: cluster2.py uses 64 perms,
+ * threshold 0.2 (-> b=28,r=2 in datasketch) and cap 64; pass 0 for these defaults. */
+int gnnagg_lsh_reorder(const int *ptr, const int *idx, int num_v, int num_e, int num_perm, int bands,
+                       int rows_per_band, int cluster_cap, uint64_t seed, int *rows);
+int gnnagg_reorder_write(const char *path, const int *rows, int num_v); /* cluster2.py:168-171 format */
+
+/* ------------------------------------------------------------------------------------------
+ * Aggregator object -- replaces class Aggregator and its subclasses
+ * ------------------------------------------------------------------------------------------ */
+
+/* replaces Aggregator::Aggregator (aggregator.h:28-57) / GCN_init_impl, GAT_init_impl
+ * (kernel_generated.cu:15-19,41-45).  h_ptr/h_idx may be NULL: they are then mirrored from the
+ * device when a host schedule needs them (aggregator.h:30-39). */
+int gnnagg_create(const int *d_ptr, const int *d_idx, const int *h_ptr, const int *h_idx, int num_v, int num_e,
+                  gnnagg_aggregator **out);
+int gnnagg_destroy(gnnagg_aggregator *a);
+
+/* edge values of the GCN aggregator: ctor argument of Aggregator_GCN (aggr_gcn.h:365-374) and
+ * Aggregator_GCN::updateval (aggr_gcn.h:540-544) / GCN_update_val_impl.  Borrowed. */
+int gnnagg_set_val(gnnagg_aggregator *a, const float *d_val);
+
+/* replaces Aggregator::schedule / Aggregator_GCN::schedule (aggregator.h:67-99,
+ * aggr_gcn.h:501-538) / GCN_schedule_impl, GAT_schedule_impl.  params[0] = par_num or
+ * neighbor_num, params[1] = neighbor_num for the combined schedule.  Builds on the host with
+ * gnnagg_schedule_build and uploads; for the locality kinds the current val (if set) is
+ * permuted alongside as in aggr_gcn.h:522-537. */
+int gnnagg_schedule_apply(gnnagg_aggregator *a, int kind, const int *params, int nparams, int total_num_v);
+int gnnagg_num_target(const gnnagg_aggregator *a); /* public field Aggregator::num_target */
+/* device views of the uploaded schedule (d_ptr_scheduled, d_idx_scheduled, d_target_scheduled,
+ * d_val_scheduled of aggregator.h:132-134 / aggr_gcn.h:549); NULL before a schedule */
+const int *gnnagg_sched_dev_ptr(const gnnagg_aggregator *a);
+const int *gnnagg_sched_dev_idx(const gnnagg_aggregator *a);
+const int *gnnagg_sched_dev_target(const gnnagg_aggregator *a);
+const float *gnnagg_sched_dev_val(const gnnagg_aggregator *a);
+
+/* GCN aggregation Y = A*X.  replaces Aggregator_GCN::run / run_with_feat (aggr_gcn.h:379-444)
+ * / GCN_run_impl and the kernels aggr_gcn (:5-36) [scheduled=0] and aggr_gcn_target (:78-114)
+ * [scheduled=1].  Y is fully overwritten in both modes (the reference memsets, :393). */
+int gnnagg_gcn_run(gnnagg_aggregator *a, const float *X, float *Y, int feat, int scheduled, void *stream);
+
+/* edge-parallel variant: replaces Aggregator_GCN::runEdgeWise + aggr_gcn_edgewise
+ * (aggr_gcn.h:291-302,445-460) and Aggregator::csr2edgelist (aggregator.h:115-122).
+ * Any feat (the reference is F=32 only). */
+int gnnagg_gcn_run_edgewise(gnnagg_aggregator *a, const float *X, float *Y, int feat, void *stream);
+int gnnagg_csr2edgelist(gnnagg_aggregator *a, int *d_edgelist /* 2*num_e */, void *stream);
+
+/* fused aggregation + combination  AX = A*X ; H = AX*W,  W row-major [feat_in, feat_out].
+ * replaces Aggregator_GCN::run_with_nn + aggr_gcn_nn (aggr_gcn.h:304-359,491-499) and the
+ * un-fused aggr_gcn_target + matmul_NN baseline (dense.h:4-23, Figure10/main_b.cu:89-90).
+ * AX may be NULL (not materialised for the caller).  Outputs are overwritten (the reference
+ * accumulates into never-zeroed buffers).  feat_in, feat_out multiples of 32 <= 256.
+ * The combination runs on tcgen05 tensor cores in 3xTF32 (fp32-level accuracy). */
+int gnnagg_gcn_layer(gnnagg_aggregator *a, const float *X, const float *W, float *H, float *AX, int feat_in,
+                     int feat_out, int scheduled, void *stream);
+/* the dense combination alone: C[M,N] = A[M,K]*B[K,N] row-major; replaces matmul_NN (dense.h:4-23) */
+int gnnagg_dense_nn(const float *A, const float *B, float *C, int64_t M, int N, int K, void *stream);
+
+/* fused GAT aggregation  Y[v] = sum_u w X[u] / sum_u w,  w = exp(max(s, slope*s)),
+ * s = att[2v] + att[2u+1].  replaces Aggregator_GAT::run / run_with_feat (aggr_gat.h:317-394)
+ * / GAT_run_impl and the kernels aggr_gat (:116-164) [scheduled=0] and aggr_gat_fine +
+ * scaleArray (:167-213) [scheduled=1; additionally leaves the un-normalised w in the
+ * aggregator's edge buffer, gnnagg_gat_edge_weights()].  Empty rows yield 0 (reference: NaN /
+ * untouched, documented deviation).  slope: the reference hard-codes 0.2 (:339,347). */
+int gnnagg_gat_run(gnnagg_aggregator *a, const float *X, const float *att, float *Y, int feat, float slope,
+                   int scheduled, void *stream);
+const float *gnnagg_gat_edge_weights(const gnnagg_aggregator *a); /* d_newval of aggr_gat.h:306, scheduled order */
+
+/* un-fused GAT pieces on the un-scheduled CSR:
+ *   gnnagg_edge_softmax   replaces run_att + attGat                (aggr_gat.h:5-31,395-401)
+ *   gnnagg_u_add_v        replaces run_u_add_v + u_add_v           (aggr_gat.h:33-48,402-409)
+ *   gnnagg_add_to_center  replaces run_add_to_center               (aggr_gat.h:50-74,410-417; out[v], stride 1)
+ *   gnnagg_each_div       replaces run_div_each + each_div         (aggr_gat.h:76-92,418-425) */
+int gnnagg_edge_softmax(gnnagg_aggregator *a, const float *att, float *out_val, float slope, void *stream);
+int gnnagg_u_add_v(gnnagg_aggregator *a, const float *att, float *out_val, void *stream);
+int gnnagg_add_to_center(gnnagg_aggregator *a, const float *in_val, float *out_center, void *stream);
+int gnnagg_each_div(gnnagg_aggregator *a, const float *in_center, float *inout_val, void *stream);
+
+/* SDDMM  val[e] = <X1[idx[e],:], X2[row(e),:]>.  replaces Aggregator_SDDMM::run + aggr_sddmm /
+ * aggr_sddmm_target (aggr_sddmm.h:5-117); scheduled=1 requires a neighbor-grouping schedule
+ * (:100) and writes in scheduled edge order (identical to CSR order for that schedule).
+ * Any feat multiple of 4 (the reference is F=32 only, :21). */
+int gnnagg_sddmm(gnnagg_aggregator *a, const float *X1, const float *X2, float *out_val, int feat, int scheduled,
+                 void *stream);
+
+/* naive reference-style SpMM + validators of include/spmm.h:
+ *   gnnagg_spmm_naive        replaces spmm<LENFEATURE> (spmm.h:223-265; thread per row; rows
+ *                            with no edge are left untouched as there, :236-237)
+ *   gnnagg_validate          replaces valid()/validate2 (spmm.h:11-21,35-69): #elements with
+ *                            |(ref-ans)/ref| > 1e-2
+ *   gnnagg_validate_reordered replaces validReordered()/validateReordered (spmm.h:23-33,71-91)
+ * The two validators synchronise and return the count through *diffnum. */
+int gnnagg_spmm_naive(int num_v, const int *d_ptr, const int *d_idx, const float *d_val, const float *X, float *Y,
+                      int feat, void *stream);
+int gnnagg_validate(const float *d_ref, const float *d_ans, int64_t num, int *diffnum, void *stream);
+int gnnagg_validate_reordered(const float *d_ref, const float *d_ans, const int *d_map, int num_v, int feat,
+                              int *diffnum, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-buffer entry points (what a caller holding HOST arrays uses; bench.py's e2e number).
+ * They copy inputs host->device, run, copy the result back and synchronise `stream`.
+ * Pinned host memory makes the copies asynchronous with respect to the host.
+ * ------------------------------------------------------------------------------------------ */
+int gnnagg_gcn_run_host(gnnagg_aggregator *a, const float *h_X, float *h_Y, int feat, int scheduled, void *stream);
+int gnnagg_gcn_layer_host(gnnagg_aggregator *a, const float *h_X, const float *h_W, float *h_H, int feat_in,
+                          int feat_out, int scheduled, void *stream);
+int gnnagg_gat_run_host(gnnagg_aggregator *a, const float *h_X, const float *h_att, float *h_Y, int feat,
+                        float slope, int scheduled, void *stream);
+
+/* synchronous device->host copy of `bytes` bytes (binding helper: lets a ctypes/cgo caller read
+ * the scheduled arrays returned by gnnagg_sched_dev_* without linking the CUDA runtime itself;
+ * the reference does this with cudaMemcpy in its drivers) */
+int gnnagg_memcpy_d2h(void *h_dst, const void *d_src, uint64_t bytes);
+
+/* number of kernels the library launched on behalf of this aggregator since creation
+ * (bench.py's gpu_launches claim) */
+int64_t gnnagg_launch_count(const gnnagg_aggregator *a);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNNAGG_H */

@@ -1,0 +1,163 @@
+"""CPU tier: host preprocessing of libgnnagg.so (schedules, reorder, loader) -- bit-exact against the
+golden vectors of the reference and against the oracle on random graphs.  Mirrors what a reference
+user relies on: graph_schedule.h:17-243, src/data.cu:4-139."""
+import os
+
+import numpy as np
+import pytest
+
+from gnnagg import synth
+
+try:
+    from hypothesis import given, settings, strategies as st
+except Exception:  # pragma: no cover
+    given = None
+
+
+def _arr(x, dt=np.int32):
+    return np.asarray(x, dt)
+
+
+def _same(a, b):
+    return all((x is None and y is None) or np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_schedules_match_golden(gn, golden):
+    for case in golden["cases"]:
+        ptr, idx, val = _arr(case["ptr"]), _arr(case["idx"]), _arr(case["val"], np.float32)
+        for s in case["schedules"]:
+            p, i, t, v = gn.schedule_build(s["kind"], ptr, idx, None if s["kind"] == 1 else val,
+                                           par_num=s.get("par_num", 0), neighbor_num=s.get("neighbor_num", 0),
+                                           total_num_v=s.get("total_num_v"))
+            assert p.tolist() == s["ptr"] and i.tolist() == s["idx"] and t.tolist() == s["target"], (case["name"], s["kind"])
+            if s["kind"] != 1:
+                assert v.tolist() == s["val"]
+            else:
+                assert v is None
+
+
+def test_reorder_matches_golden(gn, golden):
+    for case in golden["cases"]:
+        r = case["reorder"]
+        newptr, newidx = gn.reorder_csr(case["ptr"], case["idx"], r["rows"], r["reverse_rows"])
+        assert newptr.tolist() == r["newptr"] and newidx.tolist() == r["newidx"]
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_schedules_match_oracle_random(gn, orc, seed):
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(1, 3000))
+    ptr, idx = synth.small_random_csr(n, float(rng.uniform(0.2, 40)), seed, empty_frac=float(rng.uniform(0, 0.7)),
+                                      hub=int(rng.integers(0, 2) * rng.integers(100, 5000)))
+    val = rng.standard_normal(len(idx)).astype(np.float32)
+    for ng in (1, 16, 32, 64):  # Figure9/main.cu:52, Figure10/run.sh
+        assert _same(gn.schedule_build(1, ptr, idx, neighbor_num=ng)[:3], orc.neighbor_grouping(ptr, idx, ng))
+    for par in (1, 2, 4, 8, n + 3):
+        for total in (n, max(1, n - 5)):
+            assert _same(gn.schedule_build(0, ptr, idx, val, par_num=par, total_num_v=total),
+                         orc.locality(ptr, idx, par, total, val))
+            assert _same(gn.schedule_build(2, ptr, idx, val, par_num=par, neighbor_num=32, total_num_v=total),
+                         orc.locality(ptr, idx, par, total, val, neighbor_num=32))
+    # without val no val vector comes back
+    assert gn.schedule_build(0, ptr, idx, None, par_num=2)[3] is None
+    rows = rng.permutation(n).astype(np.int32)
+    rev = np.empty(n, np.int32)
+    rev[rows] = np.arange(n, dtype=np.int32)
+    assert _same(gn.reorder_csr(ptr, idx, rows, rev), orc.reorder_csr(ptr, idx, rows, rev))
+
+
+def test_row_of_exactly_k_times_ng(gn, orc):
+    """rows of exactly k*NG edges must not emit an empty trailing group (graph_schedule.h:103,112)"""
+    ptr = _arr([0, 32, 32, 96, 97])
+    idx = np.arange(97, dtype=np.int32) % 4
+    p, i, t, _ = gn.schedule_build(1, ptr, idx, neighbor_num=32)
+    assert p.tolist() == [0, 32, 64, 96, 97] and t.tolist() == [0, 2, 2, 3]
+    assert _same((p, i, t), orc.neighbor_grouping(ptr, idx, 32))
+
+
+def test_schedule_argument_errors(gn):
+    ptr, idx = _arr([0, 1]), _arr([0])
+    with pytest.raises(gn.GnnaggError):
+        gn.schedule_build(1, ptr, idx, neighbor_num=0)
+    with pytest.raises(gn.GnnaggError):
+        gn.schedule_build(0, ptr, idx, par_num=0)
+    with pytest.raises(gn.GnnaggError):
+        gn.schedule_build(3, ptr, idx)  # nop is not buildable
+    with pytest.raises(gn.GnnaggError):
+        gn.reorder_csr(_arr([0, 1, 3]), _arr([0, 1, 0]), _arr([0, 0]), _arr([0, 1]))  # not a permutation
+
+
+def test_loader_matches_golden(gn, golden, tmp_path):
+    g = golden["load_graph"]
+    d = str(tmp_path) + "/"
+    (tmp_path / "tiny.config").write_text(g["config"])
+    (tmp_path / "tiny.graph").write_text(" ".join(map(str, g["graph_ptr"])) + "\n" + " ".join(map(str, g["graph_idx"])) + "\n")
+    (tmp_path / "tiny.reorder_t").write_text(g["reorder_text"])
+    ptr, idx, rows, rev = gn.load_graph("tiny", d, "_t")
+    assert ptr.tolist() == g["reordered_ptr"] and idx.tolist() == g["reordered_idx"]
+    assert rows.tolist() == g["rows"] and rev.tolist() == g["reverse_rows"]
+    # byte-compatible cache files (src/data.cu:64-67,88-91)
+    assert np.fromfile(d + "tiny.graph.ptrdump", np.int32).tolist() == g["ptrdump"]
+    assert np.fromfile(d + "tiny.graph.edgedump", np.int32).tolist() == g["edgedump"]
+    os.remove(d + "tiny.graph")  # the caches alone are enough (src/data.cu:50-54,77-81)
+    ptr, idx, rows, _ = gn.load_graph("tiny", d)
+    assert ptr.tolist() == g["cached_ptr"] and idx.tolist() == g["cached_idx"] and rows is None
+
+
+def test_loader_roundtrip_and_errors(gn, orc, tmp_path):
+    d = str(tmp_path) + "/"
+    ptr, idx = synth.small_random_csr(500, 6.0, 3)
+    gn.write_graph("g", ptr, idx, d)
+    # python side of the reference splits the two lines on single spaces (cluster2.py:18-20)
+    lines = open(d + "g.graph").read().split("\n")
+    assert [int(x) for x in lines[0].split(" ")] == ptr.tolist()
+    assert open(d + "g.config").read().split(" ") == [str(500), str(len(idx))]
+    p2, i2, _, _ = gn.load_graph("g", d)
+    assert np.array_equal(p2, ptr) and np.array_equal(i2, idx)
+    p3, i3, _, _ = orc.load_graph(d, "g")
+    assert np.array_equal(p3, ptr) and np.array_equal(i3, idx)
+    # only the ptr cache present: indices still come from the text (superset of the reference, which
+    # can only continue the stream it opened, src/data.cu:85)
+    os.remove(d + "g.graph.edgedump")
+    p4, i4, _, _ = gn.load_graph("g", d)
+    assert np.array_equal(i4, idx)
+    rows = np.random.default_rng(0).permutation(500).astype(np.int32)
+    gn.write_reorder(d + "g.reorder_x", rows)
+    assert open(d + "g.reorder_x").read() == "".join("%d " % r for r in rows)  # cluster2.py:168-171
+    p5, i5, r5, rev5 = gn.load_graph("g", d, "_x")
+    rev = np.empty(500, np.int32)
+    rev[rows] = np.arange(500, dtype=np.int32)
+    ep, ei = orc.reorder_csr(ptr, idx, rows, rev)
+    assert np.array_equal(p5, ep) and np.array_equal(i5, ei) and np.array_equal(r5, rows) and np.array_equal(rev5, rev)
+    with pytest.raises(gn.GnnaggError):
+        gn.load_graph("missing", d)
+    (tmp_path / "bad.config").write_text("3 5")
+    (tmp_path / "bad.graph").write_text("0 1 2 4\n0 1 2 0\n")  # ptr[n] != num_e
+    with pytest.raises(gn.GnnaggError):
+        gn.load_graph("bad", d)
+    (tmp_path / "g.reorder_bad").write_text("0 0 1 ")
+    with pytest.raises(gn.GnnaggError):
+        gn.load_graph("g", d, "_bad")
+
+
+if given is not None:
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.integers(0, 70), min_size=1, max_size=40), st.integers(1, 9), st.integers(1, 40), st.data())
+    def test_schedules_property(degs, par, ng, data):
+        import gnnagg as gn
+        import oracle as orc
+
+        n = len(degs)
+        ptr = np.zeros(n + 1, np.int32)
+        ptr[1:] = np.cumsum(degs)
+        idx = _arr(data.draw(st.lists(st.integers(0, n - 1), min_size=int(ptr[-1]), max_size=int(ptr[-1]))))
+        val = np.arange(len(idx), dtype=np.float32)
+        assert _same(gn.schedule_build(1, ptr, idx, neighbor_num=ng)[:3], orc.neighbor_grouping(ptr, idx, ng))
+        assert _same(gn.schedule_build(0, ptr, idx, val, par_num=par), orc.locality(ptr, idx, par, n, val))
+        got = gn.schedule_build(2, ptr, idx, val, par_num=par, neighbor_num=ng)
+        assert _same(got, orc.locality(ptr, idx, par, n, val, neighbor_num=ng))
+        # invariants: a permutation of the edges, groups never exceed ng and never mix rows
+        assert sorted(got[3].tolist()) == val.tolist()
+        sizes = np.diff(got[0])
+        assert sizes.size == 0 or (sizes.min() >= 1 and sizes.max() <= ng)
