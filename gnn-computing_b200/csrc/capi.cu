@@ -86,7 +86,15 @@ struct gnnagg_aggregator {
     int *s_ptr = nullptr, *s_idx = nullptr, *s_target = nullptr, *s_perm = nullptr, *s_item_row = nullptr;
     float *s_val = nullptr;  // owned only when s_perm != nullptr (locality kinds); NG aliases d_val
     int64_t launches = 0;
+    // optional per-kernel timing (gnnagg_profile_enable)
+    bool prof = false;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // begin, agg0, agg1, agg_end, end
 };
+
+#define PROF_RECORD(a, i, st)                                   \
+    do {                                                        \
+        if ((a)->prof) CUDA_TRY(cudaEventRecord((a)->ev[i], st)); \
+    } while (0)
 
 namespace gnnagg {
 
@@ -163,6 +171,7 @@ static int launch_agg(gnnagg_aggregator *a, const AggParams &p, cudaStream_t st)
 {
     const int F = p.F;
     const unsigned grid = (unsigned)cdiv(p.num_edges, (int64_t)kWarpEdges * kCtaWarps);
+    PROF_RECORD(a, 1, st);
     if (F <= 32)
         agg_kernel<8, 1, MODE, SCHED><<<grid, kCtaThreads, 0, st>>>(p);
     else if (F <= 64)
@@ -172,6 +181,7 @@ static int launch_agg(gnnagg_aggregator *a, const AggParams &p, cudaStream_t st)
     else
         agg_kernel<32, 2, MODE, SCHED><<<grid, kCtaThreads, 0, st>>>(p);
     LAUNCH_CHECK(a);
+    PROF_RECORD(a, 2, st);
     if (!SCHED) {
         const int EB = kWarpEdges / (32 / lpr_for(F));
         const int64_t items = cdiv(p.num_edges, EB);
@@ -185,12 +195,12 @@ static int launch_agg(gnnagg_aggregator *a, const AggParams &p, cudaStream_t st)
 
 static int aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-static int gcn_run_impl(gnnagg_aggregator *a, const float *X, float *Y, int F, int scheduled, cudaStream_t st)
+static int gcn_run_core(gnnagg_aggregator *a, const float *X, float *Y, int F, int scheduled, cudaStream_t st)
 {
     if (!a || !X || !Y) return set_error(GNNAGG_ERR_ARG, "gnnagg_gcn_run: NULL argument");
     if (int rc = check_feat(F)) return rc;
     if (!aligned16(X) || !aligned16(Y)) return set_error(GNNAGG_ERR_ARG, "X and Y must be 16-byte aligned");
-    if (!a->d_val) return set_error(GNNAGG_ERR_STATE, "gnnagg_gcn_run: edge values not set (gnnagg_set_val)");
+    if (!a->d_val && a->m > 0) return set_error(GNNAGG_ERR_STATE, "gnnagg_gcn_run: edge values not set (gnnagg_set_val)");
     AggParams p{};
     p.X = X;
     p.Y = Y;
@@ -226,7 +236,7 @@ static int gcn_run_impl(gnnagg_aggregator *a, const float *X, float *Y, int F, i
     return launch_agg<kModeGCN, false>(a, p, st);
 }
 
-static int gat_run_impl(gnnagg_aggregator *a, const float *X, const float *att, float *Y, int F, float slope,
+static int gat_run_core(gnnagg_aggregator *a, const float *X, const float *att, float *Y, int F, float slope,
                         int scheduled, cudaStream_t st)
 {
     if (!a || !X || !Y || !att) return set_error(GNNAGG_ERR_ARG, "gnnagg_gat_run: NULL argument");
@@ -276,6 +286,35 @@ static int gat_run_impl(gnnagg_aggregator *a, const float *X, const float *att, 
     p.num_edges = a->m;
     p.bulk_ok = aligned16(p.idx);
     return launch_agg<kModeGAT, false>(a, p, st);
+}
+
+// timing brackets: ev[0] call entry, ev[3] end of the aggregation part, ev[4] end of the call
+static int gcn_run_impl(gnnagg_aggregator *a, const float *X, float *Y, int F, int scheduled, cudaStream_t st,
+                        bool last = true)
+{
+    if (a) PROF_RECORD(a, 0, st);
+    if (a && a->prof) {  // so that a call that launches no aggregation kernel still reads as 0 ms
+        CUDA_TRY(cudaEventRecord(a->ev[1], st));
+        CUDA_TRY(cudaEventRecord(a->ev[2], st));
+    }
+    if (int rc = gcn_run_core(a, X, Y, F, scheduled, st)) return rc;
+    PROF_RECORD(a, 3, st);
+    if (last) PROF_RECORD(a, 4, st);
+    return GNNAGG_OK;
+}
+
+static int gat_run_impl(gnnagg_aggregator *a, const float *X, const float *att, float *Y, int F, float slope,
+                        int scheduled, cudaStream_t st)
+{
+    if (a) PROF_RECORD(a, 0, st);
+    if (a && a->prof) {
+        CUDA_TRY(cudaEventRecord(a->ev[1], st));
+        CUDA_TRY(cudaEventRecord(a->ev[2], st));
+    }
+    if (int rc = gat_run_core(a, X, att, Y, F, slope, scheduled, st)) return rc;
+    PROF_RECORD(a, 3, st);
+    PROF_RECORD(a, 4, st);
+    return GNNAGG_OK;
 }
 
 // out[v] = sum over row v of in[e]; deterministic
@@ -355,6 +394,8 @@ int gnnagg_destroy(gnnagg_aggregator *a)
     cudaFree(a->st_out);
     cudaFree(a->st_w);
     cudaFree(a->st_att);
+    for (int i = 0; i < 5; ++i)
+        if (a->ev[i]) cudaEventDestroy(a->ev[i]);
     delete a;
     return GNNAGG_OK;
 }
@@ -443,6 +484,31 @@ const float *gnnagg_sched_dev_val(const gnnagg_aggregator *a) { return a ? a->s_
 const float *gnnagg_gat_edge_weights(const gnnagg_aggregator *a) { return a ? a->newval : nullptr; }
 int64_t gnnagg_launch_count(const gnnagg_aggregator *a) { return a ? a->launches : 0; }
 
+int gnnagg_profile_enable(gnnagg_aggregator *a, int on)
+{
+    if (!a) return set_error(GNNAGG_ERR_ARG, "gnnagg_profile_enable: NULL aggregator");
+    if (on && !a->ev[0])
+        for (int i = 0; i < 5; ++i) CUDA_TRY(cudaEventCreate(&a->ev[i]));
+    a->prof = on != 0;
+    return GNNAGG_OK;
+}
+
+int gnnagg_profile_read(gnnagg_aggregator *a, float *ms)
+{
+    if (!a || !ms || !a->ev[0]) return set_error(GNNAGG_ERR_STATE, "gnnagg_profile_read: profiling not enabled");
+    CUDA_TRY(cudaEventSynchronize(a->ev[4]));
+    float agg = 0.f, agg_total = 0.f, dense = 0.f, total = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&agg, a->ev[1], a->ev[2]));
+    CUDA_TRY(cudaEventElapsedTime(&agg_total, a->ev[0], a->ev[3]));
+    CUDA_TRY(cudaEventElapsedTime(&dense, a->ev[3], a->ev[4]));
+    CUDA_TRY(cudaEventElapsedTime(&total, a->ev[0], a->ev[4]));
+    ms[0] = agg;
+    ms[1] = agg_total - agg;
+    ms[2] = dense;
+    ms[3] = total;
+    return GNNAGG_OK;
+}
+
 int gnnagg_memcpy_d2h(void *h_dst, const void *d_src, uint64_t bytes)
 {
     if (bytes == 0) return GNNAGG_OK;
@@ -478,10 +544,12 @@ int gnnagg_gcn_layer(gnnagg_aggregator *a, const float *X, const float *W, float
         if (int rc = ensure(a->ax, a->ax_cap, (size_t)a->n * feat_in)) return rc;
         ax = a->ax;
     }
-    if (int rc = gcn_run_impl(a, X, ax, feat_in, scheduled, (cudaStream_t)stream)) return rc;
-    if (a->n == 0) return GNNAGG_OK;
-    if (int rc = dense_nn_launch(ax, W, H, a->n, feat_out, feat_in, stream)) return rc;
-    ++a->launches;
+    if (int rc = gcn_run_impl(a, X, ax, feat_in, scheduled, (cudaStream_t)stream, false)) return rc;
+    if (a->n > 0) {
+        if (int rc = dense_nn_launch(ax, W, H, a->n, feat_out, feat_in, stream)) return rc;
+        ++a->launches;
+    }
+    PROF_RECORD(a, 4, (cudaStream_t)stream);
     return GNNAGG_OK;
 }
 
@@ -489,7 +557,7 @@ int gnnagg_gcn_run_edgewise(gnnagg_aggregator *a, const float *X, float *Y, int 
 {
     if (!a || !X || !Y) return set_error(GNNAGG_ERR_ARG, "gnnagg_gcn_run_edgewise: NULL argument");
     if (int rc = check_feat(feat)) return rc;
-    if (!a->d_val) return set_error(GNNAGG_ERR_STATE, "edge values not set");
+    if (!a->d_val && a->m > 0) return set_error(GNNAGG_ERR_STATE, "edge values not set");
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaMemsetAsync(Y, 0, (size_t)a->n * feat * sizeof(float), st));  // aggr_gcn.h:447
     if (a->m == 0) return GNNAGG_OK;

@@ -83,6 +83,8 @@ _SIGS = {
     "gnnagg_gcn_layer_host": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "gnnagg_gat_run_host": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_float, C.c_int, C.c_void_p]),
     "gnnagg_launch_count": (C.c_int64, [C.c_void_p]),
+    "gnnagg_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "gnnagg_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "gnnagg_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
 }
 
@@ -260,6 +262,15 @@ class Aggregator:
     @property
     def launches(self):
         return lib().gnnagg_launch_count(self.h)
+
+    def profile(self, on=True):
+        check(lib().gnnagg_profile_enable(self.h, int(on)))
+
+    def profile_read(self):
+        """ms of the last run: dict(agg, agg_rest, dense, total)"""
+        ms = (C.c_float * 4)()
+        check(lib().gnnagg_profile_read(self.h, ms))
+        return {"agg": ms[0], "agg_rest": ms[1], "dense": ms[2], "total": ms[3]}
 
     def scheduled_arrays(self):
         """device schedule copied back as numpy (ptr, idx, target, val|None)"""

@@ -1,0 +1,51 @@
+// aggr_gat.h -- compatibility layer: class Aggregator_GAT of the reference (include/aggr_gat.h:299-441)
+// on top of libgnnagg.so.  LeakyReLU slope fixed at 0.2 as in the reference (:339,347,400).
+#ifndef AGGR_GAT_H
+#define AGGR_GAT_H
+#include "aggregator.h"
+
+class Aggregator_GAT : public Aggregator {
+public:
+    Aggregator_GAT(int *host_out_ptr, int *host_out_idx, int *dev_out_ptr, int *dev_out_idx, int out_num_v,
+                   int out_num_e, int out_feat_in, int out_feat_out)
+        : Aggregator(host_out_ptr, host_out_idx, dev_out_ptr, dev_out_idx, out_num_v, out_num_e, out_feat_in,
+                     out_feat_out)
+    {
+    }
+    Aggregator_GAT(CSRSubGraph g, int out_feat_in, int out_feat_out) : Aggregator(g, out_feat_in, out_feat_out) {}
+
+    // fused SDDMM -> edge softmax -> SpMM (:317-354); vatt is the [n,2] attention table
+    double run(float *vin, float *vatt, float *vout, int BLOCK_SIZE, bool scheduled) override
+    {
+        checkGnnagg(gnnagg_gat_run(handle, vin, vatt, vout, feat_in, 0.2f, scheduled, NULL));
+        return 0.0;
+    }
+    double run_with_feat(float *vin, float *vatt, float *vout, int BLOCK_SIZE, bool scheduled, int feat)
+    {
+        feat_in = feat;
+        return run(vin, vatt, vout, BLOCK_SIZE, scheduled);
+    }
+    void run_att(float *in_att, float *out_val, int BLOCK_SIZE)
+    {
+        checkGnnagg(gnnagg_edge_softmax(handle, in_att, out_val, 0.2f, NULL));
+    }
+    void run_u_add_v(float *in_att, float *out_val, int BLOCK_SIZE)
+    {
+        checkGnnagg(gnnagg_u_add_v(handle, in_att, out_val, NULL));
+    }
+    void run_add_to_center(float *in_val, float *out_att, int BLOCK_SIZE)
+    {
+        checkGnnagg(gnnagg_add_to_center(handle, in_val, out_att, NULL));
+    }
+    void run_div_each(float *in_att, float *in_out_val, int BLOCK_SIZE)
+    {
+        checkGnnagg(gnnagg_each_div(handle, in_att, in_out_val, NULL));
+    }
+    // the experimental backward kernel (aggr_gat_fine_bwd, :222-294) is used by no driver of the
+    // reference and is outside the forward hot path
+    void run_bwd(float *, float *, float *, float *, float *, float *, float *, float, int)
+    {
+        FatalError("Aggregator_GAT::run_bwd is not part of the forward aggregation path");
+    }
+};
+#endif

@@ -206,6 +206,15 @@ int gnnagg_gcn_layer_host(gnnagg_aggregator *a, const float *h_X, const float *h
 int gnnagg_gat_run_host(gnnagg_aggregator *a, const float *h_X, const float *h_att, float *h_Y, int feat,
                         float slope, int scheduled, void *stream);
 
+/* per-kernel device timing of the LAST gnnagg_gcn_run / gnnagg_gat_run / gnnagg_gcn_layer call:
+ * when enabled the library brackets its launches with CUDA events on the caller's stream.
+ * gnnagg_profile_read synchronises on those events and returns milliseconds in
+ * ms[0] = aggregation kernel, ms[1] = split-row fix-up (or memset+scale in scheduled mode),
+ * ms[2] = dense combination, ms[3] = whole call.  Used by bench.py for the roofline line
+ * (the reference's analogue is run_clock / aggr_gcn_clock, aggr_gcn.h:159-248,462-489). */
+int gnnagg_profile_enable(gnnagg_aggregator *a, int on);
+int gnnagg_profile_read(gnnagg_aggregator *a, float *ms /* [4] */);
+
 /* synchronous device->host copy of `bytes` bytes (binding helper: lets a ctypes/cgo caller read
  * the scheduled arrays returned by gnnagg_sched_dev_* without linking the CUDA runtime itself;
  * the reference does this with cudaMemcpy in its drivers) */

@@ -99,6 +99,15 @@ def dense_f64(A, W):
     return H, S
 
 
+def dense_f32(A, W, row_begin=0, row_end=None, out=None):
+    M, K = A.shape
+    N = W.shape[1]
+    row_end = M if row_end is None else row_end
+    H = np.zeros((M, N), np.float32) if out is None else out
+    lib().orc_dense_f32(C.c_int64(row_begin), C.c_int64(row_end), C.c_int(K), C.c_int(N), _vp(A), _vp(W), _vp(H))
+    return H
+
+
 def gcn_layer_f64(ptr, idx, val, X, W):
     n = len(ptr) - 1
     K = X.shape[1]

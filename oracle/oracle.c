@@ -147,6 +147,22 @@ void orc_dense_f64(int64_t M, int K, int N, const float *A, const float *W, floa
     }
 }
 
+/* fp32 row-block variant of the combination, used only to TIME the CPU port (bench.py
+ * cpu_baseline / --impl reference): same i-k-o loop order a scalar port would use. */
+void orc_dense_f32(int64_t row_begin, int64_t row_end, int K, int N, const float *A, const float *W, float *H)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t i = row_begin; i < row_end; ++i) {
+        float *h = H + (size_t)i * N;
+        for (int o = 0; o < N; ++o) h[o] = 0.0f;
+        for (int k = 0; k < K; ++k) {
+            const float a = A[(size_t)i * K + k];
+            const float *w = W + (size_t)k * N;
+            for (int o = 0; o < N; ++o) h[o] = fmaf(a, w[o], h[o]);
+        }
+    }
+}
+
 /* Fused layer H = (A*X)*W in fp64 end to end (no fp32 rounding of the intermediate); scale is
  * sum over edges and k of |val*x*w| so the 1e-5 gate covers both stages.
  * reference semantics: aggr_gcn.h:304-359 + 491-499 (run_with_nn), Figure10/main_b.cu:84-101. */

@@ -63,9 +63,10 @@ def test_gcn_empty_graph_and_errors(gn, cuda):
         agg.gcn_run(torch.ones((7, 30), device=cuda), torch.empty((7, 30), device=cuda))  # feat % 4 != 0
     with pytest.raises(gn.GnnaggError):
         agg.gcn_run(torch.ones((7, 32), device=cuda), torch.empty((7, 32), device=cuda), scheduled=True)  # no schedule
-    agg2 = gn.Aggregator(ptr, idx)
+    p2, i2 = dev(np.array([0, 1, 2], np.int32)), dev(np.array([1, 0], np.int32))
+    agg2 = gn.Aggregator(p2, i2)
     with pytest.raises(gn.GnnaggError):
-        agg2.gcn_run(torch.ones((7, 32), device=cuda), torch.empty((7, 32), device=cuda))  # no edge values
+        agg2.gcn_run(torch.ones((2, 32), device=cuda), torch.empty((2, 32), device=cuda))  # no edge values
 
 
 @pytest.mark.parametrize("kind,params", [(1, [16]), (1, [32]), (1, [1]), (0, [4]), (2, [4, 32]), (2, [3, 7])])

@@ -3,6 +3,7 @@ aggr_gat, aggr_gat_fine+scaleArray, attGat, u_add_v, add_to_center, each_div, ag
 recompiled for sm_100 from /root/reference into oracle/_ref/libref.so (oracle/Makefile).
 Both are also compared with the fp64 oracle so the reference's own error is visible."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -125,4 +126,82 @@ def test_gat_pieces_and_sddmm_vs_reference_kernels(gn, orc, ref, cuda):
     o_out = agg.sddmm(dev(X1), dev(X2), torch.empty(m, device=cuda))
     v64, scale = orc.sddmm_f64(ptr, idx, X1, X2)
     assert rel_gate(o_out.cpu().numpy(), v64, scale, 1e-5)[0] == 0
-    assert rel_gate(o_out.cpu().numpy(), r_out[:m].cpu().numpy(), scale, 2e-5)[0] == 0
+    assert ref.ref_sync() == 0
+    # aggr_sddmm exchanges data between lanes through shared memory with its __syncwarp commented out
+    # (aggr_sddmm.h:21-41, :39), so on Volta+ its own output is not reliable: it is compared with the
+    # oracle first and only held against ours when it is itself correct.
+    bad_ref = rel_gate(r_out[:m].cpu().numpy(), v64, scale, 1e-4)[0]
+    print("reference aggr_sddmm: %d of %d values off the fp64 oracle" % (bad_ref, m))
+    if bad_ref == 0:
+        assert rel_gate(o_out.cpu().numpy(), r_out[:m].cpu().numpy(), scale, 2e-5)[0] == 0
+
+
+@pytest.mark.skipif(os.environ.get("GNNAGG_HEAVY") != "1", reason="full-size timing run: set GNNAGG_HEAVY=1")
+@pytest.mark.parametrize("shape,F", [("arxiv", 32), ("reddit", 128), ("proteins", 64), ("products", 256)])
+def test_timing_vs_reference_kernels_full_size(gn, orc, ref, cuda, shape, F):
+    """the on-box 'kernel to beat': the reference's aggr_gcn / aggr_gcn_target / aggr_gat recompiled for
+    sm_100, timed beside ours on the BASELINE.json shapes; results land in gpurun_out/ref_vs_ours.jsonl"""
+    import json
+    import time
+
+    from gnnagg import synth
+
+    n, m = synth.shape_of(shape)
+    ptr, idx = synth.rmat_csr(n, m, seed=123, device=cuda)
+    val = synth.gcn_norm_val(ptr, idx)
+    g = torch.Generator(device=cuda).manual_seed(123)
+    X = torch.randn((n, F), device=cuda, generator=g)
+    att = torch.randn((n, 2), device=cuda, generator=g)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=cuda)
+
+    def timeit(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+
+    agg = gn.Aggregator(ptr, idx, val)
+    Y = torch.empty((n, F), device=cuda)
+    Yr = torch.zeros((n, F), device=cuda)
+    ref.ref_set_globals(n, m)
+    h = C.c_void_p(ref.ref_gcn_create(P(ptr), P(idx), P(val), n, m, F, F))
+    hg = C.c_void_p(ref.ref_gat_create(P(ptr), P(idx), n, m, F))
+    out = {"shape": shape, "n": n, "m": m, "F": F}
+    out["ours_gcn_ms"] = timeit(lambda: agg.gcn_run(X, Y))
+    block = 512 if F <= 64 else 128  # Figure9/main.cu:54 uses 512; BLOCK_SIZE >= F*? keeps >=1 row per block
+    out["ref_aggr_gcn_ms"] = timeit(lambda: ref.ref_gcn_run(h, P(X), P(Yr), max(block, F), 0, F))
+    torch.cuda.synchronize()
+    hp, hi, hv = ptr.cpu().numpy(), idx.cpu().numpy(), val.cpu().numpy()
+    # parity of both on a row sample (full fp64 oracle on 1e8 edges would take minutes)
+    rows = min(n, 4000)
+    e = int(hp[rows])
+    y64, scale = orc.spmm_f64(np.ascontiguousarray(hp[: rows + 1]), hi[:e], hv[:e], X.cpu().numpy())
+    out["ours_gcn_worst_err_over_bound"] = rel_gate(Y[:rows].cpu().numpy(), y64, scale, 1e-5)[1]
+    out["ref_gcn_worst_err_over_bound"] = rel_gate(Yr[:rows].cpu().numpy(), y64, scale, 1e-5)[1]
+    assert out["ours_gcn_worst_err_over_bound"] <= 1.0
+    t0 = time.time()
+    agg.schedule(1, [32])
+    out["ours_schedule_ng32_s"] = time.time() - t0
+    t0 = time.time()
+    ref.ref_gcn_schedule(h, 1, 32, 0)
+    out["ref_schedule_ng32_s"] = time.time() - t0
+    out["ours_gcn_sched_ms"] = timeit(lambda: agg.gcn_run(X, Y, scheduled=True))
+    out["ref_aggr_gcn_target_ms"] = timeit(lambda: ref.ref_gcn_run(h, P(X), P(Yr), max(128, F), 1, F))
+    gat = gn.Aggregator(ptr, idx)
+    out["ours_gat_ms"] = timeit(lambda: gat.gat_run(X, att, Y))
+    out["ref_aggr_gat_ms"] = timeit(lambda: ref.ref_gat_run(hg, P(X), P(att), P(Yr), max(128, F), 0, F))
+    out["gather_model_bytes"] = 4 * (n + 1) + 8 * m + 4 * m * F + 4 * n * F
+    for k in ("ours_gcn", "ref_aggr_gcn", "ours_gcn_sched", "ref_aggr_gcn_target"):
+        out[k + "_GBps"] = out["gather_model_bytes"] / out[k + "_ms"] / 1e6
+    os.makedirs(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out"), exist_ok=True)
+    with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "ref_vs_ours.jsonl"), "a") as f:
+        f.write(json.dumps(out) + "\n")
+    print(json.dumps(out))
