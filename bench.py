@@ -126,6 +126,9 @@ def main():
     ap.add_argument("--workload", default="reddit_gcn_layer_128", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU work budget of the cpu_baseline sample")
     ap.add_argument("--scheduled", type=int, default=0, help="1: run the neighbour-grouped (NG=32) path")
+    ap.add_argument("--sources", default="rmat", choices=["rmat", "uniform"],
+                    help="rmat: the R-MAT source distribution of the workload definition (default, headline); uniform: same "
+                         "degree sequence but uniformly random sources -- the cache-hostile extreme, reported as context")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -146,7 +149,7 @@ def main():
                           "%s-shaped R-MAT graph, %d vertices / %d edges per GPU" % (args.workload, fin, fout, shape, n, m),
               "graph": "rmat(a=.57,b=.19,c=.19,d=.05) seed=123, val=1/sqrt((deg_u+1)(deg_v+1)), X~N(0,1), W~N(0,1)/sqrt(F)",
               "partition": "1d-row-by-destination" if args.gpus > 1 else "single-gpu",
-              "scheduled": bool(args.scheduled),
+              "scheduled": bool(args.scheduled), "sources": args.sources,
               "l2": "flushed between timed steps (256 MiB write) and inputs (idx+val %.0f MB, X %.0f MB) exceed the 126 MB L2"
                     % (8 * m / 1e6, 4 * n * fin / 1e6)}
 
@@ -211,6 +214,9 @@ def main():
     t0 = time.time()
     ptr, idx = synth.rmat_csr(n, m, seed=123, device=dev, src_num_v=src_n if N > 1 else None,
                               dst_prefix=rank if N > 1 else None)
+    if args.sources == "uniform":
+        idx = torch.randint(0, src_n, (m,), device=dev, dtype=torch.int32,
+                            generator=torch.Generator(device=dev).manual_seed(99 + rank))
     deg = (ptr[1:] - ptr[:-1]).to(torch.float32)
     if N > 1:
         deg_all = torch.empty(src_n, device=dev)
@@ -308,7 +314,8 @@ def main():
     traffic = None
     try:  # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this workload
         summ = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
-        traffic = summ.get(args.workload + ("_sched" if args.scheduled else ""), {}).get("dram_bytes_per_launch")
+        key = args.workload + ("_sched" if args.scheduled else "") + ("_uniform" if args.sources == "uniform" else "")
+        traffic = summ.get(key, {}).get("dram_bytes_per_launch")
     except Exception:
         pass
     achieved = spmm_bytes(n, m, fin) / (agg_ms * 1e-3) / 1e9

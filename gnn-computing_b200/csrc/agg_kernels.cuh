@@ -171,8 +171,65 @@ __global__ void __launch_bounds__(kCtaThreads) agg_kernel(const AggParams p)
         int e = e0;
         while (row_end == e) flush(false);  // leading empty rows (only item 0 can see any)
 
-        while (e < e1) {
-            const int nb = min(U, e1 - e);
+        // gather base of this lane: column `col` of row 0 (inactive lanes of a partial chunk read
+        // column 0 instead of being predicated off; their results are never stored)
+        const char *xb = reinterpret_cast<const char *>(p.X + (act0 ? col : 0));
+        const uint32_t row_bytes = (uint32_t)F * 4u;
+        const int second = act1 ? LPR * 16 : 0;  // byte offset of the second float4 (NV == 2)
+
+        // ---- full batches: U edges, idx/val fetched as 128-bit shared loads (e - wbase is a multiple
+        // of U here because items start on multiples of 128 and only the last batch can be short)
+        while (e + U <= e1) {
+            const int k = e - wbase;
+            int src[U];
+            float w[U];
+#pragma unroll
+            for (int q = 0; q < U / 4; ++q) {
+                const int4 i4 = *reinterpret_cast<const int4 *>(my_idx + k + 4 * q);
+                const float4 w4 = *reinterpret_cast<const float4 *>(my_val + k + 4 * q);
+                src[4 * q] = i4.x, src[4 * q + 1] = i4.y, src[4 * q + 2] = i4.z, src[4 * q + 3] = i4.w;
+                w[4 * q] = w4.x, w[4 * q + 1] = w4.y, w[4 * q + 2] = w4.z, w[4 * q + 3] = w4.w;
+            }
+            float4 v0[U], v1[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const char *x = xb + (size_t)(uint32_t)src[u] * row_bytes;  // one IMAD.WIDE.U32
+                v0[u] = __ldg(reinterpret_cast<const float4 *>(x));
+                if (NV > 1) v1[u] = __ldg(reinterpret_cast<const float4 *>(x + second));
+            }
+            float wout = 0.f;
+            if (MODE == kModeGCN && row_end - e >= U) {
+                // no row ends inside the batch: straight FMA chain
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    fma4(acc0, w[u], v0[u]);
+                    if (NV > 1) fma4(acc1, w[u], v1[u]);
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    while (row_end == e + u) flush(false);
+                    float wu = w[u];
+                    if (MODE == kModeGAT) {
+                        const float sc = a_dst + wu;
+                        wu = __expf(fmaxf(sc, sc * p.slope));  // aggr_gat.h:143
+                        den += wu;
+                        if (SCHED && vl == u % LPR) wout = wu;
+                    }
+                    fma4(acc0, wu, v0[u]);
+                    if (NV > 1) fma4(acc1, wu, v1[u]);
+                }
+            }
+            if (MODE == kModeGAT && SCHED && cb == 0 && p.newval != nullptr) {
+                // one coalesced store per batch instead of one per edge (U <= LPR always holds)
+                if (vl < U) p.newval[e + vl] = wout;
+            }
+            e += U;
+        }
+
+        // ---- the short last batch (only the last item of the graph has one)
+        if (e < e1) {
+            const int nb = e1 - e;
             int src[U];
             float w[U];
             float4 v0[U], v1[U];
@@ -184,9 +241,9 @@ __global__ void __launch_bounds__(kCtaThreads) agg_kernel(const AggParams p)
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const float *x = p.X + (size_t)src[u] * F + col;
-                v0[u] = act0 ? ldg_f4(x) : make_float4(0.f, 0.f, 0.f, 0.f);
-                if (NV > 1) v1[u] = act1 ? ldg_f4(x + LPR * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const char *x = xb + (size_t)(uint32_t)src[u] * row_bytes;
+                v0[u] = __ldg(reinterpret_cast<const float4 *>(x));
+                if (NV > 1) v1[u] = __ldg(reinterpret_cast<const float4 *>(x + second));
             }
             float wout = 0.f;
 #pragma unroll
@@ -195,8 +252,8 @@ __global__ void __launch_bounds__(kCtaThreads) agg_kernel(const AggParams p)
                     while (row_end == e + u) flush(false);
                     float wu = w[u];
                     if (MODE == kModeGAT) {
-                        const float s = a_dst + wu;
-                        wu = __expf(fmaxf(s, s * p.slope));  // aggr_gat.h:143
+                        const float sc = a_dst + wu;
+                        wu = __expf(fmaxf(sc, sc * p.slope));
                         den += wu;
                         if (SCHED && vl == u % LPR) wout = wu;
                     }
@@ -205,10 +262,9 @@ __global__ void __launch_bounds__(kCtaThreads) agg_kernel(const AggParams p)
                 }
             }
             if (MODE == kModeGAT && SCHED && cb == 0 && p.newval != nullptr) {
-                // one coalesced store per batch instead of one per edge (U <= LPR always holds)
                 if (vl < nb) p.newval[e + vl] = wout;
             }
-            e += nb;
+            e = e1;
         }
 
         // item end

@@ -197,6 +197,7 @@ static int aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 1
 
 static int gcn_run_core(gnnagg_aggregator *a, const float *X, float *Y, int F, int scheduled, cudaStream_t st)
 {
+    if (a && a->n == 0) return GNNAGG_OK;  // an empty row block (possible after edge-balanced partitioning)
     if (!a || !X || !Y) return set_error(GNNAGG_ERR_ARG, "gnnagg_gcn_run: NULL argument");
     if (int rc = check_feat(F)) return rc;
     if (!aligned16(X) || !aligned16(Y)) return set_error(GNNAGG_ERR_ARG, "X and Y must be 16-byte aligned");
@@ -239,6 +240,7 @@ static int gcn_run_core(gnnagg_aggregator *a, const float *X, float *Y, int F, i
 static int gat_run_core(gnnagg_aggregator *a, const float *X, const float *att, float *Y, int F, float slope,
                         int scheduled, cudaStream_t st)
 {
+    if (a && a->n == 0) return GNNAGG_OK;
     if (!a || !X || !Y || !att) return set_error(GNNAGG_ERR_ARG, "gnnagg_gat_run: NULL argument");
     if (int rc = check_feat(F)) return rc;
     if (!aligned16(X) || !aligned16(Y)) return set_error(GNNAGG_ERR_ARG, "X and Y must be 16-byte aligned");
