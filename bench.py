@@ -129,6 +129,8 @@ def main():
     ap.add_argument("--sources", default="rmat", choices=["rmat", "uniform"],
                     help="rmat: the R-MAT source distribution of the workload definition (default, headline); uniform: same "
                          "degree sequence but uniformly random sources -- the cache-hostile extreme, reported as context")
+    ap.add_argument("--pipeline", type=int, default=4,
+                    help="N>1: number of row chunks of the pipelined halo all-gather (0 = one all-gather, then the layer)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -228,19 +230,37 @@ def main():
     g = torch.Generator(device=dev).manual_seed(123 + rank)
     Xs = torch.randn((n, fin), device=dev, generator=g)          # this rank's X shard
     W = torch.randn((fin, fout), device=dev, generator=torch.Generator(device=dev).manual_seed(7)) / fin ** 0.5
-    Xfull = torch.empty((src_n, fin), device=dev) if N > 1 else Xs
+    pipelined = N > 1 and args.pipeline > 0 and not args.scheduled
+    Xfull = torch.empty((src_n, fin), device=dev) if (N > 1 and not pipelined) else Xs
     H = torch.empty((n, fout), device=dev)
     agg = gnnagg.Aggregator(ptr, idx, val)
     if args.scheduled:
         agg.schedule(gnnagg.SCHED_NEIGHBOR_GROUPING, [32])
+    pipe = AX = None
+    if pipelined:
+        from gnnagg.partition import HaloPipeline
+
+        pipe = HaloPipeline(ptr, idx, val, n, N, rank, fin, chunks=args.pipeline)
+        AX = torch.empty((n, fin), device=dev)
+        config["halo"] = "all-gather cut into %d row chunks, sub-CSR of chunk c accumulated while chunk c+1 is in flight; " \
+                         "edges with local sources first" % args.pipeline
+    elif N > 1:
+        config["halo"] = "one NCCL all-gather of X, then the layer"
     torch.cuda.synchronize()
     t_setup = time.time() - t0
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
+    def layer(x_full):
+        if pipelined:
+            pipe.aggregate(Xs, AX)                    # chunked all-gather overlapped with aggregation
+            gnnagg.dense_nn(AX, W, H)
+        else:
+            if N > 1:
+                dist.all_gather_into_tensor(Xfull, Xs)   # source-feature halo over NVLink
+            agg.gcn_layer(x_full, W, H, None, scheduled=bool(args.scheduled))
+
     def step():
-        if N > 1:
-            dist.all_gather_into_tensor(Xfull, Xs)   # source-feature halo over NVLink
-        agg.gcn_layer(Xfull, W, H, None, scheduled=bool(args.scheduled))
+        layer(Xfull)
 
     # host buffers for the end-to-end number
     hX = torch.empty((n, fin), pin_memory=True).copy_(Xs)
@@ -252,8 +272,7 @@ def main():
             agg.gcn_layer_host(hX, hW, hH, scheduled=bool(args.scheduled))  # H2D + layer + D2H + sync inside
         else:
             Xs.copy_(hX, non_blocking=True)
-            dist.all_gather_into_tensor(Xfull, Xs)
-            agg.gcn_layer(Xfull, W, H, None, scheduled=bool(args.scheduled))
+            layer(Xfull)
             hH.copy_(H, non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
@@ -268,7 +287,9 @@ def main():
         barrier()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         prof = []
-        l0 = agg.launches
+        aggs = pipe.aggs if pipelined else [agg]
+        count = lambda: sum(a.launches for a in aggs)
+        l0 = count()
         sampler.active = True
         for a, b in evs:
             flush.fill_(1)  # L2 flush, outside the timed events
@@ -276,7 +297,8 @@ def main():
             fn()
             b.record()
             if profile:
-                prof.append(agg.profile_read())
+                reads = [a.profile_read() for a in aggs]
+                prof.append({k: sum(r[k] for r in reads) for k in reads[0]})
         barrier()
         sampler.active = False
         total_ms = sum(a.elapsed_time(b) for a, b in evs)
@@ -284,13 +306,15 @@ def main():
             t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             total_ms = float(t.item())
-        return total_ms / steps, agg.launches - l0, prof
+        return total_ms / steps, count() - l0 + (steps if pipelined else 0), prof  # + the dense launch per step
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    agg.profile(True)
+    for a_ in (pipe.aggs if pipelined else [agg]):
+        a_.profile(True)
     ms, launches, prof = timed(step, args.steps, args.warmup, profile=True)
-    agg.profile(False)
+    for a_ in (pipe.aggs if pipelined else [agg]):
+        a_.profile(False)
     ms_e2e, _, _ = timed(step_e2e, max(3, args.steps // 2), 3)
     clocks = sampler.result()
 
@@ -329,7 +353,12 @@ def main():
 
     import oracle as orc
 
-    gbs, t_cpu, rows, e = cpu_sample(orc, ptr, idx, val, Xfull, W, fin, fout, args.cpu_seconds)
+    if N > 1:  # the CPU port needs the replicated X of rank 0's block
+        g_all = [torch.randn((n, fin), device=dev, generator=torch.Generator(device=dev).manual_seed(123 + r)) for r in range(N)]
+        Xcpu = torch.cat(g_all)
+    else:
+        Xcpu = Xs
+    gbs, t_cpu, rows, e = cpu_sample(orc, ptr, idx, val, Xcpu, W, fin, fout, args.cpu_seconds)
     cpu_baseline = {"value": round(gbs, 3), "unit": "GB/s", "cores": orc.num_threads(), "kind": "port",
                     "sample": "rows [0,%d) = %d edges (%.2f%% of m) of rank 0's graph, %.1f s; scalar fp32 CSR port + fp32 GEMM "
                               "(oracle/oracle.c, OpenMP dynamic,64)" % (rows, e, 100.0 * e / m, t_cpu)}
@@ -342,7 +371,7 @@ def main():
             "e2e": {"value": round(e2e_value, 1), "unit": "GB/s", "ms_per_step": round(ms_e2e, 4),
                     "h2d_bytes_per_step": 4 * n * fin + (4 * fin * fout if N == 1 else 0), "d2h_bytes_per_step": 4 * n * fout,
                     "api": "gnnagg_gcn_layer_host (pinned host X, W -> H)" if N == 1 else
-                           "pinned H2D of the X shard + NCCL all-gather + gnnagg_gcn_layer + D2H of the H shard"},
+                           "pinned H2D of the X shard + NCCL halo all-gather + aggregation + combination + D2H of the H shard"},
             "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "setup_s": round(t_setup, 2)}

@@ -45,18 +45,31 @@ struct AggParams {
     int F;
     float slope;
     int bulk_ok;                         // idx/val 16-byte aligned -> TMA staging allowed
+    int num_fine_items;                  // entries of item_row
+    int accumulate;                      // GCN un-scheduled: Y += A*X instead of Y = A*X
 };
 
 enum { kModeGCN = 0, kModeGAT = 1 };
 
-template <int LPR, int NV, int MODE, bool SCHED>
-__global__ void __launch_bounds__(kCtaThreads) agg_kernel(const AggParams p)
+// row that contains edge e0 (start of an item): direct lookup when items are aligned with the
+// item_row table, bounded binary search otherwise (the small-graph variant uses 32..128-edge items)
+__device__ __forceinline__ int item_start_row(const AggParams &p, int e0)
 {
+    if (e0 % kFineItem == 0) return __ldg(p.item_row + e0 / kFineItem);
+    return row_of_edge(p.ptr, p.item_row, p.num_fine_items, p.num_rows, e0);
+}
+
+// WE = edges staged per warp: 512 normally, 128 for small graphs (4x more warps, shorter walks)
+template <int LPR, int NV, int MODE, bool SCHED, int WE>
+__global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(const AggParams p)
+{
+    constexpr int kWarpEdges = WE;            // shadows the namespace-level default
     constexpr int VPW = 32 / LPR;             // virtual warps per warp
     constexpr int EB = kWarpEdges / VPW;      // edges per item
-    constexpr int U = (NV == 1) ? 8 : 4;      // gathers in flight per lane = U*NV float4
+    // gathers in flight per lane = U*NV float4; the small-graph variant trades depth for residency
+    constexpr int U = (WE < 512) ? 4 : ((NV == 1) ? 8 : 4);
     constexpr int CHUNK = LPR * 4 * NV;       // feature columns covered per pass
-    static_assert(LPR >= 8 && U <= LPR && EB % kFineItem == 0, "virtual warp narrower than 8 lanes is not supported");
+    static_assert(LPR >= 8 && U <= LPR && EB % U == 0, "virtual warp narrower than 8 lanes is not supported");
 
     __shared__ __align__(16) int s_idx[kCtaWarps][kWarpEdges];
     __shared__ __align__(16) float s_val[kCtaWarps][kWarpEdges];
@@ -70,9 +83,10 @@ __global__ void __launch_bounds__(kCtaThreads) agg_kernel(const AggParams p)
     const int wbase = (int)wbase64;
     const int wcnt = min(kWarpEdges, p.num_edges - wbase);
 
-    // ---------------- stage idx (+val) of this warp's 512 edges ----------------
+    // ---------------- stage idx (+val) of this warp's edges ----------------
     int *my_idx = s_idx[warp];
     float *my_val = s_val[warp];
+    int first_row = 0, first_row_end = 0, first_row_begin = 0;
     {
         const int nb = p.bulk_ok ? (wcnt & ~3) : 0;  // bulk copies need 16-byte multiples
         const uint32_t bar = smem_u32(&s_bar[warp]);
@@ -89,6 +103,15 @@ __global__ void __launch_bounds__(kCtaThreads) agg_kernel(const AggParams p)
         for (int i = nb + lane; i < wcnt; i += 32) {
             my_idx[i] = __ldg(p.idx + wbase + i);
             if (MODE == kModeGCN) my_val[i] = __ldg(p.val + wbase + i);
+        }
+        // the start row of this lane's item is looked up while the bulk copy is in flight
+        {
+            const int e0s = wbase + (lane / LPR) * EB;
+            if (e0s < p.num_edges) {
+                first_row = (e0s == 0) ? 0 : item_start_row(p, e0s);
+                first_row_end = __ldg(p.ptr + first_row + 1);
+                first_row_begin = __ldg(p.ptr + first_row);
+            }
         }
         __syncwarp();
         if (nb > 0) mbar_wait(bar, 0);
@@ -114,9 +137,9 @@ __global__ void __launch_bounds__(kCtaThreads) agg_kernel(const AggParams p)
         const bool act0 = col < F;
         const bool act1 = (NV > 1) && (col + LPR * 4 < F);
 
-        int row = (e0 == 0) ? 0 : __ldg(p.item_row + e0 / kFineItem);
-        int row_end = __ldg(p.ptr + row + 1);
-        bool carry_in = SCHED ? false : (__ldg(p.ptr + row) < e0);
+        int row = first_row;
+        int row_end = first_row_end;
+        bool carry_in = SCHED ? false : (first_row_begin < e0);
         float a_dst = 0.f;
         if (MODE == kModeGAT) a_dst = __ldg(p.att + 2 * (size_t)(SCHED ? __ldg(p.target + row) : row));
 
@@ -151,6 +174,10 @@ __global__ void __launch_bounds__(kCtaThreads) agg_kernel(const AggParams p)
                     acc0 = make_float4(acc0.x * inv, acc0.y * inv, acc0.z * inv, acc0.w * inv);
                     acc1 = make_float4(acc1.x * inv, acc1.y * inv, acc1.z * inv, acc1.w * inv);
                 }
+                if (MODE == kModeGCN && p.accumulate) {  // each row is stored by exactly one item: plain RMW is safe
+                    if (act0) acc0 = add4(acc0, *reinterpret_cast<const float4 *>(y));
+                    if (act1) acc1 = add4(acc1, *reinterpret_cast<const float4 *>(y + LPR * 4));
+                }
                 if (act0) stg_f4(y, acc0);
                 if (act1) stg_f4(y + LPR * 4, acc1);
             }
@@ -178,7 +205,7 @@ __global__ void __launch_bounds__(kCtaThreads) agg_kernel(const AggParams p)
         const int second = act1 ? LPR * 16 : 0;  // byte offset of the second float4 (NV == 2)
 
         // ---- full batches: U edges, idx/val fetched as 128-bit shared loads (e - wbase is a multiple
-        // of U here because items start on multiples of 128 and only the last batch can be short)
+        // of U here because items start on multiples of U and only the last batch can be short)
         while (e + U <= e1) {
             const int k = e - wbase;
             int src[U];
@@ -279,6 +306,10 @@ __global__ void __launch_bounds__(kCtaThreads) agg_kernel(const AggParams p)
             if (MODE == kModeGAT && vl == 0 && cb == 0) p.carry_den[item] = den;
         } else {
             float *y = p.Y + (size_t)row * F + col;  // row starts here and continues: raw partial
+            if (MODE == kModeGCN && p.accumulate) {
+                if (act0) acc0 = add4(acc0, *reinterpret_cast<const float4 *>(y));
+                if (act1) acc1 = add4(acc1, *reinterpret_cast<const float4 *>(y + LPR * 4));
+            }
             if (act0) stg_f4(y, acc0);
             if (act1) stg_f4(y + LPR * 4, acc1);
             if (MODE == kModeGAT && vl == 0 && cb == 0) p.den_row[row] = den;
@@ -286,43 +317,65 @@ __global__ void __launch_bounds__(kCtaThreads) agg_kernel(const AggParams p)
     }
 }
 
-// Adds the carried partials of rows that cross item boundaries, in item order.
-// One warp per item; only the first carry item of a row does the work for that row.
-template <int MODE>
+// Adds the carried partials of rows that cross item boundaries, in a fixed order (deterministic).
+// One warp per item.  Two passes so that a hub row spanning thousands of items is not summed by a
+// single warp:  PHASE 1 -- every kFixChunk-th carry item of a row ("chunk head") sums its chunk of up
+// to kFixChunk consecutive partials; rows whose whole span fits one chunk are finished here.
+// PHASE 2 -- the first carry item of a long row adds the chunk heads and finishes the row.
+constexpr int kFixChunk = 32;
+
+template <int MODE, int PHASE>
 __global__ void __launch_bounds__(256) agg_fixup_kernel(const AggParams p, int EB, int64_t num_items)
 {
     const int64_t item = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (item < 1 || item >= num_items) return;
     const int e0 = (int)(item * EB);
-    const int row = __ldg(p.item_row + e0 / kFineItem);
+    const int row = item_start_row(p, e0);
     const int rs = __ldg(p.ptr + row);
-    if (rs >= e0) return;                  // no row enters this item
-    if (item != (int64_t)(rs / EB) + 1) return;  // not the first carry item of that row
-    const int re = __ldg(p.ptr + row + 1);
-    const int64_t last = (int64_t)(re - 1) / EB;  // item holding the row's last edge
-    const int F = p.F;
-    float dsum = 0.f;
-    if (MODE == kModeGAT) {
-        dsum = p.den_row[row];
-        for (int64_t b = item; b <= last; ++b) dsum += p.carry_den[b];
+    if (rs >= e0) return;  // no row enters this item
+    const int64_t first = (int64_t)(rs / EB) + 1;                       // first carry item of that row
+    const int64_t last = (int64_t)(__ldg(p.ptr + row + 1) - 1) / EB;    // item holding the row's last edge
+    const bool long_span = (last - first) >= kFixChunk;
+    int64_t b0, b1, step;
+    if (PHASE == 1) {
+        if ((item - first) % kFixChunk != 0) return;
+        b0 = item, b1 = min(last, item + kFixChunk - 1), step = 1;
+    } else {
+        if (item != first || !long_span) return;
+        b0 = first, b1 = last, step = kFixChunk;
     }
-    const float inv = (MODE == kModeGAT) ? ((dsum != 0.f) ? __fdividef(1.f, dsum) : 0.f) : 1.f;
+    const bool finish = (PHASE == 2) || !long_span;
+    const int F = p.F;
+    float dsum = 0.f, inv = 1.f;
+    if (MODE == kModeGAT) {
+        for (int64_t b = b0; b <= b1; b += step) dsum += p.carry_den[b];
+        if (finish) {
+            dsum += p.den_row[row];
+            inv = (dsum != 0.f) ? __fdividef(1.f, dsum) : 0.f;
+        }
+    }
     for (int col = lane * 4; col < F; col += 128) {
-        float *y = p.Y + (size_t)row * F + col;
-        float4 acc = *reinterpret_cast<const float4 *>(y);
-        int64_t b = item;
-        for (; b + 4 <= last + 1; b += 4) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int64_t b = b0;
+        for (; b + 3 * step <= b1; b += 4 * step) {
             const float4 c0 = *reinterpret_cast<const float4 *>(p.carry + (size_t)b * F + col);
-            const float4 c1 = *reinterpret_cast<const float4 *>(p.carry + (size_t)(b + 1) * F + col);
-            const float4 c2 = *reinterpret_cast<const float4 *>(p.carry + (size_t)(b + 2) * F + col);
-            const float4 c3 = *reinterpret_cast<const float4 *>(p.carry + (size_t)(b + 3) * F + col);
+            const float4 c1 = *reinterpret_cast<const float4 *>(p.carry + (size_t)(b + step) * F + col);
+            const float4 c2 = *reinterpret_cast<const float4 *>(p.carry + (size_t)(b + 2 * step) * F + col);
+            const float4 c3 = *reinterpret_cast<const float4 *>(p.carry + (size_t)(b + 3 * step) * F + col);
             acc = add4(add4(add4(add4(acc, c0), c1), c2), c3);
         }
-        for (; b <= last; ++b) acc = add4(acc, *reinterpret_cast<const float4 *>(p.carry + (size_t)b * F + col));
-        if (MODE == kModeGAT) acc = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
-        stg_f4(y, acc);
+        for (; b <= b1; b += step) acc = add4(acc, *reinterpret_cast<const float4 *>(p.carry + (size_t)b * F + col));
+        if (finish) {
+            float *y = p.Y + (size_t)row * F + col;
+            acc = add4(*reinterpret_cast<const float4 *>(y), acc);
+            if (MODE == kModeGAT) acc = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+            stg_f4(y, acc);
+        } else {
+            stg_f4(p.carry + (size_t)item * F + col, acc);  // chunk head now holds the chunk sum
+        }
     }
+    if (MODE == kModeGAT && !finish && lane == 0) p.carry_den[item] = dsum;
 }
 
 // scheduled GAT epilogue: Y[v,:] /= den[v] when den != 0  (scaleArray, aggr_gat.h:207-213)

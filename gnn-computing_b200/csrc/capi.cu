@@ -85,7 +85,9 @@ struct gnnagg_aggregator {
     int neighbor_group_size = 0, locality_partition_num = 0;
     int *s_ptr = nullptr, *s_idx = nullptr, *s_target = nullptr, *s_perm = nullptr, *s_item_row = nullptr;
     float *s_val = nullptr;  // owned only when s_perm != nullptr (locality kinds); NG aliases d_val
+    bool s_idx_owned = false;  // neighbour grouping keeps the edge order: its idx aliases d_idx
     int64_t launches = 0;
+    int warp_edges = 0;  // 0 = automatic
     // optional per-kernel timing (gnnagg_profile_enable)
     bool prof = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // begin, agg0, agg1, agg_end, end
@@ -139,7 +141,8 @@ static int build_item_rows(gnnagg_aggregator *a, const int *d_ptr, int rows, int
 static void free_schedule(gnnagg_aggregator *a)
 {
     cudaFree(a->s_ptr);
-    cudaFree(a->s_idx);
+    if (a->s_idx_owned) cudaFree(a->s_idx);
+    a->s_idx_owned = false;
     cudaFree(a->s_target);
     cudaFree(a->s_item_row);
     if (a->s_perm) cudaFree(a->s_val);
@@ -166,28 +169,55 @@ static int check_feat(int F)
 // lanes per virtual warp for a feature width
 static inline int lpr_for(int F) { return F <= 32 ? 8 : (F <= 64 ? 16 : 32); }
 
+// graphs below this many edges use the 128-edge-per-warp variant: with 512 there would be fewer than
+// ~2 waves of CTAs on 148 SMs and the kernel would be bound by the length of one warp's walk
+constexpr int64_t kSmallGraphEdges = 4000000;
+
+static inline int warp_edges_for(const gnnagg_aggregator *a, int64_t num_edges)
+{
+    if (a->warp_edges) return a->warp_edges;
+    return num_edges < kSmallGraphEdges ? 128 : kWarpEdges;
+}
+static inline int item_edges_for(const gnnagg_aggregator *a, int F, int64_t num_edges)
+{
+    return warp_edges_for(a, num_edges) / (32 / lpr_for(F));
+}
+
+template <int MODE, bool SCHED, int WE>
+static void launch_agg_we(const AggParams &p, cudaStream_t st)
+{
+    const int F = p.F;
+    const unsigned grid = (unsigned)cdiv(p.num_edges, (int64_t)WE * kCtaWarps);
+    if (F <= 32)
+        agg_kernel<8, 1, MODE, SCHED, WE><<<grid, kCtaThreads, 0, st>>>(p);
+    else if (F <= 64)
+        agg_kernel<16, 1, MODE, SCHED, WE><<<grid, kCtaThreads, 0, st>>>(p);
+    else if (F <= 128)
+        agg_kernel<32, 1, MODE, SCHED, WE><<<grid, kCtaThreads, 0, st>>>(p);
+    else
+        agg_kernel<32, 2, MODE, SCHED, WE><<<grid, kCtaThreads, 0, st>>>(p);
+}
+
 template <int MODE, bool SCHED>
 static int launch_agg(gnnagg_aggregator *a, const AggParams &p, cudaStream_t st)
 {
-    const int F = p.F;
-    const unsigned grid = (unsigned)cdiv(p.num_edges, (int64_t)kWarpEdges * kCtaWarps);
     PROF_RECORD(a, 1, st);
-    if (F <= 32)
-        agg_kernel<8, 1, MODE, SCHED><<<grid, kCtaThreads, 0, st>>>(p);
-    else if (F <= 64)
-        agg_kernel<16, 1, MODE, SCHED><<<grid, kCtaThreads, 0, st>>>(p);
-    else if (F <= 128)
-        agg_kernel<32, 1, MODE, SCHED><<<grid, kCtaThreads, 0, st>>>(p);
+    if (warp_edges_for(a, p.num_edges) == 128)
+        launch_agg_we<MODE, SCHED, 128>(p, st);
     else
-        agg_kernel<32, 2, MODE, SCHED><<<grid, kCtaThreads, 0, st>>>(p);
+        launch_agg_we<MODE, SCHED, kWarpEdges>(p, st);
     LAUNCH_CHECK(a);
     PROF_RECORD(a, 2, st);
     if (!SCHED) {
-        const int EB = kWarpEdges / (32 / lpr_for(F));
+        const int EB = item_edges_for(a, p.F, p.num_edges);
         const int64_t items = cdiv(p.num_edges, EB);
         if (items > 1) {
-            agg_fixup_kernel<MODE><<<(unsigned)cdiv(items, 8), 256, 0, st>>>(p, EB, items);
+            agg_fixup_kernel<MODE, 1><<<(unsigned)cdiv(items, 8), 256, 0, st>>>(p, EB, items);
             LAUNCH_CHECK(a);
+            if (items > kFixChunk + 1) {  // a row can only span more than kFixChunk carry items then
+                agg_fixup_kernel<MODE, 2><<<(unsigned)cdiv(items, 8), 256, 0, st>>>(p, EB, items);
+                LAUNCH_CHECK(a);
+            }
         }
     }
     return GNNAGG_OK;
@@ -195,7 +225,8 @@ static int launch_agg(gnnagg_aggregator *a, const AggParams &p, cudaStream_t st)
 
 static int aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-static int gcn_run_core(gnnagg_aggregator *a, const float *X, float *Y, int F, int scheduled, cudaStream_t st)
+static int gcn_run_core(gnnagg_aggregator *a, const float *X, float *Y, int F, int scheduled, cudaStream_t st,
+                        int accumulate = 0)
 {
     if (a && a->n == 0) return GNNAGG_OK;  // an empty row block (possible after edge-balanced partitioning)
     if (!a || !X || !Y) return set_error(GNNAGG_ERR_ARG, "gnnagg_gcn_run: NULL argument");
@@ -217,15 +248,18 @@ static int gcn_run_core(gnnagg_aggregator *a, const float *X, float *Y, int F, i
         p.item_row = a->s_item_row;
         p.num_rows = a->num_target;
         p.num_edges = a->sched_edges;
+        p.num_fine_items = a->sched_items;
         p.bulk_ok = aligned16(p.idx) && aligned16(p.val);
         return launch_agg<kModeGCN, true>(a, p, st);
     }
     if (a->m == 0) {
-        CUDA_TRY(cudaMemsetAsync(Y, 0, (size_t)a->n * F * sizeof(float), st));
+        if (!accumulate) CUDA_TRY(cudaMemsetAsync(Y, 0, (size_t)a->n * F * sizeof(float), st));
         return GNNAGG_OK;
     }
-    const int EB = kWarpEdges / (32 / lpr_for(F));
+    const int EB = item_edges_for(a, F, a->m);
     if (int rc = ensure(a->carry, a->carry_cap, (size_t)cdiv(a->m, EB) * F)) return rc;
+    p.num_fine_items = a->num_items;
+    p.accumulate = accumulate;
     p.ptr = a->d_ptr;
     p.idx = a->d_idx;
     p.val = a->d_val;
@@ -265,6 +299,7 @@ static int gat_run_core(gnnagg_aggregator *a, const float *X, const float *att, 
         p.newval = a->newval;
         p.num_rows = a->num_target;
         p.num_edges = a->sched_edges;
+        p.num_fine_items = a->sched_items;
         p.bulk_ok = aligned16(p.idx);
         if (int rc = launch_agg<kModeGAT, true>(a, p, st)) return rc;
         const int64_t total4 = (int64_t)a->n * F / 4;
@@ -276,9 +311,10 @@ static int gat_run_core(gnnagg_aggregator *a, const float *X, const float *att, 
         CUDA_TRY(cudaMemsetAsync(Y, 0, (size_t)a->n * F * sizeof(float), st));
         return GNNAGG_OK;
     }
-    const int EB = kWarpEdges / (32 / lpr_for(F));
+    const int EB = item_edges_for(a, F, a->m);
     if (int rc = ensure(a->carry, a->carry_cap, (size_t)cdiv(a->m, EB) * F)) return rc;
-    if (int rc = ensure(a->carry_den, a->carry_den_cap, (size_t)a->num_items)) return rc;
+    if (int rc = ensure(a->carry_den, a->carry_den_cap, (size_t)cdiv(a->m, EB))) return rc;
+    p.num_fine_items = a->num_items;
     p.ptr = a->d_ptr;
     p.idx = a->d_idx;
     p.item_row = a->d_item_row;
@@ -292,14 +328,14 @@ static int gat_run_core(gnnagg_aggregator *a, const float *X, const float *att, 
 
 // timing brackets: ev[0] call entry, ev[3] end of the aggregation part, ev[4] end of the call
 static int gcn_run_impl(gnnagg_aggregator *a, const float *X, float *Y, int F, int scheduled, cudaStream_t st,
-                        bool last = true)
+                        bool last = true, int accumulate = 0)
 {
     if (a) PROF_RECORD(a, 0, st);
     if (a && a->prof) {  // so that a call that launches no aggregation kernel still reads as 0 ms
         CUDA_TRY(cudaEventRecord(a->ev[1], st));
         CUDA_TRY(cudaEventRecord(a->ev[2], st));
     }
-    if (int rc = gcn_run_core(a, X, Y, F, scheduled, st)) return rc;
+    if (int rc = gcn_run_core(a, X, Y, F, scheduled, st, accumulate)) return rc;
     PROF_RECORD(a, 3, st);
     if (last) PROF_RECORD(a, 4, st);
     return GNNAGG_OK;
@@ -332,8 +368,12 @@ static int rowsum_impl(gnnagg_aggregator *a, const float *in, float *out, cudaSt
     rowsum_kernel<<<grid, 256, 0, st>>>(g, in, out, a->carry_den);
     LAUNCH_CHECK(a);
     if (a->num_items > 1) {
-        rowsum_fixup_kernel<<<grid, 256, 0, st>>>(g, out, a->carry_den);
+        rowsum_fixup_kernel<1><<<grid, 256, 0, st>>>(g, out, a->carry_den);
         LAUNCH_CHECK(a);
+        if (a->num_items > kRowsumChunk + 1) {
+            rowsum_fixup_kernel<2><<<grid, 256, 0, st>>>(g, out, a->carry_den);
+            LAUNCH_CHECK(a);
+        }
     }
     return GNNAGG_OK;
 }
@@ -424,7 +464,9 @@ int gnnagg_schedule_apply(gnnagg_aggregator *a, int kind, const int *params, int
     if (!a || !params || nparams < 1) return set_error(GNNAGG_ERR_ARG, "gnnagg_schedule_apply: bad argument");
     if (kind == GNNAGG_SCHED_LOCALITY_NEIGHBOR_GROUPING && nparams < 2)
         return set_error(GNNAGG_ERR_ARG, "locality_neighbor_grouping needs {par_num, neighbor_num}");
-    // host mirror of the CSR
+    // host mirror of the CSR (neighbour grouping only needs the row pointers: its idx_vec is a
+    // verbatim copy of idx, graph_schedule.h:123-124, so the device idx is aliased instead)
+    const bool need_idx = (kind != GNNAGG_SCHED_NEIGHBOR_GROUPING);
     const int *hp = a->h_ptr_user, *hi = a->h_idx_user;
     if (!hp) {
         if (a->h_ptr.empty()) {
@@ -433,7 +475,9 @@ int gnnagg_schedule_apply(gnnagg_aggregator *a, int kind, const int *params, int
         }
         hp = a->h_ptr.data();
     }
-    if (!hi) {
+    if (!need_idx) {
+        hi = nullptr;
+    } else if (!hi) {
         if (a->h_idx.empty() && a->m > 0) {
             a->h_idx.resize((size_t)a->m);
             CUDA_TRY(cudaMemcpy(a->h_idx.data(), a->d_idx, a->h_idx.size() * sizeof(int), cudaMemcpyDeviceToHost));
@@ -460,14 +504,19 @@ int gnnagg_schedule_apply(gnnagg_aggregator *a, int kind, const int *params, int
     a->neighbor_group_size = ng;
     a->locality_partition_num = par;
     a->num_target = (int)s.target.size();
-    a->sched_edges = (int)s.idx.size();
+    a->sched_edges = need_idx ? (int)s.idx.size() : a->m;
     auto upload = [&](int **dst, const void *src, size_t count) -> int {
         CUDA_TRY(cudaMalloc((void **)dst, (count ? count : 1) * sizeof(int)));
         if (count) CUDA_TRY(cudaMemcpy(*dst, src, count * sizeof(int), cudaMemcpyHostToDevice));
         return GNNAGG_OK;
     };
     if (int rc = upload(&a->s_ptr, s.ptr.data(), s.ptr.size())) return rc;
-    if (int rc = upload(&a->s_idx, s.idx.data(), s.idx.size())) return rc;
+    if (need_idx) {
+        if (int rc = upload(&a->s_idx, s.idx.data(), s.idx.size())) return rc;
+        a->s_idx_owned = true;
+    } else {
+        a->s_idx = const_cast<int *>(a->d_idx);
+    }
     if (int rc = upload(&a->s_target, s.target.data(), s.target.size())) return rc;
     if (permuting)
         if (int rc = upload(&a->s_perm, s.perm.data(), s.perm.size())) return rc;
@@ -485,6 +534,14 @@ const int *gnnagg_sched_dev_target(const gnnagg_aggregator *a) { return a ? a->s
 const float *gnnagg_sched_dev_val(const gnnagg_aggregator *a) { return a ? a->s_val : nullptr; }
 const float *gnnagg_gat_edge_weights(const gnnagg_aggregator *a) { return a ? a->newval : nullptr; }
 int64_t gnnagg_launch_count(const gnnagg_aggregator *a) { return a ? a->launches : 0; }
+
+int gnnagg_set_warp_edges(gnnagg_aggregator *a, int warp_edges)
+{
+    if (!a || (warp_edges != 0 && warp_edges != 128 && warp_edges != 512))
+        return set_error(GNNAGG_ERR_ARG, "gnnagg_set_warp_edges: 0, 128 or 512");
+    a->warp_edges = warp_edges;
+    return GNNAGG_OK;
+}
 
 int gnnagg_profile_enable(gnnagg_aggregator *a, int on)
 {
@@ -522,6 +579,11 @@ int gnnagg_memcpy_d2h(void *h_dst, const void *d_src, uint64_t bytes)
 int gnnagg_gcn_run(gnnagg_aggregator *a, const float *X, float *Y, int feat, int scheduled, void *stream)
 {
     return gcn_run_impl(a, X, Y, feat, scheduled, (cudaStream_t)stream);
+}
+
+int gnnagg_gcn_run_acc(gnnagg_aggregator *a, const float *X, float *Y, int feat, int accumulate, void *stream)
+{
+    return gcn_run_impl(a, X, Y, feat, 0, (cudaStream_t)stream, true, accumulate != 0);
 }
 
 int gnnagg_gat_run(gnnagg_aggregator *a, const float *X, const float *att, float *Y, int feat, float slope,

@@ -97,19 +97,36 @@ __global__ void __launch_bounds__(256) rowsum_kernel(const EdgeParams g, const f
     }
 }
 
+// two-pass, fixed-order combination of the per-item partials (see agg_fixup_kernel)
+constexpr int kRowsumChunk = 64;
+
+template <int PHASE>
 __global__ void __launch_bounds__(256) rowsum_fixup_kernel(const EdgeParams g, float *__restrict__ out,
-                                                           const float *__restrict__ carry)
+                                                           float *__restrict__ carry)
 {
     const int item = blockIdx.x * blockDim.x + threadIdx.x;
     if (item < 1 || item >= g.num_items) return;
     const int e0 = item * kFineItem;
     const int row = __ldg(g.item_row + item);
     const int rs = __ldg(g.ptr + row);
-    if (rs >= e0 || item != rs / kFineItem + 1) return;
+    if (rs >= e0) return;
+    const int first = rs / kFineItem + 1;
     const int last = (__ldg(g.ptr + row + 1) - 1) / kFineItem;
-    float acc = out[row];
-    for (int b = item; b <= last; ++b) acc += carry[b];
-    out[row] = acc;
+    const bool long_span = (last - first) >= kRowsumChunk;
+    int b0, b1, step;
+    if (PHASE == 1) {
+        if ((item - first) % kRowsumChunk != 0) return;
+        b0 = item, b1 = min(last, item + kRowsumChunk - 1), step = 1;
+    } else {
+        if (item != first || !long_span) return;
+        b0 = first, b1 = last, step = kRowsumChunk;
+    }
+    float acc = 0.f;
+    for (int b = b0; b <= b1; b += step) acc += carry[b];
+    if (PHASE == 2 || !long_span)
+        out[row] += acc;
+    else
+        carry[item] = acc;
 }
 
 // SDDMM: out[e] = <X1[idx[e], 0:F], X2[row(e), 0:F]>   (aggr_sddmm.h:17-41; target variant :45-83)

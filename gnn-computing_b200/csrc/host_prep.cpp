@@ -37,7 +37,7 @@ static int build_neighbor_grouping(const int *ptr, const int *idx, int num_v, in
     for (int i = 0; i < num_v; ++i) total += ((int64_t)ptr[i + 1] - ptr[i] + ng - 1) / ng;
     s->ptr.resize((size_t)total + 1);
     s->target.resize((size_t)total);
-    s->idx.assign(idx, idx + num_e);  // verbatim copy (:123-124)
+    if (idx) s->idx.assign(idx, idx + num_e);  // verbatim copy (:123-124); internal callers that alias idx pass NULL
     int64_t g = 0;
     s->ptr[0] = 0;
     for (int i = 0; i < num_v; ++i) {

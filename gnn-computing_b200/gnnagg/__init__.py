@@ -64,6 +64,7 @@ _SIGS = {
     "gnnagg_sched_dev_target": (C.c_void_p, [C.c_void_p]),
     "gnnagg_sched_dev_val": (C.c_void_p, [C.c_void_p]),
     "gnnagg_gcn_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "gnnagg_gcn_run_acc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "gnnagg_gcn_run_edgewise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "gnnagg_csr2edgelist": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "gnnagg_gcn_layer": (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_int, C.c_void_p]),
@@ -83,6 +84,7 @@ _SIGS = {
     "gnnagg_gcn_layer_host": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "gnnagg_gat_run_host": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_float, C.c_int, C.c_void_p]),
     "gnnagg_launch_count": (C.c_int64, [C.c_void_p]),
+    "gnnagg_set_warp_edges": (C.c_int, [C.c_void_p, C.c_int]),
     "gnnagg_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "gnnagg_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "gnnagg_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
@@ -263,6 +265,9 @@ class Aggregator:
     def launches(self):
         return lib().gnnagg_launch_count(self.h)
 
+    def set_warp_edges(self, warp_edges):
+        check(lib().gnnagg_set_warp_edges(self.h, int(warp_edges)))
+
     def profile(self, on=True):
         check(lib().gnnagg_profile_enable(self.h, int(on)))
 
@@ -294,6 +299,10 @@ class Aggregator:
     # --- GCN
     def gcn_run(self, X, Y, scheduled=False):
         check(lib().gnnagg_gcn_run(self.h, _dp(X), _dp(Y), X.shape[1], int(scheduled), _stream()))
+        return Y
+
+    def gcn_run_acc(self, X, Y, accumulate=True):
+        check(lib().gnnagg_gcn_run_acc(self.h, _dp(X), _dp(Y), X.shape[1], int(accumulate), _stream()))
         return Y
 
     def gcn_run_edgewise(self, X, Y):

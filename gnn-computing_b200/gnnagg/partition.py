@@ -59,3 +59,82 @@ def all_gather_rows(x_shard, bounds, group=None):
                 dist.broadcast(full[int(bounds[p]):int(bounds[p + 1])], src=dist.get_global_rank(group, p) if group else p,
                                group=group)
     return full
+
+
+# ------------------------------------------------------------------------------------------------
+# pipelined halo exchange: the all-gather of X is cut into `chunks` row chunks and the rank's row block
+# is split by the chunk its SOURCE falls into (the same idea as the slices of the reference's
+# locality_schedule, graph_schedule.h:24-29, applied to the communication order).  Chunk c of every
+# shard is gathered into its own buffer Xc[c] = [world, rows_c, F]; the sub-CSR of chunk c indexes that
+# buffer directly and is accumulated (gnnagg_gcn_run_acc) as soon as all-gather c has completed, while
+# all-gather c+1 is in flight.  Edges whose source lives on this rank need no communication: their
+# sub-CSR runs first, hiding the first all-gather.
+# ------------------------------------------------------------------------------------------------
+def chunk_rows(n_per, chunks):
+    """[chunks+1] row boundaries of the chunks inside one shard of n_per rows"""
+    step = -(-n_per // chunks)
+    return [min(n_per, c * step) for c in range(chunks + 1)]
+
+
+def split_by_source_chunk(ptr, idx, val, n_per, world, rank, chunks):
+    """torch tensors (any device).  Returns a list of (ptr_c, idx_c, val_c); entry 0 = edges whose source
+    is owned by `rank` (idx_c = local row in this rank's X shard), entry 1+c = remote edges whose source
+    falls in chunk c (idx_c = owner * rows_c + offset inside the chunk, an index into Xc[c])."""
+    import torch
+
+    n = ptr.numel() - 1
+    deg = (ptr[1:] - ptr[:-1]).long()
+    row = torch.repeat_interleave(torch.arange(n, device=ptr.device), deg)
+    g = idx.long()
+    owner, local = g // n_per, g % n_per
+    cb = chunk_rows(n_per, chunks)
+    bounds = torch.tensor(cb, device=ptr.device)
+    chunk = torch.bucketize(local, bounds[1:], right=True)  # chunk c: cb[c] <= local < cb[c+1]
+    own = owner == rank
+    out = []
+
+    def sub(mask, new_idx):
+        cnt = torch.bincount(row[mask], minlength=n)
+        p = torch.zeros(n + 1, dtype=torch.int64, device=ptr.device)
+        p[1:] = torch.cumsum(cnt, 0)
+        return p.to(torch.int32), new_idx.to(torch.int32).contiguous(), val[mask].contiguous()
+
+    out.append(sub(own, local[own]))
+    for c in range(chunks):
+        mask = (~own) & (chunk == c)
+        rows_c = cb[c + 1] - cb[c]
+        out.append(sub(mask, owner[mask] * rows_c + (local[mask] - cb[c])))
+    return out
+
+
+class HaloPipeline:
+    """per-rank driver of the pipelined exchange + aggregation (device side; one process per GPU)"""
+
+    def __init__(self, ptr, idx, val, n_per, world, rank, feat, chunks=4, group=None):
+        import torch
+
+        from . import Aggregator
+
+        self.n, self.n_per, self.world, self.rank, self.F, self.group = ptr.numel() - 1, n_per, world, rank, feat, group
+        self.cb = chunk_rows(n_per, chunks)
+        self.chunks = chunks
+        parts = split_by_source_chunk(ptr, idx, val, n_per, world, rank, chunks)
+        self.aggs = [Aggregator(p, i, v) for p, i, v in parts]
+        self.edges = [int(i.numel()) for _, i, _ in parts]
+        self.Xc = [torch.empty((world * (self.cb[c + 1] - self.cb[c]), feat), device=ptr.device) for c in range(chunks)]
+
+    def aggregate(self, Xs, Y):
+        """Y = A_block * X_full with X_full never materialised contiguously"""
+        import torch.distributed as dist
+
+        works = [dist.all_gather_into_tensor(self.Xc[c], Xs[self.cb[c]:self.cb[c + 1]], group=self.group, async_op=True)
+                 for c in range(self.chunks)]
+        self.aggs[0].gcn_run_acc(Xs, Y, accumulate=False)  # local sources: overlaps the first all-gather
+        for c in range(self.chunks):
+            works[c].wait()  # stream-level dependency, the host does not block
+            self.aggs[1 + c].gcn_run_acc(self.Xc[c], Y, accumulate=True)
+        return Y
+
+    @property
+    def launches(self):
+        return sum(a.launches for a in self.aggs)

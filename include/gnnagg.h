@@ -138,6 +138,12 @@ const float *gnnagg_sched_dev_val(const gnnagg_aggregator *a);
  * [scheduled=1].  Y is fully overwritten in both modes (the reference memsets, :393). */
 int gnnagg_gcn_run(gnnagg_aggregator *a, const float *X, float *Y, int feat, int scheduled, void *stream);
 
+/* Y += A*X (accumulate != 0) or Y = A*X on the un-scheduled CSR.  Building block of the multi-GPU
+ * pipeline: a rank's row block is split by SOURCE shard (the slices of locality_schedule,
+ * graph_schedule.h:24-29) and every slice is accumulated as soon as its shard of X has arrived.  With
+ * accumulate = 0 it is gnnagg_gcn_run(scheduled = 0).  Deterministic (no atomics). */
+int gnnagg_gcn_run_acc(gnnagg_aggregator *a, const float *X, float *Y, int feat, int accumulate, void *stream);
+
 /* edge-parallel variant: replaces Aggregator_GCN::runEdgeWise + aggr_gcn_edgewise
  * (aggr_gcn.h:291-302,445-460) and Aggregator::csr2edgelist (aggregator.h:115-122).
  * Any feat (the reference is F=32 only). */
@@ -205,6 +211,11 @@ int gnnagg_gcn_layer_host(gnnagg_aggregator *a, const float *h_X, const float *h
                           int feat_out, int scheduled, void *stream);
 int gnnagg_gat_run_host(gnnagg_aggregator *a, const float *h_X, const float *h_att, float *h_Y, int feat,
                         float slope, int scheduled, void *stream);
+
+/* tuning knob (the reference's analogue is the BLOCK_SIZE argument of run(), aggr_gcn.h:381-386):
+ * edges staged per warp by the aggregation kernels: 0 = automatic (128 below 4M edges, else 512),
+ * or force 128 / 512.  Results do not depend on it beyond fp32 summation order. */
+int gnnagg_set_warp_edges(gnnagg_aggregator *a, int warp_edges);
 
 /* per-kernel device timing of the LAST gnnagg_gcn_run / gnnagg_gat_run / gnnagg_gcn_layer call:
  * when enabled the library brackets its launches with CUDA events on the caller's stream.

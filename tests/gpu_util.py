@@ -32,6 +32,7 @@ GRAPHS = {
     "short_rows": (3000, 3.0, 0.3, 0),
     "medium": (700, 40.0, 0.1, 0),
     "hub": (300, 8.0, 0.2, 9000),          # one row far longer than an item
+    "bighub": (60, 4.0, 0.2, 40000),       # spans > 32 items of 512 edges: two-pass fix-up
     "leading_trailing_empty": (-1, 0, 0, 0),  # built by hand below
     "exact_items": (-2, 0, 0, 0),
 }

@@ -18,12 +18,14 @@ def _att(n, seed):
 
 @pytest.mark.parametrize("gname", list(GRAPHS))
 @pytest.mark.parametrize("F", [32, 64, 128, 256])
-def test_gat_fused_unscheduled(gn, orc, cuda, gname, F):
+@pytest.mark.parametrize("we", [128, 512])
+def test_gat_fused_unscheduled(gn, orc, cuda, gname, F, we):
     ptr, idx = make_graph(gname, seed=F + 1)
     n, m = len(ptr) - 1, len(idx)
     X, _ = rand_inputs(n, m, F, seed=13)
     att = _att(n, 14)
     agg = gn.Aggregator(dev(ptr), dev(idx))
+    agg.set_warp_edges(we)
     Y = agg.gat_run(dev(X), dev(att), torch.full((n, F), float("nan"), device=cuda))
     y64, den, scale = orc.gat_f64(ptr, idx, att, X)  # empty rows -> 0 (documented deviation from NaN)
     bad, worst = rel_gate(Y.cpu().numpy(), y64, scale, TOL)
@@ -41,6 +43,7 @@ def test_gat_fused_scheduled(gn, orc, cuda, ng, F):
     X, _ = rand_inputs(n, m, F, seed=15)
     att = _att(n, 16)
     agg = gn.Aggregator(dev(ptr), dev(idx))
+    agg.set_warp_edges(512 if ng == 16 else 128)
     agg.schedule(1, [ng])
     Y = agg.gat_run(dev(X), dev(att), torch.full((n, F), float("nan"), device=cuda), scheduled=True)
     y64, den, scale = orc.gat_f64(ptr, idx, att, X)

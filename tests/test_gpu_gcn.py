@@ -14,11 +14,13 @@ TOL = 1e-5
 
 @pytest.mark.parametrize("gname", list(GRAPHS))
 @pytest.mark.parametrize("F", [32, 64, 128, 256])
-def test_gcn_unscheduled_parity(gn, orc, cuda, gname, F):
+@pytest.mark.parametrize("we", [128, 512])
+def test_gcn_unscheduled_parity(gn, orc, cuda, gname, F, we):
     ptr, idx = make_graph(gname, seed=F)
     n, m = len(ptr) - 1, len(idx)
     X, val = rand_inputs(n, m, F, seed=1)
     agg = gn.Aggregator(dev(ptr), dev(idx), dev(val))
+    agg.set_warp_edges(we)  # both item sizes: the automatic choice would only pick 512 above 4M edges
     Y = torch.full((n, F), float("nan"), device=cuda)  # every element must be overwritten
     agg.gcn_run(dev(X), Y)
     y64, scale = orc.spmm_f64(ptr, idx, val, X)
@@ -76,6 +78,7 @@ def test_gcn_scheduled_parity_and_schedule_upload(gn, orc, cuda, kind, params, F
     n, m = len(ptr) - 1, len(idx)
     X, val = rand_inputs(n, m, F, seed=5)
     agg = gn.Aggregator(dev(ptr), dev(idx), dev(val))
+    agg.set_warp_edges(512 if F == 128 else 0)
     num_target = agg.schedule(kind, params)
     # the uploaded schedule is bit-identical to the reference semantics (oracle)
     if kind == 1:

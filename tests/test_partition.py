@@ -104,3 +104,61 @@ def test_partitioned_blocks_on_gpu_equal_single(gn, orc, cuda):
             assert np.all(err <= 1e-5 * scale + 1e-30)
             # same edges, possibly different item boundaries: equal within the same bound
             assert np.all(np.abs((Yp - ref).cpu().numpy()) <= 2e-5 * scale + 1e-30)
+
+
+def test_split_by_source_chunk_reassembles():
+    """sub-CSRs of the pipelined halo exchange: every edge lands in exactly one sub-CSR and the remapped
+    indices address the chunk buffers correctly (oracle as the aggregation)"""
+    import torch
+
+    import oracle as orc
+
+    world, n_per, F, chunks = 3, 50, 8, 4
+    rng = np.random.default_rng(5)
+    Xfull = rng.standard_normal((world * n_per, F)).astype(np.float32)
+    for rank in range(world):
+        ptr, idx = synth.small_random_csr(n_per, 9.0, 20 + rank, num_src=world * n_per, hub=300)
+        val = rng.standard_normal(len(idx)).astype(np.float32)
+        parts = partition.split_by_source_chunk(torch.from_numpy(ptr), torch.from_numpy(idx), torch.from_numpy(val),
+                                                n_per, world, rank, chunks)
+        assert sum(p[1].numel() for p in parts) == len(idx)
+        cb = partition.chunk_rows(n_per, chunks)
+        acc = np.zeros((n_per, F), np.float64)
+        Xs = Xfull[rank * n_per:(rank + 1) * n_per]
+        y, _ = orc.spmm_f64(parts[0][0].numpy(), parts[0][1].numpy(), parts[0][2].numpy(), np.ascontiguousarray(Xs))
+        acc += y
+        for c in range(chunks):
+            Xc = np.concatenate([Xfull[r * n_per + cb[c]: r * n_per + cb[c + 1]] for r in range(world)])  # all-gather c
+            p, i, v = (t.numpy() for t in parts[1 + c])
+            if len(i):
+                assert i.max() < len(Xc)
+            y, _ = orc.spmm_f64(p, i, v, np.ascontiguousarray(Xc))
+            acc += y
+        want, scale = orc.spmm_f64(ptr, idx, val, Xfull)
+        assert np.all(np.abs(acc - want) <= 1e-5 * scale + 1e-30)
+
+
+@pytest.mark.gpu
+def test_accumulate_mode_sums_sub_csrs(gn, orc, cuda):
+    """gnnagg_gcn_run_acc: Y = A0*X then Y += A1*X ... equals the un-split aggregation"""
+    import torch
+
+    world, n_per, F = 4, 700, 64
+    rng = np.random.default_rng(9)
+    ptr, idx = synth.small_random_csr(n_per, 30.0, 4, num_src=world * n_per, hub=5000)
+    val = rng.standard_normal(len(idx)).astype(np.float32)
+    Xfull = rng.standard_normal((world * n_per, F)).astype(np.float32)
+    rank, chunks = 1, 3
+    tp, ti, tv = (torch.from_numpy(a).to(cuda) for a in (ptr, idx, val))
+    parts = partition.split_by_source_chunk(tp, ti, tv, n_per, world, rank, chunks)
+    cb = partition.chunk_rows(n_per, chunks)
+    Y = torch.full((n_per, F), float("nan"), device=cuda)
+    dX = torch.from_numpy(Xfull).to(cuda)
+    aggs = [gn.Aggregator(*p) for p in parts]
+    aggs[0].gcn_run_acc(dX[rank * n_per:(rank + 1) * n_per].contiguous(), Y, accumulate=False)
+    for c in range(chunks):
+        Xc = torch.cat([dX[r * n_per + cb[c]: r * n_per + cb[c + 1]] for r in range(world)]).contiguous()
+        aggs[1 + c].gcn_run_acc(Xc, Y, accumulate=True)
+    want, scale = orc.spmm_f64(ptr, idx, val, Xfull)
+    err = np.abs(Y.cpu().numpy().astype(np.float64) - want)
+    assert np.all(err <= 1e-5 * scale + 1e-30)
