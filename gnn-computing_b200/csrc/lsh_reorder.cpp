@@ -15,10 +15,14 @@
 // Not a port of the script: signatures are computed in parallel over vertices, buckets come from
 // one sort per band instead of Python dicts, Jaccard is a sorted-list merge, the pair set is a
 // flat hash set of 64-bit keys.
+#include <parallel/algorithm>
+
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <queue>
-#include <unordered_set>
 #include <vector>
 
 #include "gnnagg.h"
@@ -49,6 +53,73 @@ struct PairOrder {  // priority_queue pops the LARGEST: higher similarity, then 
         if (a.lo != b.lo) return a.lo > b.lo;
         return a.hi > b.hi;
     }
+};
+
+// open-addressing set of 64-bit keys (the "pairs currently queued" set of cluster2.py:70,96,126);
+// linear probing, tombstones, grows at 70 % load.  Key 0 is stored shifted by one.
+class KeySet {
+public:
+    explicit KeySet(size_t expected) { rehash(expected * 2 + 16); }
+    bool contains(uint64_t k) const
+    {
+        k += 2;
+        for (size_t i = slot(k);; i = (i + 1) & mask_) {
+            if (tab_[i] == k) return true;
+            if (tab_[i] == kEmpty) return false;
+        }
+    }
+    void insert(uint64_t k)
+    {
+        if ((used_ + 1) * 10 > (mask_ + 1) * 7) rehash((live_ + 1) * 4);
+        k += 2;
+        size_t i = slot(k), grave = SIZE_MAX;
+        for (;; i = (i + 1) & mask_) {
+            if (tab_[i] == k) return;
+            if (tab_[i] == kTomb && grave == SIZE_MAX) grave = i;
+            if (tab_[i] == kEmpty) break;
+        }
+        if (grave != SIZE_MAX)
+            i = grave;
+        else
+            ++used_;
+        tab_[i] = k;
+        ++live_;
+    }
+    void erase(uint64_t k)
+    {
+        k += 2;
+        for (size_t i = slot(k);; i = (i + 1) & mask_) {
+            if (tab_[i] == k) {
+                tab_[i] = kTomb;
+                --live_;
+                return;
+            }
+            if (tab_[i] == kEmpty) return;
+        }
+    }
+
+private:
+    static constexpr uint64_t kEmpty = 0, kTomb = 1;
+    size_t slot(uint64_t k) const { return (size_t)(splitmix64(k)) & mask_; }
+    void rehash(size_t want)
+    {
+        size_t cap = 16;
+        while (cap < want) cap <<= 1;
+        std::vector<uint64_t> old;
+        old.swap(tab_);
+        tab_.assign(cap, kEmpty);
+        mask_ = cap - 1;
+        used_ = live_ = 0;
+        for (uint64_t k : old)
+            if (k > kTomb) {
+                size_t i = slot(k);
+                while (tab_[i] != kEmpty) i = (i + 1) & mask_;
+                tab_[i] = k;
+                ++used_, ++live_;
+            }
+    }
+    std::vector<uint64_t> tab_;
+    size_t mask_ = 0, used_ = 0, live_ = 0;
 };
 
 struct Reorderer {
@@ -103,11 +174,23 @@ extern "C" int gnnagg_lsh_reorder(const int *ptr, const int *idx, int num_v, int
     if (bands > 0 && (rows_per_band <= 0 || (int64_t)bands * rows_per_band > num_perm))
         return set_error(GNNAGG_ERR_ARG, "gnnagg_lsh_reorder: bands*rows_per_band must be <= num_perm");
     const int numv = num_v;
+    const bool trace = getenv("GNNAGG_REORDER_TRACE") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!trace) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[lsh_reorder] %-28s %.3f s\n", what, std::chrono::duration<double>(now - t_last).count());
+        t_last = now;
+    };
     Reorderer R{ptr, idx, numv, {}, {}};
     R.build_unique();
+    lap("unique neighbour lists");
 
-    // ---- candidate pairs -------------------------------------------------------------------
-    std::vector<std::vector<int>> cand((size_t)numv);
+    // ---- candidate pairs: unordered (lo,hi) keys, deduplicated by one sort -------------------------
+    // Candidates are symmetric and vertices are visited in ascending id (cluster2.py:80-96), so every
+    // pair is first met from its smaller endpoint: Pair(p1 = lo, p2 = hi).  Pairs that involve an
+    // empty row can only be met from the non-empty endpoint; they score 0 either way.
+    std::vector<uint64_t> keys;
     if (bands > 0) {
         std::vector<uint64_t> pa((size_t)num_perm), pb((size_t)num_perm);
         for (int k = 0; k < num_perm; ++k) {
@@ -128,31 +211,45 @@ extern "C" int gnnagg_lsh_reorder(const int *ptr, const int *idx, int num_v, int
                 }
             }
         }
-        std::vector<int> order((size_t)numv);
+        lap("minhash signatures");
+        std::vector<std::vector<uint64_t>> band_keys((size_t)bands);
+#pragma omp parallel for schedule(dynamic, 1)
         for (int j = 0; j < bands; ++j) {
-            for (int i = 0; i < numv; ++i) order[i] = i;
+            // one 64-bit bucket key per vertex (hash of the band's rows; equality re-checked below)
+            std::vector<std::pair<uint64_t, int>> order((size_t)numv);
             const uint32_t *base = sig.data() + (size_t)j * rows_per_band;
-            auto key_less = [&](int a, int b) {
-                const uint32_t *x = base + (size_t)a * used, *y = base + (size_t)b * used;
-                for (int r = 0; r < rows_per_band; ++r)
-                    if (x[r] != y[r]) return x[r] < y[r];
-                return a < b;  // members of a bucket ascending by id
-            };
-            auto key_eq = [&](int a, int b) {
+            for (int i = 0; i < numv; ++i) {
+                const uint32_t *x = base + (size_t)i * used;
+                uint64_t h = 0x243F6A8885A308D3ull;
+                for (int r = 0; r < rows_per_band; ++r) h = splitmix64(h ^ x[r]);
+                order[i] = {h, i};
+            }
+            std::sort(order.begin(), order.end());  // bucket members end up ascending by id
+            auto same = [&](int a, int b) {
                 const uint32_t *x = base + (size_t)a * used, *y = base + (size_t)b * used;
                 for (int r = 0; r < rows_per_band; ++r)
                     if (x[r] != y[r]) return false;
                 return true;
             };
-            std::sort(order.begin(), order.end(), key_less);
-            for (int s = 0; s < numv;) {
-                int e = s + 1;
-                while (e < numv && key_eq(order[s], order[e])) ++e;
-                for (int p = s; p < e; ++p)
-                    for (int q = std::max(s, p - kWindow); q < std::min(e, p + kWindow + 1); ++q)
-                        if (q != p) cand[order[p]].push_back(order[q]);
-                s = e;
+            std::vector<uint64_t> &out = band_keys[j];
+            for (int s0 = 0; s0 < numv;) {
+                int e0 = s0 + 1;
+                while (e0 < numv && order[e0].first == order[s0].first && same(order[s0].second, order[e0].second)) ++e0;
+                for (int p = s0; p < e0; ++p)
+                    for (int q = p + 1; q < std::min(e0, p + kWindow + 1); ++q) {
+                        const int a = order[p].second, b = order[q].second;  // a < b
+                        if (ptr[a] == ptr[a + 1] && ptr[b] == ptr[b + 1]) continue;  // two empty rows: never queried
+                        out.push_back(((uint64_t)a << 32) | (uint32_t)b);
+                    }
+                s0 = e0;
             }
+        }
+        size_t total = 0;
+        for (auto &v : band_keys) total += v.size();
+        keys.reserve(total);
+        for (auto &v : band_keys) {
+            keys.insert(keys.end(), v.begin(), v.end());
+            std::vector<uint64_t>().swap(v);
         }
     } else {  // exhaustive: every pair sharing a neighbour (test mode, small graphs)
         std::vector<std::vector<int>> owners;
@@ -162,34 +259,35 @@ extern "C" int gnnagg_lsh_reorder(const int *ptr, const int *idx, int num_v, int
         for (int i = 0; i < numv; ++i)
             for (int e = R.uptr[i]; e < R.uptr[i + 1]; ++e) owners[R.uidx[e]].push_back(i);
         for (auto &members : owners)
-            for (int a : members)
-                for (int b : members)
-                    if (a != b) cand[a].push_back(b);
+            for (size_t x = 0; x < members.size(); ++x)
+                for (size_t y = x + 1; y < members.size(); ++y)
+                    keys.push_back(((uint64_t)members[x] << 32) | (uint32_t)members[y]);
     }
-    for (auto &c : cand) {
-        std::sort(c.begin(), c.end());
-        c.erase(std::unique(c.begin(), c.end()), c.end());
-    }
+    lap("band buckets");
+    __gnu_parallel::sort(keys.begin(), keys.end());
+    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    lap("candidate dedup");
 
-    // ---- heap of scored pairs ----------------------------------------------------------------
+    // ---- scored pairs -> heap -----------------------------------------------------------------
     auto makenum = [numv](int a, int b) -> uint64_t {
         return a <= b ? (uint64_t)a * (uint64_t)numv + (uint64_t)b : (uint64_t)b * (uint64_t)numv + (uint64_t)a;
     };
-    std::priority_queue<Pair, std::vector<Pair>, PairOrder> heap;
-    std::unordered_set<uint64_t> sset;
+    std::vector<Pair> scored(keys.size());
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (int64_t k = 0; k < (int64_t)keys.size(); ++k) {
+        const int a = (int)(keys[k] >> 32), b = (int)(keys[k] & 0xFFFFFFFFu);
+        scored[k] = Pair{R.jaccard(a, b), a, b, a, b};
+    }
+    KeySet sset(keys.size());
+    for (uint64_t k : keys) sset.insert(makenum((int)(k >> 32), (int)(k & 0xFFFFFFFFu)));
+    std::vector<uint64_t>().swap(keys);
+    std::priority_queue<Pair, std::vector<Pair>, PairOrder> heap(PairOrder(), std::move(scored));  // heapify, O(n)
     auto put = [&](int p1, int p2) {
         heap.push(Pair{R.jaccard(p1, p2), std::min(p1, p2), std::max(p1, p2), p1, p2});
         sset.insert(makenum(p1, p2));
     };
-    for (int i = 0; i < numv; ++i) {
-        if (ptr[i] == ptr[i + 1]) continue;
-        for (int c : cand[i]) {
-            if (c == i || sset.count(makenum(i, c))) continue;
-            put(i, c);
-        }
-        std::vector<int>().swap(cand[i]);
-    }
-
+    lap("jaccard + heap build");
+    if (trace) fprintf(stderr, "[lsh_reorder] scored pairs: %zu\n", heap.size());
     // ---- greedy size-capped union-find ---------------------------------------------------------
     std::vector<int> cluster_id((size_t)numv), cluster_sz((size_t)numv, 1);
     std::vector<char> deleted((size_t)numv, 0);
@@ -222,10 +320,11 @@ extern "C" int gnnagg_lsh_reorder(const int *ptr, const int *idx, int num_v, int
             p1 = root(p1);
             p2 = root(p2);
             if (deleted[p1] || deleted[p2]) continue;
-            if (p1 != p2 && !sset.count(makenum(p1, p2))) put(p1, p2);
+            if (p1 != p2 && !sset.contains(makenum(p1, p2))) put(p1, p2);
         }
     }
 
+    lap("union-find");
     // ---- emit: clusters by first member, members ascending -----------------------------------
     std::vector<int> slot((size_t)numv, -1), count;
     std::vector<int> root_of((size_t)numv);

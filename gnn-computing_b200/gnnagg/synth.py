@@ -137,3 +137,22 @@ def small_random_csr(num_v, avg_deg, seed, empty_frac=0.2, hub=0, num_src=None):
     ptr[1:] = np.cumsum(deg)
     idx = rng.integers(0, max(num_src, 1), int(ptr[-1])).astype(np.int32)
     return ptr, idx
+
+
+def planted_community_csr(num_v, comm=48, pool=48, picks=24, noise=4, seed=123, device="cpu"):
+    """graph WITH community structure and scrambled ids: the `comm` members of a community draw `picks`
+    neighbours from a community-specific pool of `pool` random vertices plus `noise` uniformly random
+    ones.  Members of one community have Jaccard similarity ~0.25 (above the 0.2 LSH threshold of
+    script/cluster2.py) but are scattered over the id range, which is the situation the reference's
+    locality reorder is built for (R-MAT graphs have no such structure to recover)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    ncomm = (num_v + comm - 1) // comm
+    perm = torch.randperm(num_v, generator=g, device=device)               # vertex -> scrambled id
+    pools = torch.randint(0, num_v, (ncomm, pool), generator=g, device=device)
+    member_comm = torch.arange(num_v, device=device) // comm
+    sel = torch.rand((num_v, pool), generator=g, device=device).argsort(1)[:, :picks]   # picks distinct pool slots
+    nbr = torch.gather(pools[member_comm], 1, sel)
+    rnd = torch.randint(0, num_v, (num_v, noise), generator=g, device=device)
+    nbr = torch.cat([nbr, rnd], 1)                                          # [num_v, picks+noise]
+    dst = perm.repeat_interleave(picks + noise)
+    return to_csr(dst, nbr.reshape(-1), num_v)
