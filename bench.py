@@ -34,11 +34,19 @@ WORKLOADS = {
     "arxiv_gcn_layer_32": ("arxiv", 32, 32),
     "proteins_gcn_layer_64": ("proteins", 64, 64),
     "products_gcn_layer_256": ("products", 256, 256),
+    # BASELINE.json configs[4]: GCN aggregation only on the RMAT scale-26 graph (2^26 vertices / 2^30 edges), the
+    # whole graph 1-D row-partitioned over the N ranks (strong scaling); a step = halo all-gather + aggregation
+    "rmat26_gcn_agg_64": ("rmat26", 64, None),
+    "rmat22_gcn_agg_64": ("rmat22", 64, None),   # down-scaled variant of the same workload
 }
+RMAT_SCALES = {"rmat26": (1 << 26, 1 << 30), "rmat22": (1 << 22, 1 << 26)}
 
 
 def layer_bytes(n, m, fin, fout):
-    """algorithmic bytes of one fused layer on one rank (gather model)"""
+    """algorithmic bytes of one fused layer (or, fout=None, of the aggregation alone) on one rank
+    (gather model)"""
+    if fout is None:
+        return spmm_bytes(n, m, fin)
     return 4 * (n + 1) + 4 * m + 4 * m + 4 * m * fin + 4 * n * fout + 4 * fin * fout
 
 
@@ -84,10 +92,11 @@ def cpu_port_time(orc, hp, hi, hv, hX, hW, rows, fin, fout):
     import numpy as np
 
     AX = np.zeros((rows, fin), np.float32)
-    H = np.zeros((rows, fout), np.float32)
+    H = np.zeros((rows, fout), np.float32) if fout is not None else None
     t0 = time.perf_counter()
     orc.spmm_f32(hp, hi, hv, hX, 0, rows, out=AX)
-    orc.dense_f32(AX, hW, 0, rows, out=H)
+    if fout is not None:
+        orc.dense_f32(AX, hW, 0, rows, out=H)
     return time.perf_counter() - t0
 
 
@@ -129,7 +138,10 @@ def main():
     ap.add_argument("--sources", default="rmat", choices=["rmat", "uniform"],
                     help="rmat: the R-MAT source distribution of the workload definition (default, headline); uniform: same "
                          "degree sequence but uniformly random sources -- the cache-hostile extreme, reported as context")
-    ap.add_argument("--pipeline", type=int, default=4,
+    ap.add_argument("--halo", default="auto", choices=["auto", "allgather", "pruned"],
+                    help="N>1: all-gather the whole X, or exchange only the referenced source rows (all-to-all). "
+                         "auto = pruned for the partitioned R-MAT graph, all-gather otherwise")
+    ap.add_argument("--pipeline", type=int, default=0,
                     help="N>1: number of row chunks of the pipelined halo all-gather (0 = one all-gather, then the layer)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -146,9 +158,17 @@ def main():
 
     from gnnagg import synth
 
-    n, m = synth.shape_of(shape)
-    config = {"workload": "%s: fused GCN layer (CSR SpMM aggregation + dense combination) feat %d->%d on synthetic "
-                          "%s-shaped R-MAT graph, %d vertices / %d edges per GPU" % (args.workload, fin, fout, shape, n, m),
+    strong = shape in RMAT_SCALES
+    if strong:  # one fixed graph, partitioned: per-rank block = total / N
+        n_tot, m_tot = RMAT_SCALES[shape]
+        n, m = n_tot // args.gpus, m_tot // args.gpus
+        what = "GCN aggregation (CSR SpMM) feat %d on the R-MAT %s graph (%d vertices / %d edges in total), %d rows / %d edges per GPU" % (
+            fin, shape, n_tot, m_tot, n, m)
+    else:
+        n, m = synth.shape_of(shape)
+        what = "fused GCN layer (CSR SpMM aggregation + dense combination) feat %d->%d on synthetic %s-shaped R-MAT graph, " \
+               "%d vertices / %d edges per GPU" % (fin, fout, shape, n, m)
+    config = {"workload": "%s: %s" % (args.workload, what),
               "graph": "rmat(a=.57,b=.19,c=.19,d=.05) seed=123, val=1/sqrt((deg_u+1)(deg_v+1)), X~N(0,1), W~N(0,1)/sqrt(F)",
               "partition": "1d-row-by-destination" if args.gpus > 1 else "single-gpu",
               "scheduled": bool(args.scheduled), "sources": args.sources,
@@ -164,11 +184,13 @@ def main():
         dev = torch.device("cuda:%d" % local_rank) if torch.cuda.is_available() else torch.device("cpu")
         # the same graph; a leading row block is what gets timed, so only that block is built when no GPU is around
         gen_rows, gen_edges = (n, m) if dev.type == "cuda" else (n, min(m, 4_000_000))
-        ptr, idx = synth.rmat_csr(gen_rows, gen_edges, seed=123, device=dev)
-        val = synth.gcn_norm_val(ptr, idx)
+        src_total = n * args.gpus if strong else n  # the reference arm always times rank 0's block
+        ptr, idx = synth.rmat_csr(gen_rows, gen_edges, seed=123, device=dev, src_num_v=src_total if strong and args.gpus > 1 else None,
+                                  dst_prefix=0 if strong and args.gpus > 1 else None)
+        val = synth.gcn_norm_val(ptr, idx) if src_total == n else torch.rand(idx.numel(), device=dev) + 0.5
         g = torch.Generator(device=dev).manual_seed(123)
-        X = torch.randn((n, fin), device=dev, generator=g)
-        W = torch.randn((fin, fout), device=dev, generator=g) / fin ** 0.5
+        X = torch.randn((src_total, fin), device=dev, generator=g)
+        W = torch.randn((fin, fout or fin), device=dev, generator=g) / fin ** 0.5
         per_step = []
         info = None
         for it in range(args.warmup + args.steps):
@@ -229,11 +251,23 @@ def main():
         val = synth.gcn_norm_val(ptr, idx)
     g = torch.Generator(device=dev).manual_seed(123 + rank)
     Xs = torch.randn((n, fin), device=dev, generator=g)          # this rank's X shard
-    W = torch.randn((fin, fout), device=dev, generator=torch.Generator(device=dev).manual_seed(7)) / fin ** 0.5
-    pipelined = N > 1 and args.pipeline > 0 and not args.scheduled
-    Xfull = torch.empty((src_n, fin), device=dev) if (N > 1 and not pipelined) else Xs
-    H = torch.empty((n, fout), device=dev)
-    agg = gnnagg.Aggregator(ptr, idx, val)
+    agg_only = fout is None
+    W = torch.randn((fin, fout or fin), device=dev, generator=torch.Generator(device=dev).manual_seed(7)) / fin ** 0.5
+    halo = args.halo if args.halo != "auto" else ("pruned" if strong else "allgather")
+    pruned = N > 1 and halo == "pruned" and not args.scheduled
+    pipelined = N > 1 and args.pipeline > 0 and not args.scheduled and not pruned
+    Xfull = torch.empty((src_n, fin), device=dev) if (N > 1 and not pipelined and not pruned) else Xs
+    H = torch.empty((n, fout or fin), device=dev)
+    ph = None
+    if pruned:
+        from gnnagg.partition import PrunedHalo
+
+        ph = PrunedHalo(ptr, idx, val, n, N, rank, fin)
+        agg = ph.agg
+        config["halo"] = "pruned: only referenced source rows travel (all-to-all, %.1f%% of X on rank 0), CSR re-indexed " \
+                         "into the compact receive buffer" % (100 * ph.referenced_fraction)
+    else:
+        agg = gnnagg.Aggregator(ptr, idx, val)
     if args.scheduled:
         agg.schedule(gnnagg.SCHED_NEIGHBOR_GROUPING, [32])
     pipe = AX = None
@@ -244,7 +278,7 @@ def main():
         AX = torch.empty((n, fin), device=dev)
         config["halo"] = "all-gather cut into %d row chunks, sub-CSR of chunk c accumulated while chunk c+1 is in flight; " \
                          "edges with local sources first" % args.pipeline
-    elif N > 1:
+    elif N > 1 and not pruned:
         config["halo"] = "one NCCL all-gather of X, then the layer"
     torch.cuda.synchronize()
     t_setup = time.time() - t0
@@ -252,23 +286,31 @@ def main():
 
     def layer(x_full):
         if pipelined:
-            pipe.aggregate(Xs, AX)                    # chunked all-gather overlapped with aggregation
-            gnnagg.dense_nn(AX, W, H)
+            pipe.aggregate(Xs, H if agg_only else AX)  # chunked all-gather overlapped with aggregation
+            if not agg_only:
+                gnnagg.dense_nn(AX, W, H)
         else:
-            if N > 1:
+            if pruned:
+                x_full = ph.exchange(Xs)                  # pack + all-to-all of the referenced rows
+            elif N > 1:
                 dist.all_gather_into_tensor(Xfull, Xs)   # source-feature halo over NVLink
-            agg.gcn_layer(x_full, W, H, None, scheduled=bool(args.scheduled))
+            if agg_only:
+                agg.gcn_run(x_full, H, scheduled=bool(args.scheduled))
+            else:
+                agg.gcn_layer(x_full, W, H, None, scheduled=bool(args.scheduled))
 
     def step():
         layer(Xfull)
 
     # host buffers for the end-to-end number
     hX = torch.empty((n, fin), pin_memory=True).copy_(Xs)
-    hW = torch.empty((fin, fout), pin_memory=True).copy_(W)
-    hH = torch.empty((n, fout), pin_memory=True)
+    hW = torch.empty((fin, fout or fin), pin_memory=True).copy_(W)
+    hH = torch.empty((n, fout or fin), pin_memory=True)
 
     def step_e2e():
-        if N == 1:
+        if N == 1 and agg_only:
+            agg.gcn_run_host(hX, hH, scheduled=bool(args.scheduled))
+        elif N == 1:
             agg.gcn_layer_host(hX, hW, hH, scheduled=bool(args.scheduled))  # H2D + layer + D2H + sync inside
         else:
             Xs.copy_(hX, non_blocking=True)
@@ -306,7 +348,7 @@ def main():
             t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             total_ms = float(t.item())
-        return total_ms / steps, count() - l0 + (steps if pipelined else 0), prof  # + the dense launch per step
+        return total_ms / steps, count() - l0 + (steps if (pipelined and not agg_only) else 0), prof  # + the dense launch
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -343,7 +385,9 @@ def main():
     except Exception:
         pass
     achieved = spmm_bytes(n, m, fin) / (agg_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "agg_kernel<32,1,GCN,%s> (CSR SpMM aggregation)" % ("sched" if args.scheduled else "csr"),
+    lpr, nv = (8, 1) if fin <= 32 else (16, 1) if fin <= 64 else (32, 1) if fin <= 128 else (32, 2)
+    roofline = {"bound": "hbm", "kernel": "agg_kernel<%d,%d,GCN,%s,%d> (CSR SpMM aggregation)" % (
+                    lpr, nv, "sched" if args.scheduled else "csr", 128 if m < 4000000 else 512),
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": spmm_bytes(n, m, fin), "kernel_ms": round(agg_ms, 4),
@@ -363,16 +407,21 @@ def main():
                     "sample": "rows [0,%d) = %d edges (%.2f%% of m) of rank 0's graph, %.1f s; scalar fp32 CSR port + fp32 GEMM "
                               "(oracle/oracle.c, OpenMP dynamic,64)" % (rows, e, 100.0 * e / m, t_cpu)}
 
-    line = {"metric": "gcn_layer_algorithmic_GBps", "value": round(value, 1), "unit": "GB/s", "n_gpus": N,
+    line = {"metric": "gcn_aggregation_algorithmic_GBps" if agg_only else "gcn_layer_algorithmic_GBps", "value": round(value, 1),
+            "unit": "GB/s", "n_gpus": N,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "edges_feat_per_s": round(N * m * fin / (ms * 1e-3), 1),
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 1), "unit": "GB/s", "ms_per_step": round(ms_e2e, 4),
-                    "h2d_bytes_per_step": 4 * n * fin + (4 * fin * fout if N == 1 else 0), "d2h_bytes_per_step": 4 * n * fout,
-                    "api": "gnnagg_gcn_layer_host (pinned host X, W -> H)" if N == 1 else
+                    "h2d_bytes_per_step": 4 * n * fin + (4 * fin * fout if (N == 1 and not agg_only) else 0),
+                    "d2h_bytes_per_step": 4 * n * (fout or fin),
+                    "api": ("gnnagg_gcn_run_host (pinned host X -> Y)" if agg_only else "gnnagg_gcn_layer_host (pinned host X, W -> H)") if N == 1 else
                            "pinned H2D of the X shard + NCCL halo all-gather + aggregation + combination + D2H of the H shard"},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches) + (args.steps if pruned else 0),  # + the row-packing kernel
+            "compute_only": {"ms_per_step": round(float(np.mean([p["total"] for p in prof])), 4),
+                             "value": round(N * bytes_rank / (float(np.mean([p["total"] for p in prof])) * 1e-3) / 1e9, 1), "unit": "GB/s",
+                             "note": "rank 0's kernels only (X already resident, no halo exchange), from the library's own CUDA events"},
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "setup_s": round(t_setup, 2)}
     print(json.dumps(line))

@@ -714,6 +714,18 @@ int gnnagg_sddmm(gnnagg_aggregator *a, const float *X1, const float *X2, float *
     return GNNAGG_OK;
 }
 
+int gnnagg_gather_rows(const float *X, const int64_t *rows, float *out, int64_t count, int feat, void *stream)
+{
+    if (count == 0) return GNNAGG_OK;
+    if (!X || !rows || !out || count < 0) return set_error(GNNAGG_ERR_ARG, "gnnagg_gather_rows: bad argument");
+    if (int rc = check_feat(feat)) return rc;
+    if (!aligned16(X) || !aligned16(out)) return set_error(GNNAGG_ERR_ARG, "X and out must be 16-byte aligned");
+    const int64_t total4 = count * (feat / 4);
+    gather_rows_kernel<<<(unsigned)cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(X, rows, out, total4, feat / 4);
+    CUDA_TRY(cudaPeekAtLastError());
+    return GNNAGG_OK;
+}
+
 int gnnagg_spmm_naive(int num_v, const int *d_ptr, const int *d_idx, const float *d_val, const float *X, float *Y,
                       int feat, void *stream)
 {

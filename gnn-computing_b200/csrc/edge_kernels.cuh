@@ -212,6 +212,17 @@ __global__ void __launch_bounds__(256) csr2edgelist_kernel(const EdgeParams g, i
     reinterpret_cast<int2 *>(edgelist)[e] = make_int2(__ldg(g.idx + e), v);
 }
 
+// out[i,:] = X[rows[i],:]: one float4 per thread, F/4 consecutive threads per row (halo packing)
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float *__restrict__ X, const int64_t *__restrict__ rows,
+                                                          float *__restrict__ out, int64_t total4, int F4)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total4) return;
+    const int64_t i = t / F4;
+    const int c = (int)(t % F4);
+    reinterpret_cast<float4 *>(out)[t] = __ldg(reinterpret_cast<const float4 *>(X) + __ldg(rows + i) * F4 + c);
+}
+
 // thread-per-row SpMM of include/spmm.h:223-265 (kept for API completeness; rows without edges
 // are left untouched exactly as there, :236-237)
 __global__ void __launch_bounds__(128) spmm_naive_kernel(int num_v, const int *__restrict__ ptr,

@@ -76,6 +76,7 @@ _SIGS = {
     "gnnagg_add_to_center": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gnnagg_each_div": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gnnagg_sddmm": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_void_p]),
+    "gnnagg_gather_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "gnnagg_spmm_naive": (C.c_int, [C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p]),
     "gnnagg_validate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int), C.c_void_p]),
     "gnnagg_validate_reordered": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
@@ -366,6 +367,12 @@ class Aggregator:
 def dense_nn(A, B, Cout):
     check(lib().gnnagg_dense_nn(_dp(A), _dp(B), _dp(Cout), A.shape[0], B.shape[1], A.shape[1], _stream()))
     return Cout
+
+
+def gather_rows(X, rows, out):
+    """out[i] = X[rows[i]] (rows: int64 CUDA tensor)"""
+    check(lib().gnnagg_gather_rows(_dp(X), _dp(rows), _dp(out), rows.numel(), X.shape[1], _stream()))
+    return out
 
 
 def spmm_naive(ptr, idx, val, X, Y):

@@ -144,6 +144,11 @@ int gnnagg_gcn_run(gnnagg_aggregator *a, const float *X, float *Y, int feat, int
  * accumulate = 0 it is gnnagg_gcn_run(scheduled = 0).  Deterministic (no atomics). */
 int gnnagg_gcn_run_acc(gnnagg_aggregator *a, const float *X, float *Y, int feat, int accumulate, void *stream);
 
+/* out[i,:] = X[rows[i],:] for i < count (feat a multiple of 4).  Packs the rows of the local X shard that
+ * another rank's row block references before the pruned halo exchange (multi-GPU path, new functionality:
+ * the reference is single-GPU). */
+int gnnagg_gather_rows(const float *X, const int64_t *rows, float *out, int64_t count, int feat, void *stream);
+
 /* edge-parallel variant: replaces Aggregator_GCN::runEdgeWise + aggr_gcn_edgewise
  * (aggr_gcn.h:291-302,445-460) and Aggregator::csr2edgelist (aggregator.h:115-122).
  * Any feat (the reference is F=32 only). */

@@ -59,6 +59,66 @@ def _worker(rank, world, port, balance, q):
         dist.destroy_process_group()
 
 
+def _worker_pruned(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    import oracle as orc
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n_per, F = 200, 16
+        rng = np.random.default_rng(3)                       # same stream on every rank: the global X
+        Xfull = rng.standard_normal((world * n_per, F)).astype(np.float32)
+        ptr, idx = synth.small_random_csr(n_per, 5.0, 40 + rank, num_src=world * n_per, hub=400)
+        # make the referenced set sparse so pruning matters: keep only sources = 0 mod 3
+        idx = (idx // 3 * 3).astype(np.int32)
+        val = np.random.default_rng(rank).standard_normal(len(idx)).astype(np.float32)
+        plan = partition.pruned_plan(torch.from_numpy(idx), n_per, world, rank)
+        shard = torch.from_numpy(Xfull[rank * n_per:(rank + 1) * n_per].copy())
+        send = shard[plan["send_rows"]]                       # the packing step (gnnagg_gather_rows on the GPU)
+        recv = torch.empty((plan["num_recv"], F))
+        dist.all_to_all_single(recv, send, output_split_sizes=plan["recv_counts"], input_split_sizes=plan["send_counts"])
+        y, _ = orc.spmm_f64(ptr, plan["idx_compact"].numpy(), val, recv.numpy())
+        want, _ = orc.spmm_f64(ptr, idx, val, Xfull)
+        ok = np.array_equal(y, want) and plan["num_recv"] <= world * n_per // 3 + 1
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_pruned_halo_plan_gloo_world2():
+    """only the referenced source rows travel; the re-indexed CSR on the compact buffer gives identical sums"""
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_pruned, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert sorted(q.get(timeout=5) for _ in range(2)) == [(0, True), (1, True)]
+
+
+@pytest.mark.gpu
+def test_gather_rows_kernel(gn, cuda):
+    import torch
+
+    X = torch.randn((1000, 64), device=cuda)
+    rows = torch.randint(0, 1000, (5000,), device=cuda, dtype=torch.int64)
+    out = gn.gather_rows(X, rows, torch.empty((5000, 64), device=cuda))
+    assert torch.equal(out, X[rows])
+    assert gn.gather_rows(X, rows[:0], torch.empty((0, 64), device=cuda)).numel() == 0
+
+
 @pytest.mark.parametrize("balance", ["rows", "edges"])
 def test_partitioned_equals_single_gloo_world2(balance):
     import torch.multiprocessing as mp
