@@ -262,15 +262,25 @@ def main():
     if pruned:
         from gnnagg.partition import PrunedHalo
 
-        ph = PrunedHalo(ptr, idx, val, n, N, rank, fin)
-        agg = ph.agg
-        config["halo"] = "pruned: only referenced source rows travel (all-to-all, %.1f%% of X on rank 0), CSR re-indexed " \
-                         "into the compact receive buffer" % (100 * ph.referenced_fraction)
+        if args.pipeline > 0:
+            from gnnagg.partition import PipelinedPrunedHalo
+
+            ph = PipelinedPrunedHalo(ptr, idx, val, n, N, rank, fin, chunks=args.pipeline)
+            agg = ph.aggs[0]
+            config["halo"] = "pruned + pipelined: %d row chunks, chunk c fetches only the referenced source rows no earlier chunk " \
+                             "fetched (all-to-all per chunk, %.1f%% of X on rank 0, stage shares %s) while chunk c-1 is aggregated" % (
+                                 args.pipeline, 100 * ph.referenced_fraction, [round(f, 2) for f in ph.stage_fraction])
+        else:
+            ph = PrunedHalo(ptr, idx, val, n, N, rank, fin)
+            agg = ph.agg
+            config["halo"] = "pruned: only referenced source rows travel (all-to-all, %.1f%% of X on rank 0), CSR re-indexed " \
+                             "into the compact receive buffer" % (100 * ph.referenced_fraction)
     else:
         agg = gnnagg.Aggregator(ptr, idx, val)
     if args.scheduled:
         agg.schedule(gnnagg.SCHED_NEIGHBOR_GROUPING, [32])
     pipe = AX = None
+    AXp = torch.empty((n, fin), device=dev) if (pruned and args.pipeline > 0 and not agg_only) else None
     if pipelined:
         from gnnagg.partition import HaloPipeline
 
@@ -290,6 +300,11 @@ def main():
             if not agg_only:
                 gnnagg.dense_nn(AX, W, H)
         else:
+            if pruned and args.pipeline > 0:
+                ph.aggregate(Xs, H if agg_only else AXp)   # pack, per-chunk all-to-all overlapped with aggregation
+                if not agg_only:
+                    gnnagg.dense_nn(AXp, W, H)
+                return
             if pruned:
                 x_full = ph.exchange(Xs)                  # pack + all-to-all of the referenced rows
             elif N > 1:
@@ -329,7 +344,7 @@ def main():
         barrier()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         prof = []
-        aggs = pipe.aggs if pipelined else [agg]
+        aggs = pipe.aggs if pipelined else (ph.aggs if (pruned and args.pipeline > 0) else [agg])
         count = lambda: sum(a.launches for a in aggs)
         l0 = count()
         sampler.active = True
@@ -352,10 +367,11 @@ def main():
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    for a_ in (pipe.aggs if pipelined else [agg]):
+    prof_aggs = pipe.aggs if pipelined else (ph.aggs if (pruned and args.pipeline > 0) else [agg])
+    for a_ in prof_aggs:
         a_.profile(True)
     ms, launches, prof = timed(step, args.steps, args.warmup, profile=True)
-    for a_ in (pipe.aggs if pipelined else [agg]):
+    for a_ in prof_aggs:
         a_.profile(False)
     ms_e2e, _, _ = timed(step_e2e, max(3, args.steps // 2), 3)
     clocks = sampler.result()

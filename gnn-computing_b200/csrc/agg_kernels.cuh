@@ -35,6 +35,7 @@ struct AggParams {
     const int *__restrict__ item_row;    // row containing edge k*kFineItem
     const float *__restrict__ X;         // [*, F]
     const float *__restrict__ att;       // GAT attention table [n,2]
+    const float *__restrict__ P;         // MLP: projected features P = X*W, [n, F] (also the gather source)
     float *__restrict__ Y;               // [n, F]
     float *__restrict__ carry;           // [num_items, F] partials of rows entering an item
     float *__restrict__ den_row;         // GAT: [n] denominator of rows that start in an item and leave it
@@ -49,7 +50,7 @@ struct AggParams {
     int accumulate;                      // GCN un-scheduled: Y += A*X instead of Y = A*X
 };
 
-enum { kModeGCN = 0, kModeGAT = 1 };
+enum { kModeGCN = 0, kModeGAT = 1, kModeMLP = 2 };
 
 // row that contains edge e0 (start of an item): direct lookup when items are aligned with the
 // item_row table, bounded binary search otherwise (the small-graph variant uses 32..128-edge items)
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
                 mbar_init(bar, 1);
                 fence_proxy_async();  // init visible to the async proxy; CTA scope (no L1 invalidate)
                 const uint32_t bytes = (uint32_t)nb * 4u;
-                mbar_expect_tx(bar, (MODE == kModeGCN) ? 2u * bytes : bytes);
+                mbar_expect_tx(bar, (MODE == kModeGCN) ? 2u * bytes : bytes);  // GAT / MLP stage idx only
                 bulk_g2s(smem_u32(my_idx), p.idx + wbase, bytes, bar);
                 if (MODE == kModeGCN) bulk_g2s(smem_u32(my_val), p.val + wbase, bytes, bar);
             }
@@ -145,6 +146,14 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
 
         float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
         float den = 0.f;
+        // MLP: projected feature of the destination row, P[dst, col..] (aggr_nn.h:26 `cached`, after projection)
+        float4 pd0 = make_float4(0.f, 0.f, 0.f, 0.f), pd1 = pd0;
+        auto load_dst = [&](int r) {
+            const float *q = p.P + (size_t)(SCHED ? __ldg(p.target + r) : r) * F + col;
+            if (act0) pd0 = ldg_f4(q);
+            if (act1) pd1 = ldg_f4(q + LPR * 4);
+        };
+        if (MODE == kModeMLP) load_dst(first_row);
 
         // closes `row`: writes / accumulates its result and moves to the next row
         auto flush = [&](bool at_item_end) {
@@ -190,6 +199,7 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
             if (row < p.num_rows) {
                 row_end = __ldg(p.ptr + row + 1);
                 if (MODE == kModeGAT) a_dst = __ldg(p.att + 2 * (size_t)(SCHED ? __ldg(p.target + row) : row));
+                if (MODE == kModeMLP) load_dst(row);
             } else {
                 row_end = INT_MAX;
             }
@@ -213,7 +223,8 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
 #pragma unroll
             for (int q = 0; q < U / 4; ++q) {
                 const int4 i4 = *reinterpret_cast<const int4 *>(my_idx + k + 4 * q);
-                const float4 w4 = *reinterpret_cast<const float4 *>(my_val + k + 4 * q);
+                const float4 w4 = (MODE == kModeMLP) ? make_float4(0.f, 0.f, 0.f, 0.f)
+                                                     : *reinterpret_cast<const float4 *>(my_val + k + 4 * q);
                 src[4 * q] = i4.x, src[4 * q + 1] = i4.y, src[4 * q + 2] = i4.z, src[4 * q + 3] = i4.w;
                 w[4 * q] = w4.x, w[4 * q + 1] = w4.y, w[4 * q + 2] = w4.z, w[4 * q + 3] = w4.w;
             }
@@ -225,12 +236,17 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
                 if (NV > 1) v1[u] = __ldg(reinterpret_cast<const float4 *>(x + second));
             }
             float wout = 0.f;
-            if (MODE == kModeGCN && row_end - e >= U) {
+            if (MODE != kModeGAT && row_end - e >= U) {
                 // no row ends inside the batch: straight FMA chain
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    fma4(acc0, w[u], v0[u]);
-                    if (NV > 1) fma4(acc1, w[u], v1[u]);
+                    if (MODE == kModeMLP) {
+                        relu_add4(acc0, pd0, v0[u]);
+                        if (NV > 1) relu_add4(acc1, pd1, v1[u]);
+                    } else {
+                        fma4(acc0, w[u], v0[u]);
+                        if (NV > 1) fma4(acc1, w[u], v1[u]);
+                    }
                 }
             } else {
 #pragma unroll
@@ -243,8 +259,13 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
                         den += wu;
                         if (SCHED && vl == u % LPR) wout = wu;
                     }
-                    fma4(acc0, wu, v0[u]);
-                    if (NV > 1) fma4(acc1, wu, v1[u]);
+                    if (MODE == kModeMLP) {
+                        relu_add4(acc0, pd0, v0[u]);
+                        if (NV > 1) relu_add4(acc1, pd1, v1[u]);
+                    } else {
+                        fma4(acc0, wu, v0[u]);
+                        if (NV > 1) fma4(acc1, wu, v1[u]);
+                    }
                 }
             }
             if (MODE == kModeGAT && SCHED && cb == 0 && p.newval != nullptr) {
@@ -264,7 +285,7 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
             for (int u = 0; u < U; ++u) {
                 const int k = min(e + u, e1 - 1) - wbase;
                 src[u] = my_idx[k];
-                w[u] = my_val[k];
+                w[u] = (MODE == kModeMLP) ? 0.f : my_val[k];
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -284,8 +305,13 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
                         den += wu;
                         if (SCHED && vl == u % LPR) wout = wu;
                     }
-                    fma4(acc0, wu, v0[u]);
-                    if (NV > 1) fma4(acc1, wu, v1[u]);
+                    if (MODE == kModeMLP) {
+                        relu_add4(acc0, pd0, v0[u]);
+                        if (NV > 1) relu_add4(acc1, pd1, v1[u]);
+                    } else {
+                        fma4(acc0, wu, v0[u]);
+                        if (NV > 1) fma4(acc1, wu, v1[u]);
+                    }
                 }
             }
             if (MODE == kModeGAT && SCHED && cb == 0 && p.newval != nullptr) {

@@ -326,6 +326,44 @@ static int gat_run_core(gnnagg_aggregator *a, const float *X, const float *att, 
     return launch_agg<kModeGAT, false>(a, p, st);
 }
 
+static int mlp_run_core(gnnagg_aggregator *a, const float *P, float *Y, int F, int scheduled, cudaStream_t st)
+{
+    AggParams p{};
+    p.X = P;
+    p.P = P;
+    p.Y = Y;
+    p.F = F;
+    if (scheduled) {
+        if (a->sched_kind == GNNAGG_SCHED_NOP) return set_error(GNNAGG_ERR_STATE, "scheduled run before schedule");
+        CUDA_TRY(cudaMemsetAsync(Y, 0, (size_t)a->n * F * sizeof(float), st));  // aggr_nn.h:314
+        if (a->sched_edges == 0) return GNNAGG_OK;
+        p.ptr = a->s_ptr;
+        p.idx = a->s_idx;
+        p.target = a->s_target;
+        p.item_row = a->s_item_row;
+        p.num_rows = a->num_target;
+        p.num_edges = a->sched_edges;
+        p.num_fine_items = a->sched_items;
+        p.bulk_ok = aligned16(p.idx);
+        return launch_agg<kModeMLP, true>(a, p, st);
+    }
+    if (a->m == 0) {
+        CUDA_TRY(cudaMemsetAsync(Y, 0, (size_t)a->n * F * sizeof(float), st));
+        return GNNAGG_OK;
+    }
+    const int EB = item_edges_for(a, F, a->m);
+    if (int rc = ensure(a->carry, a->carry_cap, (size_t)cdiv(a->m, EB) * F)) return rc;
+    p.num_fine_items = a->num_items;
+    p.ptr = a->d_ptr;
+    p.idx = a->d_idx;
+    p.item_row = a->d_item_row;
+    p.carry = a->carry;
+    p.num_rows = a->n;
+    p.num_edges = a->m;
+    p.bulk_ok = aligned16(p.idx);
+    return launch_agg<kModeMLP, false>(a, p, st);
+}
+
 // timing brackets: ev[0] call entry, ev[3] end of the aggregation part, ev[4] end of the call
 static int gcn_run_impl(gnnagg_aggregator *a, const float *X, float *Y, int F, int scheduled, cudaStream_t st,
                         bool last = true, int accumulate = 0)
@@ -614,6 +652,27 @@ int gnnagg_gcn_layer(gnnagg_aggregator *a, const float *X, const float *W, float
         ++a->launches;
     }
     PROF_RECORD(a, 4, (cudaStream_t)stream);
+    return GNNAGG_OK;
+}
+
+int gnnagg_mlp_run(gnnagg_aggregator *a, const float *X, const float *W, float *Y, int feat, int scheduled,
+                   void *stream)
+{
+    if (a && a->n == 0) return GNNAGG_OK;
+    if (!a || !X || !W || !Y) return set_error(GNNAGG_ERR_ARG, "gnnagg_mlp_run: NULL argument");
+    if (!aligned16(X) || !aligned16(Y)) return set_error(GNNAGG_ERR_ARG, "X and Y must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = ensure(a->ax, a->ax_cap, (size_t)a->n * feat)) return rc;
+    PROF_RECORD(a, 0, st);
+    if (int rc = dense_nn_launch(X, W, a->ax, a->n, feat, feat, stream)) return rc;  // P = X W, once per call
+    ++a->launches;
+    if (a->prof) {
+        CUDA_TRY(cudaEventRecord(a->ev[1], st));
+        CUDA_TRY(cudaEventRecord(a->ev[2], st));
+    }
+    if (int rc = mlp_run_core(a, a->ax, Y, feat, scheduled, st)) return rc;
+    PROF_RECORD(a, 3, st);
+    PROF_RECORD(a, 4, st);
     return GNNAGG_OK;
 }
 

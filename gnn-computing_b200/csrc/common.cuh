@@ -70,6 +70,14 @@ __device__ __forceinline__ void fma4(float4 &acc, float w, const float4 &v)
     acc.z = fmaf(w, v.z, acc.z);
     acc.w = fmaf(w, v.w, acc.w);
 }
+// acc += max(a + b, 0): the per-edge op of the MLP aggregator after the projection has been hoisted
+__device__ __forceinline__ void relu_add4(float4 &acc, const float4 &a, const float4 &b)
+{
+    acc.x += fmaxf(a.x + b.x, 0.f);
+    acc.y += fmaxf(a.y + b.y, 0.f);
+    acc.z += fmaxf(a.z + b.z, 0.f);
+    acc.w += fmaxf(a.w + b.w, 0.f);
+}
 __device__ __forceinline__ float4 add4(const float4 &a, const float4 &b)
 {
     return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);

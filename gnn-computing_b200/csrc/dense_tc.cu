@@ -121,27 +121,46 @@ dense_tf32x3_kernel(const float *__restrict__ A, const float *__restrict__ B, fl
     uint32_t c = 0;          // chunks produced so far by this CTA (ring position)
     uint32_t acc_phase = 0;  // parity of s_acc
 
+    // this thread's 4 float4 of chunk (tile, kc): 128 rows x 8 float4; a warp covers 8 rows x 64 B
+    // (full sectors from global, conflict-free 128-byte runs in shared memory)
+    auto fetch = [&](int64_t tile, int kc, float4 (&v)[4]) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int u = p * kDenseThreads + tid;
+            const int r8 = u & 7, kq = (u >> 3) & 7, rb = u >> 6;
+            const int64_t row = tile * kTileM + rb * 8 + r8;
+            v[p] = (tile < tiles && row < M) ? ldg_f4(A + (size_t)row * K + kc * kChunkK + kq * 4)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    float4 cur[4], nxt[4];
+    fetch(blockIdx.x, 0, cur);
+
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int64_t row0 = tile * kTileM;
         for (int kc = 0; kc < chunks; ++kc, ++c) {
+            // software pipeline: the global loads of the NEXT chunk are in flight while this one is
+            // split, stored and multiplied
+            if (kc + 1 < chunks)
+                fetch(tile, kc + 1, nxt);
+            else
+                fetch(tile + gridDim.x, 0, nxt);
             const uint32_t stage = c & 1;
             if (c >= 2) mbar_wait(smem_u32(&s_empty[stage]), ((c >> 1) - 1) & 1);  // MMAs of chunk c-2 retired
             uint8_t *aHi = sA + stage * 2 * kStageBytes, *aLo = aHi + kStageBytes;
-            // 128 rows x 8 float4; a warp covers 8 rows x 64 B: full sectors from global,
-            // conflict-free 128-byte runs in shared memory
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
                 const int u = p * kDenseThreads + tid;
                 const int r8 = u & 7, kq = (u >> 3) & 7, rb = u >> 6;
-                const int64_t row = row0 + rb * 8 + r8;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row < M) v = ldg_f4(A + (size_t)row * K + kc * kChunkK + kq * 4);
+                const float4 v = cur[p];
                 const float4 h = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
                 const float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
                 const uint32_t off = (uint32_t)rb * sbo_a + (uint32_t)kq * 128u + (uint32_t)r8 * 16u;
                 *reinterpret_cast<float4 *>(aHi + off) = h;
                 *reinterpret_cast<float4 *>(aLo + off) = l;
             }
+#pragma unroll
+            for (int p = 0; p < 4; ++p) cur[p] = nxt[p];
             fence_proxy_async();
             __syncthreads();
             if (tid == 0) {
@@ -194,20 +213,6 @@ dense_tf32x3_kernel(const float *__restrict__ A, const float *__restrict__ B, fl
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)tmem_cols) : "memory");
 }
 
-// debug-only fp32 SIMT product used to bisect tensor-core issues (GNNAGG_DENSE_SIMT=1); never the
-// default path
-__global__ void __launch_bounds__(256) dense_simt_kernel(const float *__restrict__ A, const float *__restrict__ B,
-                                                         float *__restrict__ C, int64_t M, int N, int K)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= M * N) return;
-    const int64_t r = i / N;
-    const int c = (int)(i % N);
-    float acc = 0.f;
-    for (int k = 0; k < K; ++k) acc = fmaf(A[r * K + k], B[(size_t)k * N + c], acc);
-    C[i] = acc;
-}
-
 int dense_nn_launch(const float *A, const float *B, float *C, int64_t M, int N, int K, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
@@ -215,11 +220,6 @@ int dense_nn_launch(const float *A, const float *B, float *C, int64_t M, int N, 
         return set_error(GNNAGG_ERR_ARG, "dense combination: feat_in and feat_out must be multiples of 32 in [32,256]");
     if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(C)) & 15)
         return set_error(GNNAGG_ERR_ARG, "dense combination: A and C must be 16-byte aligned");
-    static const bool simt = getenv("GNNAGG_DENSE_SIMT") != nullptr;
-    if (simt) {
-        dense_simt_kernel<<<(unsigned)((M * N + 255) / 256), 256, 0, st>>>(A, B, C, M, N, K);
-        return cudaPeekAtLastError() == cudaSuccess ? GNNAGG_OK : set_error(GNNAGG_ERR_CUDA, "dense_simt launch failed");
-    }
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess ||
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)

@@ -75,6 +75,7 @@ _SIGS = {
     "gnnagg_u_add_v": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gnnagg_add_to_center": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gnnagg_each_div": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gnnagg_mlp_run": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_void_p]),
     "gnnagg_sddmm": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_void_p]),
     "gnnagg_gather_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "gnnagg_spmm_naive": (C.c_int, [C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p]),
@@ -342,6 +343,11 @@ class Aggregator:
     def each_div(self, in_center, inout_val):
         check(lib().gnnagg_each_div(self.h, _dp(in_center), _dp(inout_val), _stream()))
         return inout_val
+
+    # --- per-edge MLP aggregator (aggr_nn.h)
+    def mlp_run(self, X, W, Y, scheduled=False):
+        check(lib().gnnagg_mlp_run(self.h, _dp(X), _dp(W), _dp(Y), X.shape[1], int(scheduled), _stream()))
+        return Y
 
     # --- SDDMM
     def sddmm(self, X1, X2, out_val, scheduled=False):

@@ -186,6 +186,14 @@ int gnnagg_u_add_v(gnnagg_aggregator *a, const float *att, float *out_val, void 
 int gnnagg_add_to_center(gnnagg_aggregator *a, const float *in_val, float *out_center, void *stream);
 int gnnagg_each_div(gnnagg_aggregator *a, const float *in_center, float *inout_val, void *stream);
 
+/* per-edge MLP aggregation  Y[v,:] = sum_{u in N(v)} ReLU((X[v,:] + X[u,:]) * W),  W row-major [feat, feat].
+ * replaces Aggregator_MLP::run + aggr_mlp / aggr_mlp_target (include/aggr_nn.h:51-341; there feat = 32 only and
+ * a 32x32 mat-vec per EDGE).  Here the projection is hoisted out of the edge loop: (x_v + x_u) W = P[v] + P[u]
+ * with P = X W computed once on the tensor cores (gnnagg_dense_nn), so an edge costs one gathered row and
+ * `feat` adds.  feat a multiple of 32 <= 256; scheduled = 1 uses the current schedule (RED combination). */
+int gnnagg_mlp_run(gnnagg_aggregator *a, const float *X, const float *W, float *Y, int feat, int scheduled,
+                   void *stream);
+
 /* SDDMM  val[e] = <X1[idx[e],:], X2[row(e),:]>.  replaces Aggregator_SDDMM::run + aggr_sddmm /
  * aggr_sddmm_target (aggr_sddmm.h:5-117); scheduled=1 requires a neighbor-grouping schedule
  * (:100) and writes in scheduled edge order (identical to CSR order for that schedule).

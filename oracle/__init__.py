@@ -161,6 +161,15 @@ def each_div(ptr, center, newval):
     return out
 
 
+def mlp_f64(ptr, idx, X, W):
+    n = len(ptr) - 1
+    F = X.shape[1]
+    Y = np.empty((n, F), np.float32)
+    S = np.empty((n, F), np.float32)
+    lib().orc_mlp_f64(C.c_int64(n), _vp(ptr), _vp(idx), _vp(X), _vp(W), C.c_int(F), _vp(Y), _vp(S))
+    return Y, S
+
+
 def sddmm_f64(ptr, idx, X1, X2):
     F = X1.shape[1]
     out = np.empty(len(idx), np.float32)
@@ -249,10 +258,11 @@ def ref():
         _ref.ref_sched_run.restype = C.c_longlong
         _ref.ref_sched_num_edges.restype = C.c_longlong
         _ref.ref_sched_num_ptr.restype = C.c_longlong
-        for f in ("ref_gcn_create", "ref_gat_create", "ref_sddmm_create"):
+        for f in ("ref_gcn_create", "ref_gat_create", "ref_sddmm_create", "ref_mlp_create"):
             getattr(_ref, f).restype = C.c_void_p
         _ref.ref_gcn_run_edgewise.restype = C.c_double
         _ref.ref_sddmm_run.restype = C.c_double
+        _ref.ref_mlp_run.restype = C.c_double
     return _ref
 
 

@@ -291,6 +291,41 @@ void orc_each_div(int64_t n, const int *ptr, const float *in, float *newval)
 }
 
 /* ------------------------------------------------------------------------------------------
+ * per-edge MLP aggregation  Y[v,o] = sum_{u in N(v)} ReLU( sum_k (X[v,k] + X[u,k]) * W[k*F + o] )
+ * reference: aggr_nn.h:11-48 (macro COMP, the PURE_COMP path both kernels use): input[k] = cached[k] +
+ * vin[idx*32 + k] (:35), ans = sum_k input[k] * shared_weight[lane + 32*k] (:38-41), `if (ans > 0) rs += ans`
+ * (:42-43); F = 32 there.  scale = sum over edges and k of |(x_v + x_u) w| for the parity gate.
+ * ------------------------------------------------------------------------------------------ */
+void orc_mlp_f64(int64_t n, const int *ptr, const int *idx, const float *X, const float *W, int F, float *Y,
+                 float *scale)
+{
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t v = 0; v < n; ++v) {
+        double *acc = (double *)calloc((size_t)2 * F, sizeof(double));
+        double *mag = acc + F;
+        const float *xv = X + (size_t)v * F;
+        for (int e = ptr[v]; e < ptr[v + 1]; ++e) {
+            const float *xu = X + (size_t)idx[e] * F;
+            for (int o = 0; o < F; ++o) {
+                double ans = 0.0, m = 0.0;
+                for (int k = 0; k < F; ++k) {
+                    const double t = ((double)xv[k] + (double)xu[k]) * (double)W[(size_t)k * F + o];
+                    ans += t;
+                    m += fabs((double)xv[k] * (double)W[(size_t)k * F + o]) + fabs((double)xu[k] * (double)W[(size_t)k * F + o]);
+                }
+                if (ans > 0) acc[o] += ans;
+                mag[o] += m;
+            }
+        }
+        for (int o = 0; o < F; ++o) {
+            Y[(size_t)v * F + o] = (float)acc[o];
+            if (scale) scale[(size_t)v * F + o] = (float)mag[o];
+        }
+        free(acc);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
  * SDDMM  val[e] = < X1[idx[e], 0:F], X2[row, 0:F] >             (aggr_sddmm.h:17-41)
  * The reference hard-wires the X1 row stride to 32 (aggr_sddmm.h:21,27) and reads 32 lanes;
  * with F = 32 both agree, which is the only case the reference supports.

@@ -15,6 +15,7 @@
 #include "aggr_gcn.h"
 #include "aggr_gat.h"
 #include "aggr_sddmm.h"
+#include "aggr_nn.h"
 #include "dense.h"
 
 #include <cstring>
@@ -185,6 +186,22 @@ void ref_sddmm_schedule(void *h, int kind, int p0, int p1)
 double ref_sddmm_run(void *h, float *v1, float *v2, float *outval, int block, int scheduled)
 {
     return ((Aggregator_SDDMM *)h)->run(v1, v2, outval, block, scheduled != 0);
+}
+
+void *ref_mlp_create(int *d_ptr, int *d_idx, int num_v, int num_e, float *d_weight)
+{
+    registerPtr(d_ptr);
+    registerPtr(d_idx);
+    return new Aggregator_MLP(NULL, NULL, d_ptr, d_idx, num_v, num_e, 32, 32, d_weight);  // aggr_nn.h is F = 32 only
+}
+void ref_mlp_schedule(void *h, int kind, int p0, int p1)
+{
+    int arr[2] = {p0, p1};
+    ((Aggregator_MLP *)h)->schedule((Schedule)kind, arr);
+}
+double ref_mlp_run(void *h, float *vin, float *vout, int block, int scheduled)
+{
+    return ((Aggregator_MLP *)h)->run(vin, vout, block, scheduled != 0);
 }
 
 // un-fused combination baseline (dense.h:4-23); tmp is an [M,N] scratch

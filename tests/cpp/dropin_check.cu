@@ -11,6 +11,7 @@
 #include "aggr_gcn.h"
 #include "aggr_gat.h"
 #include "aggr_sddmm.h"
+#include "aggr_nn.h"
 #include "dense.h"
 
 static float *dev_random(curandGenerator_t gen, size_t count, bool positive)
@@ -114,6 +115,17 @@ int main(int argc, char **argv)
     atsd->run(x, y_naive, e1, 128, 0);
     atsd->run(x, y_naive, e2, 128, 1);
     expect("aggr_sddmm vs aggr_sddmm_target", valid(e1, e2, m));
+
+    // ---- per-edge MLP aggregator (aggr_nn.h): un-scheduled vs neighbour-grouped
+    if (F == 32) {
+        float *wmlp = dev_random(curand, (size_t)F * F + 64, false);
+        Aggregator_MLP *atmlp = new Aggregator_MLP(g, F, F, wmlp);
+        atmlp->schedule(neighbor_grouping, tmparr);
+        double t_mlp = atmlp->run(x, y, 128, 0);
+        atmlp->run(x, y2, 128, 1);
+        expect("aggr_mlp vs aggr_mlp_target", valid(y, y2, n * F));
+        dbg(t_mlp);
+    }
 
     if (failures) {
         std::cerr << "DROPIN_CHECK FAILED (" << failures << " comparisons)\n";

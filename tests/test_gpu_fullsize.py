@@ -1,0 +1,111 @@
+"""GPU tier: parity at BASELINE.json's FULL sizes through size-independent properties (the fp64 oracle would
+need minutes per case there): linearity, column checksums against an independent fp64 scatter, row sums with
+X = 1, scheduled == un-scheduled, run-to-run determinism, oracle on a row sample, layer == aggregation @ W."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_gate
+from gnnagg import synth
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("arxiv", 32), ("reddit", 128), ("proteins", 64), ("products", 256)]  # BASELINE.json configs[0..3]
+
+
+@pytest.mark.parametrize("shape,F", CASES)
+def test_full_size_properties(gn, orc, cuda, shape, F):
+    n, m = synth.shape_of(shape)
+    ptr, idx = synth.rmat_csr(n, m, seed=123, device=cuda)
+    assert ptr.numel() == n + 1 and int(ptr[-1]) == m == idx.numel()
+    val = synth.gcn_norm_val(ptr, idx)
+    g = torch.Generator(device=cuda).manual_seed(5)
+    X1 = torch.rand((n, F), device=cuda, generator=g)
+    X2 = torch.randn((n, F), device=cuda, generator=g)
+    agg = gn.Aggregator(ptr, idx, val)
+    Y1 = agg.gcn_run(X1, torch.empty((n, F), device=cuda))
+    Y2 = agg.gcn_run(X2, torch.empty((n, F), device=cuda))
+
+    # determinism of the un-scheduled path
+    assert torch.equal(Y1, agg.gcn_run(X1, torch.empty((n, F), device=cuda)))
+
+    # oracle on a leading row sample
+    rows = min(n, 3000)
+    hp = ptr[: rows + 1].cpu().numpy()
+    e = int(hp[-1])
+    y64, scale = orc.spmm_f64(np.ascontiguousarray(hp), idx[:e].cpu().numpy(), val[:e].cpu().numpy(), X2.cpu().numpy())
+    assert rel_gate(Y2[:rows].cpu().numpy(), y64, scale, 1e-5)[0] == 0
+
+    # magnitude scale per element for the property gates: |A| |X| computed by the same kernel (all terms >= 0)
+    absY = agg.gcn_run(X2.abs() + X1, torch.empty((n, F), device=cuda)).double()
+
+    # linearity: A(2 X1 - 3 X2) == 2 A X1 - 3 A X2
+    Y3 = agg.gcn_run(2 * X1 - 3 * X2, torch.empty((n, F), device=cuda))
+    lin_err = (Y3.double() - (2 * Y1.double() - 3 * Y2.double())).abs()
+    assert bool((lin_err <= 5e-5 * absY + 1e-30).all())
+
+    # column checksum against an independent fp64 scatter: sum_r Y[r,:] == sum_u w_u X[u,:],  w_u = sum of val over edges with source u
+    w = torch.zeros(n, dtype=torch.float64, device=cuda).index_add_(0, idx.long(), val.double())
+    want = (w[:, None] * X2.double()).sum(0)
+    mag = (w[:, None] * X2.double().abs()).sum(0)
+    got = Y2.double().sum(0)
+    assert bool(((got - want).abs() <= 1e-5 * mag).all())
+
+    # row sums: X = 1 -> every column of Y equals the row sum of val (torch segment sum in fp64 as the check)
+    ones = torch.ones((n, F), device=cuda)
+    Yr = agg.gcn_run(ones, torch.empty((n, F), device=cuda))
+    cs = torch.zeros(m + 1, dtype=torch.float64, device=cuda)
+    cs[1:] = torch.cumsum(val.double(), 0)
+    rowsum = cs[ptr[1:].long()] - cs[ptr[:-1].long()]
+    assert bool(((Yr.double() - rowsum[:, None]).abs() <= 1e-5 * rowsum[:, None] + 1e-12).all())
+    center = agg.add_to_center(val, torch.empty(n, device=cuda))  # the edge-parallel row-sum kernel, same quantity
+    assert bool(((center.double() - rowsum).abs() <= 1e-5 * rowsum + 1e-12).all())
+
+    # neighbour-grouped schedule gives the same aggregation
+    nt = agg.schedule(1, [32])
+    deg = (ptr[1:] - ptr[:-1]).long()
+    assert nt == int(((deg + 31) // 32).sum())  # G = sum ceil(deg/NG), graph_schedule.h:100-120
+    Ys = agg.gcn_run(X2, torch.empty((n, F), device=cuda), scheduled=True)
+    assert bool(((Ys.double() - Y2.double()).abs() <= 2e-5 * absY + 1e-30).all())
+
+    # layer == aggregation followed by an fp64 matmul, on a row sample
+    if F <= 256:
+        W = torch.randn((F, F), device=cuda, generator=g) / F ** 0.5
+        AX = torch.empty((n, F), device=cuda)
+        H = agg.gcn_layer(X2, W, torch.empty((n, F), device=cuda), AX)
+        assert torch.equal(AX, Y2)
+        sl = slice(0, 5000)
+        want = AX[sl].double() @ W.double()
+        mag = AX[sl].double().abs() @ W.double().abs()
+        assert bool(((H[sl].double() - want).abs() <= 1e-5 * mag + 1e-30).all())
+
+
+def test_full_size_gat_properties(gn, orc, cuda):
+    """C3: fused GAT on the proteins-shaped graph, F = 64"""
+    n, m = synth.shape_of("proteins")
+    F = 64
+    ptr, idx = synth.rmat_csr(n, m, seed=123, device=cuda)
+    g = torch.Generator(device=cuda).manual_seed(6)
+    X = torch.randn((n, F), device=cuda, generator=g)
+    att = torch.randn((n, 2), device=cuda, generator=g)
+    agg = gn.Aggregator(ptr, idx)
+    Y = agg.gat_run(X, att, torch.empty((n, F), device=cuda))
+    assert torch.equal(Y, agg.gat_run(X, att, torch.empty((n, F), device=cuda)))
+    rows = 2000
+    hp = ptr[: rows + 1].cpu().numpy()
+    e = int(hp[-1])
+    y64, _, scale = orc.gat_f64(np.ascontiguousarray(hp), idx[:e].cpu().numpy(), att.cpu().numpy(), X.cpu().numpy())
+    assert rel_gate(Y[:rows].cpu().numpy(), y64, scale, 1.2e-5)[0] == 0
+    # a convex combination: with X = const every non-empty row returns that constant, empty rows 0
+    Yc = agg.gat_run(torch.full((n, F), 3.0, device=cuda), att, torch.empty((n, F), device=cuda))
+    deg = ptr[1:] - ptr[:-1]
+    assert bool(((Yc[deg > 0] - 3.0).abs() <= 3e-5).all()) and bool((Yc[deg == 0] == 0).all())
+    # the un-fused pipeline (edge softmax -> GCN aggregation) agrees with the fused kernel
+    sm = agg.edge_softmax(att, torch.empty(m, device=cuda))
+    gcn = gn.Aggregator(ptr, idx, sm)
+    Yu = gcn.gcn_run(X, torch.empty((n, F), device=cuda))
+    absY = gcn.gcn_run(X.abs(), torch.empty((n, F), device=cuda))
+    assert bool(((Yu - Y).abs() <= 3e-5 * absY + 1e-30).all())
+    agg.schedule(1, [32])
+    Ys = agg.gat_run(X, att, torch.empty((n, F), device=cuda), scheduled=True)
+    assert bool(((Ys - Y).abs() <= 3e-5 * absY + 1e-30).all())

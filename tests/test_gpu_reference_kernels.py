@@ -198,6 +198,12 @@ def test_timing_vs_reference_kernels_full_size(gn, orc, ref, cuda, shape, F):
     gat = gn.Aggregator(ptr, idx)
     out["ours_gat_ms"] = timeit(lambda: gat.gat_run(X, att, Y))
     out["ref_aggr_gat_ms"] = timeit(lambda: ref.ref_gat_run(hg, P(X), P(att), P(Yr), max(128, F), 0, F))
+    if F == 32:  # the per-edge MLP aggregator exists for F = 32 only in the reference (aggr_nn.h)
+        Wm = torch.randn((32, 32), device=cuda, generator=g) / 32 ** 0.5
+        hm = C.c_void_p(ref.ref_mlp_create(P(ptr), P(idx), n, m, P(Wm)))
+        mlp = gn.Aggregator(ptr, idx)
+        out["ours_mlp_ms"] = timeit(lambda: mlp.mlp_run(X, Wm, Y))
+        out["ref_aggr_mlp_ms"] = timeit(lambda: ref.ref_mlp_run(hm, P(X), P(Yr), 128, 0), reps=3)
     out["gather_model_bytes"] = 4 * (n + 1) + 8 * m + 4 * m * F + 4 * n * F
     for k in ("ours_gcn", "ref_aggr_gcn", "ours_gcn_sched", "ref_aggr_gcn_target"):
         out[k + "_GBps"] = out["gather_model_bytes"] / out[k + "_ms"] / 1e6

@@ -89,6 +89,66 @@ def _worker_pruned(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _worker_incremental(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    import oracle as orc
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n_per, F, chunks = 300, 8, 3
+        Xfull = np.random.default_rng(3).standard_normal((world * n_per, F)).astype(np.float32)
+        ptr, idx = synth.small_random_csr(n_per, 6.0, 60 + rank, num_src=world * n_per, hub=700)
+        idx = (idx // 2 * 2).astype(np.int32)
+        val = np.random.default_rng(rank).standard_normal(len(idx)).astype(np.float32)
+        plan = partition.incremental_plan(torch.from_numpy(ptr), torch.from_numpy(idx), n_per, world, rank, chunks)
+        shard = torch.from_numpy(Xfull[rank * n_per:(rank + 1) * n_per].copy())
+        recv = torch.full((plan["num_recv"], F), float("nan"))
+        Y = np.zeros((n_per, F), np.float32)
+        rb = plan["row_bounds"]
+        ok = True
+        for c in range(chunks):
+            o, cnt = plan["recv_offset"][c], sum(plan["recv_counts"][c])
+            send = shard[plan["send_rows"][c]]
+            out = torch.empty((cnt, F))
+            dist.all_to_all_single(out, send, output_split_sizes=plan["recv_counts"][c], input_split_sizes=plan["send_counts"][c])
+            recv[o:o + cnt] = out
+            r0, r1 = int(rb[c]), int(rb[c + 1])
+            e0, e1 = int(ptr[r0]), int(ptr[r1])
+            sub_idx = plan["idx_compact"][e0:e1].numpy()
+            # chunk c may only touch rows that have arrived by stage c
+            ok = ok and (len(sub_idx) == 0 or sub_idx.max() < o + cnt)
+            y, _ = orc.spmm_f64((ptr[r0:r1 + 1] - e0).astype(np.int32), sub_idx, val[e0:e1], recv.numpy())
+            Y[r0:r1] = y
+        want, _ = orc.spmm_f64(ptr, idx, val, Xfull)
+        ok = ok and np.array_equal(Y, want) and plan["num_recv"] == len(np.unique(idx))
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_incremental_halo_plan_gloo_world2():
+    """pipelined pruned exchange: each row chunk fetches only sources no earlier chunk fetched; results equal"""
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_incremental, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert sorted(q.get(timeout=5) for _ in range(2)) == [(0, True), (1, True)]
+
+
 def test_pruned_halo_plan_gloo_world2():
     """only the referenced source rows travel; the re-indexed CSR on the compact buffer gives identical sums"""
     import torch.multiprocessing as mp
