@@ -127,8 +127,9 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
     // ---------------- the walk: one virtual warp per item ----------------
     const int vw = lane / LPR;
     const int vl = lane % LPR;
+    const unsigned vw_mask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (vw * LPR));  // lanes of this virtual warp
     const int e0 = wbase + vw * EB;
-    if (e0 >= p.num_edges) return;  // no *_sync below this point
+    if (e0 >= p.num_edges) return;  // below, only shuffles restricted to the lanes of one virtual warp (vw_mask)
     const int e1 = min(p.num_edges, e0 + EB);
     const int64_t item = gwarp * VPW + vw;
     const int F = p.F;
@@ -236,7 +237,23 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
                 if (NV > 1) v1[u] = __ldg(reinterpret_cast<const float4 *>(x + second));
             }
             float wout = 0.f;
-            if (MODE != kModeGAT && row_end - e >= U) {
+            if (MODE == kModeGAT && row_end - e >= U) {
+                // no row ends inside the batch: lane u of the virtual warp evaluates the weight of edge u once
+                // (one MUFU per edge instead of one per edge-lane) and the virtual warp shares it by shuffle
+                float wgt = 0.f;
+                if (vl < U) {
+                    const float sc = a_dst + my_val[k + vl];
+                    wgt = __expf(fmaxf(sc, sc * p.slope));  // aggr_gat.h:143
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const float wu = __shfl_sync(vw_mask, wgt, u, LPR);
+                    den += wu;
+                    fma4(acc0, wu, v0[u]);
+                    if (NV > 1) fma4(acc1, wu, v1[u]);
+                }
+                wout = wgt;
+            } else if (MODE != kModeGAT && row_end - e >= U) {
                 // no row ends inside the batch: straight FMA chain
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
