@@ -48,6 +48,9 @@ struct AggParams {
     int bulk_ok;                         // idx/val 16-byte aligned -> TMA staging allowed
     int num_fine_items;                  // entries of item_row
     int accumulate;                      // GCN un-scheduled: Y += A*X instead of Y = A*X
+    // row-range launch (un-scheduled only): rows [row_lo, row_hi) = edges [edge_lo, edge_hi); the whole graph is
+    // (0, num_rows, 0, num_edges).  Items keep their global numbering, a range just clips them.
+    int row_lo, row_hi, edge_lo, edge_hi;
 };
 
 enum { kModeGCN = 0, kModeGAT = 1, kModeMLP = 2 };
@@ -78,9 +81,9 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int64_t gwarp = (int64_t)blockIdx.x * kCtaWarps + warp;
+    const int64_t gwarp = (int64_t)(p.edge_lo / kWarpEdges) + (int64_t)blockIdx.x * kCtaWarps + warp;
     const int64_t wbase64 = gwarp * kWarpEdges;
-    if (wbase64 >= p.num_edges) return;  // whole warp idle (warp-uniform)
+    if (wbase64 >= p.edge_hi) return;  // whole warp idle (warp-uniform)
     const int wbase = (int)wbase64;
     const int wcnt = min(kWarpEdges, p.num_edges - wbase);
 
@@ -107,9 +110,9 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
         }
         // the start row of this lane's item is looked up while the bulk copy is in flight
         {
-            const int e0s = wbase + (lane / LPR) * EB;
-            if (e0s < p.num_edges) {
-                first_row = (e0s == 0) ? 0 : item_start_row(p, e0s);
+            const int e0s = max(wbase + (lane / LPR) * EB, p.edge_lo);
+            if (e0s < p.edge_hi) {
+                first_row = (e0s == p.edge_lo) ? p.row_lo : item_start_row(p, e0s);
                 first_row_end = __ldg(p.ptr + first_row + 1);
                 first_row_begin = __ldg(p.ptr + first_row);
             }
@@ -128,9 +131,9 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
     const int vw = lane / LPR;
     const int vl = lane % LPR;
     const unsigned vw_mask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (vw * LPR));  // lanes of this virtual warp
-    const int e0 = wbase + vw * EB;
-    if (e0 >= p.num_edges) return;  // below, only shuffles restricted to the lanes of one virtual warp (vw_mask)
-    const int e1 = min(p.num_edges, e0 + EB);
+    const int e0 = max(wbase + vw * EB, p.edge_lo);            // item clipped to the launched edge range
+    const int e1 = min(wbase + vw * EB + EB, p.edge_hi);
+    if (e0 >= e1) return;  // below, only shuffles restricted to the lanes of one virtual warp (vw_mask)
     const int64_t item = gwarp * VPW + vw;
     const int F = p.F;
 
@@ -160,7 +163,7 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
         auto flush = [&](bool at_item_end) {
             if (SCHED) {
                 const int t = __ldg(p.target + row);
-                const bool merge = !at_item_end && (row + 1 < p.num_rows) && (__ldg(p.target + row + 1) == t);
+                const bool merge = !at_item_end && (row + 1 < p.row_hi) && (__ldg(p.target + row + 1) == t);
                 if (!merge) {  // consecutive groups of one target are summed in registers first
                     float *y = p.Y + (size_t)t * F + col;
                     if (act0) red_add_f4(y, acc0);
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
                 den = 0.f;
             }
             ++row;
-            if (row < p.num_rows) {
+            if (row < p.row_hi) {
                 row_end = __ldg(p.ptr + row + 1);
                 if (MODE == kModeGAT) a_dst = __ldg(p.att + 2 * (size_t)(SCHED ? __ldg(p.target + row) : row));
                 if (MODE == kModeMLP) load_dst(row);
@@ -215,8 +218,57 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
         const uint32_t row_bytes = (uint32_t)F * 4u;
         const int second = act1 ? LPR * 16 : 0;  // byte offset of the second float4 (NV == 2)
 
-        // ---- full batches: U edges, idx/val fetched as 128-bit shared loads (e - wbase is a multiple
-        // of U here because items start on multiples of U and only the last batch can be short)
+        // a batch of nb < U edges starting at e (scalar shared loads, clamped): used to re-align the first item of a
+        // clipped row range and for the ragged end of the last item
+        auto short_batch = [&](const int nb) {
+            int src[U];
+            float w[U];
+            float4 v0[U], v1[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int k = min(e + u, e1 - 1) - wbase;
+                src[u] = my_idx[k];
+                w[u] = (MODE == kModeMLP) ? 0.f : my_val[k];
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const char *x = xb + (size_t)(uint32_t)src[u] * row_bytes;
+                v0[u] = __ldg(reinterpret_cast<const float4 *>(x));
+                if (NV > 1) v1[u] = __ldg(reinterpret_cast<const float4 *>(x + second));
+            }
+            float wout = 0.f;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (u < nb) {
+                    while (row_end == e + u) flush(false);
+                    float wu = w[u];
+                    if (MODE == kModeGAT) {
+                        const float sc = a_dst + wu;
+                        wu = __expf(fmaxf(sc, sc * p.slope));
+                        den += wu;
+                        if (SCHED && vl == u % LPR) wout = wu;
+                    }
+                    if (MODE == kModeMLP) {
+                        relu_add4(acc0, pd0, v0[u]);
+                        if (NV > 1) relu_add4(acc1, pd1, v1[u]);
+                    } else {
+                        fma4(acc0, wu, v0[u]);
+                        if (NV > 1) fma4(acc1, wu, v1[u]);
+                    }
+                }
+            }
+            if (MODE == kModeGAT && SCHED && cb == 0 && p.newval != nullptr) {
+                if (vl < nb) p.newval[e + vl] = wout;
+            }
+            e += nb;
+        };
+
+        {
+            const int head = min((4 - ((e - wbase) & 3)) & 3, e1 - e);  // 128-bit shared loads below need e - wbase = 0 mod 4
+            if (head > 0) short_batch(head);
+        }
+
+        // ---- full batches: U edges, idx/val fetched as 128-bit shared loads
         while (e + U <= e1) {
             const int k = e - wbase;
             int src[U];
@@ -292,54 +344,11 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
             e += U;
         }
 
-        // ---- the short last batch (only the last item of the graph has one)
-        if (e < e1) {
-            const int nb = e1 - e;
-            int src[U];
-            float w[U];
-            float4 v0[U], v1[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int k = min(e + u, e1 - 1) - wbase;
-                src[u] = my_idx[k];
-                w[u] = (MODE == kModeMLP) ? 0.f : my_val[k];
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const char *x = xb + (size_t)(uint32_t)src[u] * row_bytes;
-                v0[u] = __ldg(reinterpret_cast<const float4 *>(x));
-                if (NV > 1) v1[u] = __ldg(reinterpret_cast<const float4 *>(x + second));
-            }
-            float wout = 0.f;
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (u < nb) {
-                    while (row_end == e + u) flush(false);
-                    float wu = w[u];
-                    if (MODE == kModeGAT) {
-                        const float sc = a_dst + wu;
-                        wu = __expf(fmaxf(sc, sc * p.slope));
-                        den += wu;
-                        if (SCHED && vl == u % LPR) wout = wu;
-                    }
-                    if (MODE == kModeMLP) {
-                        relu_add4(acc0, pd0, v0[u]);
-                        if (NV > 1) relu_add4(acc1, pd1, v1[u]);
-                    } else {
-                        fma4(acc0, wu, v0[u]);
-                        if (NV > 1) fma4(acc1, wu, v1[u]);
-                    }
-                }
-            }
-            if (MODE == kModeGAT && SCHED && cb == 0 && p.newval != nullptr) {
-                if (vl < nb) p.newval[e + vl] = wout;
-            }
-            e = e1;
-        }
+        if (e < e1) short_batch(e1 - e);
 
         // item end
         if (row_end == e1) {
-            while (row < p.num_rows && row_end == e1) flush(true);  // row closes here (+ trailing empty rows)
+            while (row < p.row_hi && row_end == e1) flush(true);  // row closes here (+ trailing empty rows)
         } else if (SCHED) {
             flush(true);
         } else if (carry_in) {
@@ -370,9 +379,10 @@ constexpr int kFixChunk = 32;
 template <int MODE, int PHASE>
 __global__ void __launch_bounds__(256) agg_fixup_kernel(const AggParams p, int EB, int64_t num_items)
 {
-    const int64_t item = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // items of the launched edge range only; the first one is clipped at a row start, so nothing enters it
+    const int64_t item = (int64_t)(p.edge_lo / EB) + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (item < 1 || item >= num_items) return;
+    if (item < 1 || item >= num_items || item * EB >= p.edge_hi || item * EB <= p.edge_lo) return;
     const int e0 = (int)(item * EB);
     const int row = item_start_row(p, e0);
     const int rs = __ldg(p.ptr + row);

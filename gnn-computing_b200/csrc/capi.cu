@@ -88,6 +88,10 @@ struct gnnagg_aggregator {
     bool s_idx_owned = false;  // neighbour grouping keeps the edge order: its idx aliases d_idx
     int64_t launches = 0;
     int warp_edges = 0;  // 0 = automatic
+    // host-buffer entry points: the result is copied back per row chunk on a second stream while the next chunk computes
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t chunk_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t copies_done = nullptr;
     // optional per-kernel timing (gnnagg_profile_enable)
     bool prof = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // begin, agg0, agg1, agg_end, end
@@ -187,7 +191,8 @@ template <int MODE, bool SCHED, int WE>
 static void launch_agg_we(const AggParams &p, cudaStream_t st)
 {
     const int F = p.F;
-    const unsigned grid = (unsigned)cdiv(p.num_edges, (int64_t)WE * kCtaWarps);
+    const int64_t first = (int64_t)(p.edge_lo / WE) * WE;  // warps keep their global 512-edge alignment (TMA staging)
+    const unsigned grid = (unsigned)cdiv(p.edge_hi - first, (int64_t)WE * kCtaWarps);
     if (F <= 32)
         agg_kernel<8, 1, MODE, SCHED, WE><<<grid, kCtaThreads, 0, st>>>(p);
     else if (F <= 64)
@@ -199,8 +204,12 @@ static void launch_agg_we(const AggParams &p, cudaStream_t st)
 }
 
 template <int MODE, bool SCHED>
-static int launch_agg(gnnagg_aggregator *a, const AggParams &p, cudaStream_t st)
+static int launch_agg(gnnagg_aggregator *a, AggParams p, cudaStream_t st)
 {
+    if (p.row_hi == 0 && p.edge_hi == 0) {  // callers that do not set a row range get the whole graph
+        p.row_lo = 0, p.row_hi = p.num_rows, p.edge_lo = 0, p.edge_hi = p.num_edges;
+    }
+    if (p.edge_hi <= p.edge_lo) return GNNAGG_OK;
     PROF_RECORD(a, 1, st);
     if (warp_edges_for(a, p.num_edges) == 128)
         launch_agg_we<MODE, SCHED, 128>(p, st);
@@ -211,11 +220,12 @@ static int launch_agg(gnnagg_aggregator *a, const AggParams &p, cudaStream_t st)
     if (!SCHED) {
         const int EB = item_edges_for(a, p.F, p.num_edges);
         const int64_t items = cdiv(p.num_edges, EB);
-        if (items > 1) {
-            agg_fixup_kernel<MODE, 1><<<(unsigned)cdiv(items, 8), 256, 0, st>>>(p, EB, items);
+        const int64_t range_items = cdiv(p.edge_hi, EB) - p.edge_lo / EB;  // items touched by the launched range
+        if (range_items > 1) {
+            agg_fixup_kernel<MODE, 1><<<(unsigned)cdiv(range_items, 8), 256, 0, st>>>(p, EB, items);
             LAUNCH_CHECK(a);
-            if (items > kFixChunk + 1) {  // a row can only span more than kFixChunk carry items then
-                agg_fixup_kernel<MODE, 2><<<(unsigned)cdiv(items, 8), 256, 0, st>>>(p, EB, items);
+            if (range_items > kFixChunk + 1) {  // a row can only span more than kFixChunk carry items then
+                agg_fixup_kernel<MODE, 2><<<(unsigned)cdiv(range_items, 8), 256, 0, st>>>(p, EB, items);
                 LAUNCH_CHECK(a);
             }
         }
@@ -225,8 +235,9 @@ static int launch_agg(gnnagg_aggregator *a, const AggParams &p, cudaStream_t st)
 
 static int aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// rows [row_lo, row_hi) of the un-scheduled aggregation (row_hi < 0: all rows); Y is indexed by GLOBAL row
 static int gcn_run_core(gnnagg_aggregator *a, const float *X, float *Y, int F, int scheduled, cudaStream_t st,
-                        int accumulate = 0)
+                        int accumulate = 0, int row_lo = 0, int row_hi = -1, int edge_lo = 0, int edge_hi = 0)
 {
     if (a && a->n == 0) return GNNAGG_OK;  // an empty row block (possible after edge-balanced partitioning)
     if (!a || !X || !Y) return set_error(GNNAGG_ERR_ARG, "gnnagg_gcn_run: NULL argument");
@@ -268,7 +279,58 @@ static int gcn_run_core(gnnagg_aggregator *a, const float *X, float *Y, int F, i
     p.num_rows = a->n;
     p.num_edges = a->m;
     p.bulk_ok = aligned16(p.idx) && aligned16(p.val);
+    if (row_hi >= 0) {
+        p.row_lo = row_lo, p.row_hi = row_hi, p.edge_lo = edge_lo, p.edge_hi = edge_hi;
+        if (row_hi <= row_lo) return GNNAGG_OK;
+        if (edge_hi <= edge_lo) {  // a chunk of empty rows
+            if (!accumulate) CUDA_TRY(cudaMemsetAsync(Y + (size_t)row_lo * F, 0, (size_t)(row_hi - row_lo) * F * sizeof(float), st));
+            return GNNAGG_OK;
+        }
+    }
     return launch_agg<kModeGCN, false>(a, p, st);
+}
+
+// host mirror of the row pointers (needed to cut row chunks)
+static int host_ptr(gnnagg_aggregator *a, const int **out)
+{
+    if (a->h_ptr_user) {
+        *out = a->h_ptr_user;
+        return GNNAGG_OK;
+    }
+    if (a->h_ptr.empty()) {
+        a->h_ptr.resize((size_t)a->n + 1);
+        CUDA_TRY(cudaMemcpy(a->h_ptr.data(), a->d_ptr, a->h_ptr.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    *out = a->h_ptr.data();
+    return GNNAGG_OK;
+}
+
+// edge-balanced row chunk boundaries: bounds[0..chunks]
+static void row_chunks(const int *hp, int n, int m, int chunks, int *bounds)
+{
+    bounds[0] = 0;
+    for (int c = 1; c < chunks; ++c) {
+        const int64_t target = (int64_t)m * c / chunks;
+        int lo = bounds[c - 1], hi = n;  // first row with ptr[row] >= target
+        while (lo < hi) {
+            const int mid = lo + (hi - lo) / 2;
+            if (hp[mid] >= target)
+                hi = mid;
+            else
+                lo = mid + 1;
+        }
+        bounds[c] = lo;
+    }
+    bounds[chunks] = n;
+}
+
+static int ensure_copy_stream(gnnagg_aggregator *a)
+{
+    if (a->copy_stream) return GNNAGG_OK;
+    CUDA_TRY(cudaStreamCreateWithFlags(&a->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; ++i) CUDA_TRY(cudaEventCreateWithFlags(&a->chunk_done[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&a->copies_done, cudaEventDisableTiming));
+    return GNNAGG_OK;
 }
 
 static int gat_run_core(gnnagg_aggregator *a, const float *X, const float *att, float *Y, int F, float slope,
@@ -476,6 +538,10 @@ int gnnagg_destroy(gnnagg_aggregator *a)
     cudaFree(a->st_att);
     for (int i = 0; i < 5; ++i)
         if (a->ev[i]) cudaEventDestroy(a->ev[i]);
+    for (int i = 0; i < 8; ++i)
+        if (a->chunk_done[i]) cudaEventDestroy(a->chunk_done[i]);
+    if (a->copies_done) cudaEventDestroy(a->copies_done);
+    if (a->copy_stream) cudaStreamDestroy(a->copy_stream);
     delete a;
     return GNNAGG_OK;
 }
@@ -831,35 +897,75 @@ int gnnagg_validate_reordered(const float *d_ref, const float *d_ans, const int 
 }
 
 // ------------------------------------------------------------------ host-buffer entry points
+// Host-buffer GCN aggregation / layer.  The un-scheduled path is pipelined over kHostChunks edge-balanced row
+// chunks: chunk c is aggregated (and combined) on `stream` while the finished rows of chunk c-1 travel back to
+// the host on a second stream, so only the input copy and one chunk of the output copy are exposed.
+constexpr int kHostChunks = 4;
+
+static int gcn_host_pipeline(gnnagg_aggregator *a, const float *h_X, const float *h_W, float *h_out, int feat_in,
+                             int feat_out, int scheduled, cudaStream_t st)
+{
+    const bool layer = h_W != nullptr;
+    const int fo = layer ? feat_out : feat_in;
+    const size_t cin = (size_t)a->n * feat_in, cout = (size_t)a->n * fo;
+    if (int rc = ensure(a->st_in, a->st_in_cap, cin)) return rc;
+    if (int rc = ensure(a->st_out, a->st_out_cap, cout)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(a->st_in, h_X, cin * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (layer) {
+        if (int rc = ensure(a->st_w, a->st_w_cap, (size_t)feat_in * feat_out)) return rc;
+        if (int rc = ensure(a->ax, a->ax_cap, cin)) return rc;
+        CUDA_TRY(cudaMemcpyAsync(a->st_w, h_W, (size_t)feat_in * feat_out * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    float *agg_out = layer ? a->ax : a->st_out;
+    if (scheduled || a->n < 4096) {  // scheduled order is not row-contiguous; tiny graphs are not worth chunking
+        if (int rc = gcn_run_impl(a, a->st_in, agg_out, feat_in, scheduled, st, !layer)) return rc;
+        if (layer && a->n > 0) {
+            if (int rc = dense_nn_launch(a->ax, a->st_w, a->st_out, a->n, feat_out, feat_in, st)) return rc;
+            ++a->launches;
+        }
+        CUDA_TRY(cudaMemcpyAsync(h_out, a->st_out, cout * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return GNNAGG_OK;
+    }
+    if (int rc = check_feat(feat_in)) return rc;
+    if (!a->d_val && a->m > 0) return set_error(GNNAGG_ERR_STATE, "edge values not set (gnnagg_set_val)");
+    const int *hp = nullptr;
+    if (int rc = host_ptr(a, &hp)) return rc;
+    if (int rc = ensure_copy_stream(a)) return rc;
+    int bounds[kHostChunks + 1];
+    row_chunks(hp, a->n, a->m, kHostChunks, bounds);
+    for (int c = 0; c < kHostChunks; ++c) {
+        const int r0 = bounds[c], r1 = bounds[c + 1];
+        if (r1 <= r0) continue;
+        if (int rc = gcn_run_core(a, a->st_in, agg_out, feat_in, 0, st, 0, r0, r1, hp[r0], hp[r1])) return rc;
+        if (layer) {
+            if (int rc = dense_nn_launch(a->ax + (size_t)r0 * feat_in, a->st_w, a->st_out + (size_t)r0 * fo, r1 - r0, feat_out,
+                                         feat_in, st))
+                return rc;
+            ++a->launches;
+        }
+        CUDA_TRY(cudaEventRecord(a->chunk_done[c], st));
+        CUDA_TRY(cudaStreamWaitEvent(a->copy_stream, a->chunk_done[c], 0));
+        CUDA_TRY(cudaMemcpyAsync(h_out + (size_t)r0 * fo, a->st_out + (size_t)r0 * fo, (size_t)(r1 - r0) * fo * sizeof(float),
+                                 cudaMemcpyDeviceToHost, a->copy_stream));
+    }
+    CUDA_TRY(cudaEventRecord(a->copies_done, a->copy_stream));
+    CUDA_TRY(cudaStreamWaitEvent(st, a->copies_done, 0));  // the caller's stream is ordered after the copies as well
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return GNNAGG_OK;
+}
+
 int gnnagg_gcn_run_host(gnnagg_aggregator *a, const float *h_X, float *h_Y, int feat, int scheduled, void *stream)
 {
     if (!a || !h_X || !h_Y) return set_error(GNNAGG_ERR_ARG, "gnnagg_gcn_run_host: NULL argument");
-    cudaStream_t st = (cudaStream_t)stream;
-    const size_t cnt = (size_t)a->n * feat;
-    if (int rc = ensure(a->st_in, a->st_in_cap, cnt)) return rc;
-    if (int rc = ensure(a->st_out, a->st_out_cap, cnt)) return rc;
-    CUDA_TRY(cudaMemcpyAsync(a->st_in, h_X, cnt * sizeof(float), cudaMemcpyHostToDevice, st));
-    if (int rc = gcn_run_impl(a, a->st_in, a->st_out, feat, scheduled, st)) return rc;
-    CUDA_TRY(cudaMemcpyAsync(h_Y, a->st_out, cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    return GNNAGG_OK;
+    return gcn_host_pipeline(a, h_X, nullptr, h_Y, feat, feat, scheduled, (cudaStream_t)stream);
 }
 
 int gnnagg_gcn_layer_host(gnnagg_aggregator *a, const float *h_X, const float *h_W, float *h_H, int feat_in,
                           int feat_out, int scheduled, void *stream)
 {
     if (!a || !h_X || !h_W || !h_H) return set_error(GNNAGG_ERR_ARG, "gnnagg_gcn_layer_host: NULL argument");
-    cudaStream_t st = (cudaStream_t)stream;
-    const size_t cin = (size_t)a->n * feat_in, cout = (size_t)a->n * feat_out, cw = (size_t)feat_in * feat_out;
-    if (int rc = ensure(a->st_in, a->st_in_cap, cin)) return rc;
-    if (int rc = ensure(a->st_out, a->st_out_cap, cout)) return rc;
-    if (int rc = ensure(a->st_w, a->st_w_cap, cw)) return rc;
-    CUDA_TRY(cudaMemcpyAsync(a->st_in, h_X, cin * sizeof(float), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(a->st_w, h_W, cw * sizeof(float), cudaMemcpyHostToDevice, st));
-    if (int rc = gnnagg_gcn_layer(a, a->st_in, a->st_w, a->st_out, nullptr, feat_in, feat_out, scheduled, stream)) return rc;
-    CUDA_TRY(cudaMemcpyAsync(h_H, a->st_out, cout * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    return GNNAGG_OK;
+    return gcn_host_pipeline(a, h_X, h_W, h_H, feat_in, feat_out, scheduled, (cudaStream_t)stream);
 }
 
 int gnnagg_gat_run_host(gnnagg_aggregator *a, const float *h_X, const float *h_att, float *h_Y, int feat,

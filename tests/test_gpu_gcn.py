@@ -138,6 +138,34 @@ def test_gcn_host_entry_point(gn, orc, cuda):
     assert rel_gate(hY.numpy(), y64, scale, TOL)[0] == 0
 
 
+@pytest.mark.parametrize("F", [32, 128, 256])
+@pytest.mark.parametrize("we", [0, 512])
+def test_host_entry_points_pipelined_row_chunks(gn, orc, cuda, F, we):
+    """above 4096 rows the host-buffer calls aggregate edge-balanced ROW CHUNKS (clipped items) and copy each
+    chunk back while the next one computes; hubs, empty chunks' rows and chunk borders inside items included"""
+    from gnnagg import synth
+
+    ptr, idx = synth.small_random_csr(9000, 14.0, F, empty_frac=0.3, hub=30000)
+    n, m = len(ptr) - 1, len(idx)
+    X, val = rand_inputs(n, m, F, seed=3)
+    agg = gn.Aggregator(dev(ptr), dev(idx), dev(val))
+    agg.set_warp_edges(we)
+    hX = torch.from_numpy(X).pin_memory()
+    hY = torch.full((n, F), float("nan")).pin_memory()
+    agg.gcn_run_host(hX, hY)
+    y64, scale = orc.spmm_f64(ptr, idx, val, X)
+    assert rel_gate(hY.numpy(), y64, scale, TOL)[0] == 0
+    # identical to the single-launch device path (same items, same order of additions)
+    Yd = agg.gcn_run(dev(X), torch.empty((n, F), device=cuda))
+    assert np.array_equal(hY.numpy(), Yd.cpu().numpy())
+    if F <= 256:
+        W = (np.random.default_rng(4).standard_normal((F, 64)) / np.sqrt(F)).astype(np.float32)
+        hH = torch.full((n, 64), float("nan")).pin_memory()
+        agg.gcn_layer_host(hX, torch.from_numpy(W).pin_memory(), hH)
+        _, h64, hs = orc.gcn_layer_f64(ptr, idx, val, X, W)
+        assert rel_gate(hH.numpy(), h64, hs, TOL)[0] == 0
+
+
 def test_naive_spmm_and_validators(gn, orc, cuda):
     """include/spmm.h: spmm<>, valid(), validReordered()"""
     ptr, idx = make_graph("medium", seed=5)
