@@ -75,8 +75,8 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
     constexpr int CHUNK = LPR * 4 * NV;       // feature columns covered per pass
     static_assert(LPR >= 8 && U <= LPR && EB % U == 0, "virtual warp narrower than 8 lanes is not supported");
 
-    __shared__ __align__(16) int s_idx[kCtaWarps][kWarpEdges];
-    __shared__ __align__(16) float s_val[kCtaWarps][kWarpEdges];
+    // per warp: [0] = idx, [1] = val (float bits); one base address serves both (val = idx + kWarpEdges words)
+    __shared__ __align__(16) int s_stage[kCtaWarps][2][kWarpEdges];
     __shared__ __align__(8) uint64_t s_bar[kCtaWarps];
 
     const int warp = threadIdx.x >> 5;
@@ -88,8 +88,8 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
     const int wcnt = min(kWarpEdges, p.num_edges - wbase);
 
     // ---------------- stage idx (+val) of this warp's edges ----------------
-    int *my_idx = s_idx[warp];
-    float *my_val = s_val[warp];
+    int *const my_idx = s_stage[warp][0];
+    float *const my_val = reinterpret_cast<float *>(my_idx + kWarpEdges);
     int first_row = 0, first_row_end = 0, first_row_begin = 0;
     {
         const int nb = p.bulk_ok ? (wcnt & ~3) : 0;  // bulk copies need 16-byte multiples
@@ -214,8 +214,9 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
 
         // gather base of this lane: column `col` of row 0 (inactive lanes of a partial chunk read
         // column 0 instead of being predicated off; their results are never stored)
-        const char *xb = reinterpret_cast<const char *>(p.X + (act0 ? col : 0));
-        const uint32_t row_bytes = (uint32_t)F * 4u;
+        const char *xb = reinterpret_cast<const char *>(opaque64(reinterpret_cast<uint64_t>(p.X + (act0 ? col : 0))));
+        const uint32_t row_bytes = opaque32((uint32_t)F * 4u);
+        const uint32_t s_base = opaque32(smem_u32(my_idx));  // shared address of this warp's staged idx (val: + 4*kWarpEdges)
         const int second = act1 ? LPR * 16 : 0;  // byte offset of the second float4 (NV == 2)
 
         // a batch of nb < U edges starting at e (scalar shared loads, clamped): used to re-align the first item of a
@@ -275,9 +276,9 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
             float w[U];
 #pragma unroll
             for (int q = 0; q < U / 4; ++q) {
-                const int4 i4 = *reinterpret_cast<const int4 *>(my_idx + k + 4 * q);
+                const int4 i4 = lds_i4(s_base + 4u * (uint32_t)(k + 4 * q));
                 const float4 w4 = (MODE == kModeMLP) ? make_float4(0.f, 0.f, 0.f, 0.f)
-                                                     : *reinterpret_cast<const float4 *>(my_val + k + 4 * q);
+                                                     : lds_f4(s_base + 4u * (uint32_t)(k + 4 * q + kWarpEdges));
                 src[4 * q] = i4.x, src[4 * q + 1] = i4.y, src[4 * q + 2] = i4.z, src[4 * q + 3] = i4.w;
                 w[4 * q] = w4.x, w[4 * q + 1] = w4.y, w[4 * q + 2] = w4.z, w[4 * q + 3] = w4.w;
             }

@@ -568,26 +568,6 @@ int gnnagg_schedule_apply(gnnagg_aggregator *a, int kind, const int *params, int
     if (!a || !params || nparams < 1) return set_error(GNNAGG_ERR_ARG, "gnnagg_schedule_apply: bad argument");
     if (kind == GNNAGG_SCHED_LOCALITY_NEIGHBOR_GROUPING && nparams < 2)
         return set_error(GNNAGG_ERR_ARG, "locality_neighbor_grouping needs {par_num, neighbor_num}");
-    // host mirror of the CSR (neighbour grouping only needs the row pointers: its idx_vec is a
-    // verbatim copy of idx, graph_schedule.h:123-124, so the device idx is aliased instead)
-    const bool need_idx = (kind != GNNAGG_SCHED_NEIGHBOR_GROUPING);
-    const int *hp = a->h_ptr_user, *hi = a->h_idx_user;
-    if (!hp) {
-        if (a->h_ptr.empty()) {
-            a->h_ptr.resize((size_t)a->n + 1);
-            CUDA_TRY(cudaMemcpy(a->h_ptr.data(), a->d_ptr, a->h_ptr.size() * sizeof(int), cudaMemcpyDeviceToHost));
-        }
-        hp = a->h_ptr.data();
-    }
-    if (!need_idx) {
-        hi = nullptr;
-    } else if (!hi) {
-        if (a->h_idx.empty() && a->m > 0) {
-            a->h_idx.resize((size_t)a->m);
-            CUDA_TRY(cudaMemcpy(a->h_idx.data(), a->d_idx, a->h_idx.size() * sizeof(int), cudaMemcpyDeviceToHost));
-        }
-        hi = a->h_idx.data();
-    }
     int par = 0, ng = 0;
     if (kind == GNNAGG_SCHED_NEIGHBOR_GROUPING)
         ng = params[0];
@@ -598,32 +578,27 @@ int gnnagg_schedule_apply(gnnagg_aggregator *a, int kind, const int *params, int
     else
         return set_error(GNNAGG_ERR_ARG, "gnnagg_schedule_apply: unknown kind");
 
-    gnnagg_schedule s;
-    const bool permuting = (kind != GNNAGG_SCHED_NEIGHBOR_GROUPING);
-    s.want_perm = permuting;  // edge values are permuted on the device from this (aggr_gcn.h:522-537)
-    if (int rc = schedule_build(kind, hp, hi, nullptr, a->n, a->m, par, ng, total_num_v, &s)) return rc;
-
+    // built on the device (sched_device.cu); bit-identical to the host builders of gnnagg_schedule_build.
+    // Neighbour grouping keeps the CSR edge order (graph_schedule.h:123-124): idx and val are aliased, not copied.
+    int *sp = nullptr, *si = nullptr, *stg = nullptr, *sperm = nullptr, nt = 0, se = 0;
+    if (int rc = schedule_build_device(kind, a->d_ptr, a->d_idx, a->d_item_row, a->num_items, a->n, a->m, par, ng,
+                                       total_num_v, &sp, &si, &stg, &sperm, &nt, &se, 0))
+        return rc;
     free_schedule(a);
     a->sched_kind = kind;
     a->neighbor_group_size = ng;
     a->locality_partition_num = par;
-    a->num_target = (int)s.target.size();
-    a->sched_edges = need_idx ? (int)s.idx.size() : a->m;
-    auto upload = [&](int **dst, const void *src, size_t count) -> int {
-        CUDA_TRY(cudaMalloc((void **)dst, (count ? count : 1) * sizeof(int)));
-        if (count) CUDA_TRY(cudaMemcpy(*dst, src, count * sizeof(int), cudaMemcpyHostToDevice));
-        return GNNAGG_OK;
-    };
-    if (int rc = upload(&a->s_ptr, s.ptr.data(), s.ptr.size())) return rc;
-    if (need_idx) {
-        if (int rc = upload(&a->s_idx, s.idx.data(), s.idx.size())) return rc;
+    a->num_target = nt;
+    a->sched_edges = se;
+    a->s_ptr = sp;
+    a->s_target = stg;
+    a->s_perm = sperm;
+    if (si) {
+        a->s_idx = si;
         a->s_idx_owned = true;
     } else {
         a->s_idx = const_cast<int *>(a->d_idx);
     }
-    if (int rc = upload(&a->s_target, s.target.data(), s.target.size())) return rc;
-    if (permuting)
-        if (int rc = upload(&a->s_perm, s.perm.data(), s.perm.size())) return rc;
     if (int rc = build_item_rows(a, a->s_ptr, a->num_target, a->sched_edges, &a->s_item_row, &a->sched_items, 0))
         return rc;
     if (int rc = gnnagg_set_val(a, a->d_val)) return rc;

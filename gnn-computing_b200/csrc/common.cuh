@@ -60,6 +60,35 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
     }
 }
 
+// 128-bit shared loads from a 32-bit shared address held in a register (see opaque32)
+__device__ __forceinline__ int4 lds_i4(uint32_t addr)
+{
+    int4 v;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+// Makes a loop-invariant value opaque to the optimiser so that it stays in a register instead of being
+// re-derived from %tid / kernel parameters in every iteration of the hot loop (ptxas rematerialises address
+// arithmetic under register pressure; in the gather loop that cost ~15 instructions per 8 edges).
+__device__ __forceinline__ uint32_t opaque32(uint32_t x)
+{
+    uint32_t y;
+    asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
+__device__ __forceinline__ uint64_t opaque64(uint64_t x)
+{
+    uint64_t y;
+    asm volatile("mov.u64 %0, %1;" : "=l"(y) : "l"(x));
+    return y;
+}
+
 // ---- vector loads / stores -------------------------------------------------------------------
 __device__ __forceinline__ float4 ldg_f4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 __device__ __forceinline__ void stg_f4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }

@@ -1,5 +1,6 @@
 // internal.h -- private declarations shared by the translation units of libgnnagg.so
 #pragma once
+#include <cuda_runtime.h>
 #include <stdint.h>
 
 #include <vector>
@@ -20,6 +21,11 @@ int set_error(int code, const char *msg);
 // host schedule builder (host_prep.cpp)
 int schedule_build(int kind, const int *ptr, const int *idx, const float *val, int num_v, int num_e, int par_num,
                    int neighbor_num, int total_num_v, gnnagg_schedule *s);
+
+// schedules built on the GPU, bit-identical to schedule_build (sched_device.cu); outputs are cudaMalloc'ed
+int schedule_build_device(int kind, const int *d_ptr, const int *d_idx, const int *d_item_row, int num_items, int n, int m,
+                          int par_num, int ng, int total, int **s_ptr, int **s_idx, int **s_target, int **s_perm,
+                          int *num_target, int *sched_edges, cudaStream_t st);
 
 // dense combination on tcgen05 (dense_tc.cu); stream is a cudaStream_t
 int dense_nn_launch(const float *A, const float *B, float *C, int64_t M, int N, int K, void *stream);
