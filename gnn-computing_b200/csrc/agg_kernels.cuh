@@ -35,7 +35,7 @@ struct AggParams {
     const int *__restrict__ item_row;    // row containing edge k*kFineItem
     const float *__restrict__ X;         // [*, F]
     const float *__restrict__ att;       // GAT attention table [n,2]
-    const float *__restrict__ P;         // MLP: projected features P = X*W, [n, F] (also the gather source)
+    const float *__restrict__ P;         // MLP: projected features P = X*W, [n, F] (also the gather source); SDDMM: X2
     float *__restrict__ Y;               // [n, F]
     float *__restrict__ carry;           // [num_items, F] partials of rows entering an item
     float *__restrict__ den_row;         // GAT: [n] denominator of rows that start in an item and leave it
@@ -53,7 +53,9 @@ struct AggParams {
     int row_lo, row_hi, edge_lo, edge_hi;
 };
 
-enum { kModeGCN = 0, kModeGAT = 1, kModeMLP = 2 };
+enum { kModeGCN = 0, kModeGAT = 1, kModeMLP = 2, kModeSDDMM = 3 };
+__host__ __device__ constexpr bool mode_has_dst(int mode) { return mode == kModeMLP || mode == kModeSDDMM; }  // keeps P[dst,:] in registers
+__host__ __device__ constexpr bool mode_stages_val(int mode) { return mode == kModeGCN; }
 
 // row that contains edge e0 (start of an item): direct lookup when items are aligned with the
 // item_row table, bounded binary search otherwise (the small-graph variant uses 32..128-edge items)
@@ -157,11 +159,13 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
             if (act0) pd0 = ldg_f4(q);
             if (act1) pd1 = ldg_f4(q + LPR * 4);
         };
-        if (MODE == kModeMLP) load_dst(first_row);
+        if (mode_has_dst(MODE)) load_dst(first_row);
 
         // closes `row`: writes / accumulates its result and moves to the next row
         auto flush = [&](bool at_item_end) {
-            if (SCHED) {
+            if (MODE == kModeSDDMM) {
+                // nothing is accumulated per row: the flush only advances to the next row / group
+            } else if (SCHED) {
                 const int t = __ldg(p.target + row);
                 const bool merge = !at_item_end && (row + 1 < p.row_hi) && (__ldg(p.target + row + 1) == t);
                 if (!merge) {  // consecutive groups of one target are summed in registers first
@@ -203,7 +207,7 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
             if (row < p.row_hi) {
                 row_end = __ldg(p.ptr + row + 1);
                 if (MODE == kModeGAT) a_dst = __ldg(p.att + 2 * (size_t)(SCHED ? __ldg(p.target + row) : row));
-                if (MODE == kModeMLP) load_dst(row);
+                if (mode_has_dst(MODE)) load_dst(row);
             } else {
                 row_end = INT_MAX;
             }
@@ -219,6 +223,29 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
         const uint32_t s_base = opaque32(smem_u32(my_idx));  // shared address of this warp's staged idx (val: + 4*kWarpEdges)
         const int second = act1 ? LPR * 16 : 0;  // byte offset of the second float4 (NV == 2)
 
+        // per-edge combination of the gathered row (u is a compile-time constant after unrolling)
+        float dd[U];  // SDDMM: this lane's partial dot products of the batch
+        auto combine = [&](const int u, const float wu, const float4 &a0, const float4 &a1) {
+            if (MODE == kModeMLP) {
+                relu_add4(acc0, pd0, a0);
+                if (NV > 1) relu_add4(acc1, pd1, a1);
+            } else if (MODE == kModeSDDMM) {
+                dd[u] = (act0 ? dot4(pd0, a0) : 0.f) + ((NV > 1 && act1) ? dot4(pd1, a1) : 0.f);
+            } else {
+                fma4(acc0, wu, a0);
+                if (NV > 1) fma4(acc1, wu, a1);
+            }
+        };
+        // SDDMM: totals of the batch's dot products (reduce-scatter over the virtual warp) -> out[e .. e+nb)
+        auto sddmm_emit = [&](const int nb) {
+            VwReduceScatter<LPR, LPR / 2, U>::run(dd, vl, vw_mask);
+            const int id = vl / (LPR / U);
+            if ((vl % (LPR / U)) == 0 && id < nb) {
+                float *o = p.newval + e + id;
+                *o = (cb == 0) ? dd[0] : *o + dd[0];  // wide rows: column chunks accumulate
+            }
+        };
+
         // a batch of nb < U edges starting at e (scalar shared loads, clamped): used to re-align the first item of a
         // clipped row range and for the ragged end of the last item
         auto short_batch = [&](const int nb) {
@@ -229,7 +256,7 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
             for (int u = 0; u < U; ++u) {
                 const int k = min(e + u, e1 - 1) - wbase;
                 src[u] = my_idx[k];
-                w[u] = (MODE == kModeMLP) ? 0.f : my_val[k];
+                w[u] = mode_has_dst(MODE) ? 0.f : my_val[k];
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -249,18 +276,15 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
                         den += wu;
                         if (SCHED && vl == u % LPR) wout = wu;
                     }
-                    if (MODE == kModeMLP) {
-                        relu_add4(acc0, pd0, v0[u]);
-                        if (NV > 1) relu_add4(acc1, pd1, v1[u]);
-                    } else {
-                        fma4(acc0, wu, v0[u]);
-                        if (NV > 1) fma4(acc1, wu, v1[u]);
-                    }
+                    combine(u, wu, v0[u], v1[u]);
+                } else if (MODE == kModeSDDMM) {
+                    dd[u] = 0.f;
                 }
             }
             if (MODE == kModeGAT && SCHED && cb == 0 && p.newval != nullptr) {
                 if (vl < nb) p.newval[e + vl] = wout;
             }
+            if (MODE == kModeSDDMM) sddmm_emit(nb);
             e += nb;
         };
 
@@ -277,7 +301,7 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
 #pragma unroll
             for (int q = 0; q < U / 4; ++q) {
                 const int4 i4 = lds_i4(s_base + 4u * (uint32_t)(k + 4 * q));
-                const float4 w4 = (MODE == kModeMLP) ? make_float4(0.f, 0.f, 0.f, 0.f)
+                const float4 w4 = mode_has_dst(MODE) ? make_float4(0.f, 0.f, 0.f, 0.f)
                                                      : lds_f4(s_base + 4u * (uint32_t)(k + 4 * q + kWarpEdges));
                 src[4 * q] = i4.x, src[4 * q + 1] = i4.y, src[4 * q + 2] = i4.z, src[4 * q + 3] = i4.w;
                 w[4 * q] = w4.x, w[4 * q + 1] = w4.y, w[4 * q + 2] = w4.z, w[4 * q + 3] = w4.w;
@@ -309,15 +333,7 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
             } else if (MODE != kModeGAT && row_end - e >= U) {
                 // no row ends inside the batch: straight FMA chain
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    if (MODE == kModeMLP) {
-                        relu_add4(acc0, pd0, v0[u]);
-                        if (NV > 1) relu_add4(acc1, pd1, v1[u]);
-                    } else {
-                        fma4(acc0, w[u], v0[u]);
-                        if (NV > 1) fma4(acc1, w[u], v1[u]);
-                    }
-                }
+                for (int u = 0; u < U; ++u) combine(u, w[u], v0[u], v1[u]);
             } else {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -329,26 +345,23 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
                         den += wu;
                         if (SCHED && vl == u % LPR) wout = wu;
                     }
-                    if (MODE == kModeMLP) {
-                        relu_add4(acc0, pd0, v0[u]);
-                        if (NV > 1) relu_add4(acc1, pd1, v1[u]);
-                    } else {
-                        fma4(acc0, wu, v0[u]);
-                        if (NV > 1) fma4(acc1, wu, v1[u]);
-                    }
+                    combine(u, wu, v0[u], v1[u]);
                 }
             }
             if (MODE == kModeGAT && SCHED && cb == 0 && p.newval != nullptr) {
                 // one coalesced store per batch instead of one per edge (U <= LPR always holds)
                 if (vl < U) p.newval[e + vl] = wout;
             }
+            if (MODE == kModeSDDMM) sddmm_emit(U);
             e += U;
         }
 
         if (e < e1) short_batch(e1 - e);
 
         // item end
-        if (row_end == e1) {
+        if (MODE == kModeSDDMM) {
+            // per-edge outputs were written batch by batch
+        } else if (row_end == e1) {
             while (row < p.row_hi && row_end == e1) flush(true);  // row closes here (+ trailing empty rows)
         } else if (SCHED) {
             flush(true);

@@ -217,7 +217,7 @@ static int launch_agg(gnnagg_aggregator *a, AggParams p, cudaStream_t st)
         launch_agg_we<MODE, SCHED, kWarpEdges>(p, st);
     LAUNCH_CHECK(a);
     PROF_RECORD(a, 2, st);
-    if (!SCHED) {
+    if (!SCHED && MODE != kModeSDDMM) {
         const int EB = item_edges_for(a, p.F, p.num_edges);
         const int64_t items = cdiv(p.num_edges, EB);
         const int64_t range_items = cdiv(p.edge_hi, EB) - p.edge_lo / EB;  // items touched by the launched range
@@ -792,26 +792,37 @@ int gnnagg_sddmm(gnnagg_aggregator *a, const float *X1, const float *X2, float *
     if (!a || !X1 || !X2 || (!out_val && a->m > 0)) return set_error(GNNAGG_ERR_ARG, "gnnagg_sddmm: NULL argument");
     if (int rc = check_feat(feat)) return rc;
     if (!aligned16(X1) || !aligned16(X2)) return set_error(GNNAGG_ERR_ARG, "X1 and X2 must be 16-byte aligned");
-    EdgeParams g = edge_params(a);
-    const int *target = nullptr;
+    // same edge-balanced traversal as the aggregation (agg_kernel, MODE = SDDMM): X1 rows are gathered per edge,
+    // the X2 row of the destination stays in registers, per-edge dot products leave through a reduce-scatter
+    AggParams p{};
+    p.X = X1;
+    p.P = X2;
+    p.newval = out_val;
+    p.F = feat;
+    cudaStream_t st = (cudaStream_t)stream;
     if (scheduled) {
         if (a->sched_kind != GNNAGG_SCHED_NEIGHBOR_GROUPING)  // aggr_sddmm.h:100
             return set_error(GNNAGG_ERR_STATE, "scheduled SDDMM needs a neighbor_grouping schedule");
-        g = edge_params_sched(a);
-        target = a->s_target;
+        if (a->sched_edges == 0) return GNNAGG_OK;
+        p.ptr = a->s_ptr;
+        p.idx = a->s_idx;
+        p.target = a->s_target;
+        p.item_row = a->s_item_row;
+        p.num_rows = a->num_target;
+        p.num_edges = a->sched_edges;
+        p.num_fine_items = a->sched_items;
+        p.bulk_ok = aligned16(p.idx);
+        return launch_agg<kModeSDDMM, true>(a, p, st);
     }
-    if (g.num_edges == 0) return GNNAGG_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int lpr = lpr_for(feat);
-    const unsigned grid = (unsigned)cdiv(cdiv(g.num_items, 32 / lpr), 8);
-    if (lpr == 8)
-        sddmm_kernel<8><<<grid, 256, 0, st>>>(g, target, X1, X2, out_val, feat);
-    else if (lpr == 16)
-        sddmm_kernel<16><<<grid, 256, 0, st>>>(g, target, X1, X2, out_val, feat);
-    else
-        sddmm_kernel<32><<<grid, 256, 0, st>>>(g, target, X1, X2, out_val, feat);
-    LAUNCH_CHECK(a);
-    return GNNAGG_OK;
+    if (a->m == 0) return GNNAGG_OK;
+    p.ptr = a->d_ptr;
+    p.idx = a->d_idx;
+    p.item_row = a->d_item_row;
+    p.num_rows = a->n;
+    p.num_edges = a->m;
+    p.num_fine_items = a->num_items;
+    p.bulk_ok = aligned16(p.idx);
+    return launch_agg<kModeSDDMM, false>(a, p, st);
 }
 
 int gnnagg_gather_rows(const float *X, const int64_t *rows, float *out, int64_t count, int feat, void *stream)

@@ -114,6 +114,38 @@ __device__ __forceinline__ float4 add4(const float4 &a, const float4 &b)
 // 128-bit reduction into global memory (RED.E.ADD.F32x4 on sm_90+)
 __device__ __forceinline__ void red_add_f4(float *p, const float4 &v) { atomicAdd(reinterpret_cast<float4 *>(p), v); }
 
+__device__ __forceinline__ float dot4(const float4 &a, const float4 &b)
+{
+    return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+
+// Reduce-scatter of CNT per-lane values over a virtual warp of LPR lanes (LPR >= CNT, both powers of two): at
+// every butterfly step half of the values travel and half stay, so CNT values cost CNT-1 + log2(LPR/CNT)
+// shuffles instead of CNT*log2(LPR).  Afterwards d[0] of lane vl holds the total of value index
+// vl / (LPR/CNT); the LPR/CNT lanes of such a group hold the same total.
+template <int LPR, int OFF, int CNT>
+struct VwReduceScatter {
+    static __device__ __forceinline__ void run(float *d, int vl, unsigned mask)
+    {
+        if constexpr (OFF >= 1) {
+            if constexpr (CNT > 1) {
+                constexpr int H = CNT / 2;
+                const bool upper = (vl & OFF) != 0;
+#pragma unroll
+                for (int i = 0; i < H; ++i) {
+                    const float send = upper ? d[i] : d[i + H];
+                    const float keep = upper ? d[i + H] : d[i];
+                    d[i] = keep + __shfl_xor_sync(mask, send, OFF, LPR);
+                }
+                VwReduceScatter<LPR, OFF / 2, H>::run(d, vl, mask);
+            } else {
+                d[0] += __shfl_xor_sync(mask, d[0], OFF, LPR);
+                VwReduceScatter<LPR, OFF / 2, 1>::run(d, vl, mask);
+            }
+        }
+    }
+};
+
 // row that contains edge e: last r with ptr[r] <= e.  item_row narrows the search to the rows
 // that intersect the kFineItem-edge block of e.
 __device__ __forceinline__ int row_of_edge(const int *__restrict__ ptr, const int *__restrict__ item_row,

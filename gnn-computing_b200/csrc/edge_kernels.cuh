@@ -1,4 +1,4 @@
-// edge_kernels.cuh -- edge-parallel kernels: un-fused GAT pieces, SDDMM, edge-wise GCN,
+// edge_kernels.cuh -- edge-parallel kernels: un-fused GAT pieces, edge-wise GCN,
 // CSR->edge list, the naive SpMM and the validators of include/spmm.h.
 //
 // The reference runs all of these warp-per-row (aggr_gat.h:5-92, aggr_sddmm.h:5-83,
@@ -127,60 +127,6 @@ __global__ void __launch_bounds__(256) rowsum_fixup_kernel(const EdgeParams g, f
         out[row] += acc;
     else
         carry[item] = acc;
-}
-
-// SDDMM: out[e] = <X1[idx[e], 0:F], X2[row(e), 0:F]>   (aggr_sddmm.h:17-41; target variant :45-83)
-// A virtual warp of LPR lanes walks one item; float4 per lane per 4*LPR columns, xor-shuffle
-// reduction, 4 edges in flight.  `target` (nullable) maps a group to its row (scheduled mode).
-template <int LPR>
-__global__ void __launch_bounds__(256) sddmm_kernel(const EdgeParams g, const int *__restrict__ target,
-                                                    const float *__restrict__ X1, const float *__restrict__ X2,
-                                                    float *__restrict__ out, int F)
-{
-    constexpr int VPW = 32 / LPR;
-    constexpr int U = 4;
-    const int lane = threadIdx.x & 31;
-    const int vw = lane / LPR, vl = lane % LPR;
-    const int64_t item = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * VPW + vw;
-    // every lane of the warp runs the same number of batches (shuffles below use the full mask)
-    const int64_t e0_64 = item * kFineItem;
-    const bool live = e0_64 < g.num_edges;
-    const int e0 = live ? (int)e0_64 : 0;
-    const int e1 = live ? min(g.num_edges, e0 + kFineItem) : 0;
-    int row = 0, row_end = 0;
-    if (live) {
-        row = (e0 == 0) ? 0 : __ldg(g.item_row + item);
-        row_end = __ldg(g.ptr + row + 1);
-    }
-    for (int e = e0; e < e0 + kFineItem; e += U) {
-        float d[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            d[u] = 0.f;
-            const int ee = e + u;
-            if (ee < e1) {
-                while (row_end <= ee) {
-                    ++row;
-                    row_end = __ldg(g.ptr + row + 1);
-                }
-                const int dst = target ? __ldg(target + row) : row;
-                const float *a = X1 + (size_t)__ldg(g.idx + ee) * F;
-                const float *b = X2 + (size_t)dst * F;
-                for (int col = vl * 4; col < F; col += LPR * 4) {
-                    const float4 x = ldg_f4(a + col), y = ldg_f4(b + col);
-                    d[u] = fmaf(x.x, y.x, fmaf(x.y, y.y, fmaf(x.z, y.z, fmaf(x.w, y.w, d[u]))));
-                }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-#pragma unroll
-            for (int k = LPR / 2; k > 0; k >>= 1) d[u] += __shfl_xor_sync(0xffffffffu, d[u], k);
-        if (vl < U && e + vl < e1) {
-            const float r = (vl == 0) ? d[0] : (vl == 1) ? d[1] : (vl == 2) ? d[2] : d[3];
-            out[e + vl] = r;
-        }
-    }
 }
 
 // edge-wise GCN aggregation: Y[dst] += X[src]*val[e], one virtual warp per edge and 128-bit

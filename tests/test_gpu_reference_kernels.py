@@ -198,6 +198,19 @@ def test_timing_vs_reference_kernels_full_size(gn, orc, ref, cuda, shape, F):
     gat = gn.Aggregator(ptr, idx)
     out["ours_gat_ms"] = timeit(lambda: gat.gat_run(X, att, Y))
     out["ref_aggr_gat_ms"] = timeit(lambda: ref.ref_gat_run(hg, P(X), P(att), P(Yr), max(128, F), 0, F))
+    # un-fused GAT pieces and SDDMM (rows a13 / a14)
+    newval = torch.empty(m + 64, device=cuda)
+    center = torch.empty(2 * n, device=cuda)
+    out["ours_edge_softmax_ms"] = timeit(lambda: gat.edge_softmax(att, newval))
+    out["ref_attGat_ms"] = timeit(lambda: ref.ref_gat_run_att(hg, P(att), P(newval), 128))
+    out["ours_u_add_v_ms"] = timeit(lambda: gat.u_add_v(att, newval))
+    out["ref_u_add_v_ms"] = timeit(lambda: ref.ref_gat_run_u_add_v(hg, P(att), P(newval), 128))
+    out["ours_add_to_center_ms"] = timeit(lambda: gat.add_to_center(newval, center))
+    out["ref_add_to_center_ms"] = timeit(lambda: ref.ref_gat_run_add_to_center(hg, P(newval), P(center), 128))
+    if F == 32:
+        hs = C.c_void_p(ref.ref_sddmm_create(P(ptr), P(idx), n, m, 32))
+        out["ref_aggr_sddmm_ms"] = timeit(lambda: ref.ref_sddmm_run(hs, P(X), P(X), P(newval), 128, 0), reps=3)
+    out["ours_sddmm_ms"] = timeit(lambda: gat.sddmm(X, X, newval))
     if F == 32:  # the per-edge MLP aggregator exists for F = 32 only in the reference (aggr_nn.h)
         Wm = torch.randn((32, 32), device=cuda, generator=g) / 32 ** 0.5
         hm = C.c_void_p(ref.ref_mlp_create(P(ptr), P(idx), n, m, P(Wm)))
