@@ -73,27 +73,28 @@ inline double getFLOP(double time)
     return 2.0 * (double)m * (double)feature_len / time / 1e9;
 }
 
-#define FatalError(s)                                                                     \
-    do {                                                                                  \
-        std::cerr << std::string(s) << "\n" << __FILE__ << ':' << __LINE__ << "\nAborting...\n"; \
-        cudaDeviceReset();                                                                \
-        exit(1);                                                                          \
-    } while (0)
+namespace gnnagg_compat {
+// prints the message with its source position, resets the device and terminates: the reference's only error
+// policy (util.h:82-104 there), kept because its drivers assume a failed call never returns
+[[noreturn]] inline void die(const std::string &what, const char *file, int line)
+{
+    std::cerr << what << "\n" << file << ':' << line << "\nAborting...\n";
+    cudaDeviceReset();
+    exit(1);
+}
+inline void expect_cuda(long status, const char *file, int line)
+{
+    if (status != 0) die("Cuda failure: " + std::to_string(status), file, line);
+}
+inline void expect_gnnagg(int status, const char *file, int line)
+{
+    if (status != 0) die(std::string("gnnagg failure: ") + gnnagg_last_error(), file, line);
+}
+}  // namespace gnnagg_compat
 
-#define checkCudaErrors(status)                              \
-    do {                                                     \
-        if ((status) != 0) {                                 \
-            std::stringstream _error;                        \
-            _error << "Cuda failure: " << (int)(status);     \
-            FatalError(_error.str());                        \
-        }                                                    \
-    } while (0)
-
-// status check for the C ABI, same abort semantics
-#define checkGnnagg(status)                                                              \
-    do {                                                                                 \
-        if ((status) != 0) FatalError(std::string("gnnagg failure: ") + gnnagg_last_error()); \
-    } while (0)
+#define FatalError(s) gnnagg_compat::die(std::string(s), __FILE__, __LINE__)
+#define checkCudaErrors(status) gnnagg_compat::expect_cuda((long)(status), __FILE__, __LINE__)
+#define checkGnnagg(status) gnnagg_compat::expect_gnnagg((status), __FILE__, __LINE__)  // same policy for the C ABI
 
 static inline unsigned int roundUp(unsigned int nominator, unsigned int denominator)
 {
