@@ -253,7 +253,17 @@ def main():
     Xs = torch.randn((n, fin), device=dev, generator=g)          # this rank's X shard
     agg_only = fout is None
     W = torch.randn((fin, fout or fin), device=dev, generator=torch.Generator(device=dev).manual_seed(7)) / fin ** 0.5
-    halo = args.halo if args.halo != "auto" else ("pruned" if strong else "allgather")
+    halo = args.halo
+    if halo == "auto" and args.gpus > 1:
+        # exchange only the referenced source rows when that is clearly less than X (decided from the data, identically
+        # on every rank: the fraction of rank 0 is broadcast)
+        import torch.distributed as dist0
+
+        frac = torch.tensor([torch.unique(idx).numel() / float(src_n)], device=dev)
+        dist0.broadcast(frac, src=0)
+        halo = "pruned" if float(frac.item()) < 0.7 else "allgather"
+    elif halo == "auto":
+        halo = "allgather"
     pruned = N > 1 and halo == "pruned" and not args.scheduled
     pipelined = N > 1 and args.pipeline > 0 and not args.scheduled and not pruned
     Xfull = torch.empty((src_n, fin), device=dev) if (N > 1 and not pipelined and not pruned) else Xs

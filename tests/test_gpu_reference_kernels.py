@@ -224,3 +224,92 @@ def test_timing_vs_reference_kernels_full_size(gn, orc, ref, cuda, shape, F):
     with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "ref_vs_ours.jsonl"), "a") as f:
         f.write(json.dumps(out) + "\n")
     print(json.dumps(out))
+
+
+@pytest.mark.skipif(os.environ.get("GNNAGG_HEAVY") != "1", reason="full-size timing run: set GNNAGG_HEAVY=1")
+@pytest.mark.parametrize("shape", ["arxiv", "reddit", "proteins", "products"])
+def test_three_layer_forward_vs_reference_kernels(gn, orc, ref, cuda, shape):
+    """Figure 7 of the reference in a framework setting (Figure7/our.py:171-188,247-290): 3-layer GCN and GAT
+    forward, 512 -> 128 -> 64 -> 32, torch.mm for the combination + the aggregator (NG 32, blocksize 128), through
+    gnnagg.plugin and through the reference's own kernels (libref); appended to gpurun_out/r1_figure7_layers.jsonl"""
+    import json
+
+    import gnnagg.plugin as gnc
+    from gnnagg import synth
+
+    n, m = synth.shape_of(shape)
+    ptr, idx = synth.rmat_csr(n, m, seed=123, device=cuda)
+    vals = torch.ones(m, device=cuda)                     # our.py:78
+    torch.manual_seed(123)
+    dims = [512, 128, 64, 32]
+    W = [torch.randn(dims[i], dims[i + 1], device=cuda) / dims[i] ** 0.5 for i in range(3)]
+    Wlr = [torch.randn(dims[i + 1], 2, device=cuda) / dims[i + 1] ** 0.5 for i in range(3)]
+    h0 = torch.randn(n, 512, device=cuda)
+    outs = [torch.empty(n, d, device=cuda) for d in dims[1:]]
+
+    at = gnc.gcn_init(ptr, idx, vals)
+    gnc.gcn_schedule(at, 32)
+    at_gat = gnc.gat_init(ptr, idx)
+    gnc.gat_schedule(at_gat, 32)
+    ref.ref_set_globals(n, m)
+    rg = C.c_void_p(ref.ref_gcn_create(P(ptr), P(idx), P(vals), n, m, 32, 32))
+    ref.ref_gcn_schedule(rg, 1, 32, 0)
+    ra = C.c_void_p(ref.ref_gat_create(P(ptr), P(idx), n, m, 32))
+    ref.ref_gat_schedule(ra, 1, 32, 0)
+
+    def gcn(agg_call):
+        h = h0
+        for w, o in zip(W, outs):
+            feat2 = torch.mm(h, w)
+            agg_call(feat2, o)
+            h = torch.relu(o)
+        return h
+
+    def gat(agg_call):
+        h = h0
+        for w, wlr, o in zip(W, Wlr, outs):
+            feat2 = torch.mm(h, w)
+            att = torch.mm(feat2, wlr)
+            agg_call(feat2, att, o)
+            h = o
+        return h
+
+    def zero_then(fn):  # the reference's scheduled GAT never zeroes its outputs (aggr_gat.h:327-335): do it for it
+        def call(*a):
+            a[-1].zero_()
+            fn(*a)
+        return call
+
+    variants = {
+        "ours_gcn_ms": lambda: gcn(lambda f, o: gnc.gcn_run(at, f, o, 128, 1)),
+        "ours_gcn_unscheduled_ms": lambda: gcn(lambda f, o: gnc.gcn_run(at, f, o, 128, 0)),
+        "ref_gcn_ms": lambda: gcn(lambda f, o: ref.ref_gcn_run(rg, P(f), P(o), 128, 1, f.shape[1])),
+        "ours_gat_ms": lambda: gat(lambda f, a, o: gnc.gat_run(at_gat, f, a, o, 128, 1)),
+        "ours_gat_unscheduled_ms": lambda: gat(lambda f, a, o: gnc.gat_run(at_gat, f, a, o, 128, 0)),
+        "ref_gat_ms": lambda: gat(zero_then(lambda f, a, o: ref.ref_gat_run(ra, P(f), P(a), P(o), 128, 1, f.shape[1]))),
+    }
+    out = {"shape": shape, "n": n, "m": m, "dims": dims}
+    for name, fn in variants.items():
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        out[name] = float(np.median(ts))
+    # the two GCN paths agree
+    y_ours = gcn(lambda f, o: gnc.gcn_run(at, f, o, 128, 1)).clone()
+    y_ref = gcn(lambda f, o: ref.ref_gcn_run(rg, P(f), P(o), 128, 1, f.shape[1])).clone()
+    scale = y_ref.abs().max().item()
+    assert (y_ours - y_ref).abs().max().item() <= 1e-3 * scale
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(root, "gpurun_out", "r1_figure7_layers.jsonl"), "a") as f:
+        f.write(json.dumps(out) + "\n")
+    print(json.dumps(out))
+    gnc.destroy(at)
+    gnc.destroy(at_gat)
