@@ -213,6 +213,158 @@ dense_tf32x3_kernel(const float *__restrict__ A, const float *__restrict__ B, fl
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)tmem_cols) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Streamed-W variant for feat_in*feat_out > 16 384 (W's hi/lo split no longer fits beside the A ring).
+// W is split ONCE per call into Whi / Wlo laid out chunk by chunk in the canonical operand layout
+// (split_w_kernel); the main kernel then streams BOTH operands through a 2-stage ring in 32-wide K chunks: the A
+// chunk is produced by the threads (fp32 -> hi/lo, as above), the two W chunks arrive by bulk copy (TMA, UBLKCP)
+// from L2 on the stage's `full` mbarrier while the threads convert A.  One launch covers all N columns, so A is
+// read once (the resident variant would need N/64 column slabs and re-read A for each).
+// ---------------------------------------------------------------------------------------------------------
+// element (k, n) of W -> chunk kc = k/32:  kc*N*32 + (n/8)*256 + ((k%32)/4)*32 + (n%8)*4 + (k%4)   [floats]
+__global__ void __launch_bounds__(256) split_w_kernel(const float *__restrict__ W, float *__restrict__ Whi,
+                                                      float *__restrict__ Wlo, int K, int N)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K * N) return;
+    const int k = i / N, n = i % N;
+    const float w = __ldg(W + i);
+    const float hi = tf32_round(w);
+    const size_t off = (size_t)(k >> 5) * N * 32 + (size_t)(n >> 3) * 256 + (size_t)((k & 31) >> 2) * 32 + (size_t)(n & 7) * 4 + (k & 3);
+    Whi[off] = hi;
+    Wlo[off] = w - hi;
+}
+
+__global__ void __launch_bounds__(kDenseThreads, 1)
+dense_tf32x3_stream_kernel(const float *__restrict__ A, const float *__restrict__ Whi, const float *__restrict__ Wlo,
+                           float *__restrict__ C, int64_t M, int N, int K, int tmem_cols)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t s_empty[2], s_full[2];
+    __shared__ __align__(8) uint64_t s_acc;
+    __shared__ uint32_t s_tmem;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t b_chunk = (uint32_t)N * 128u;                 // one of Whi / Wlo, one K chunk
+    const uint32_t stage_bytes = 2u * kStageBytes + 2u * b_chunk;  // [Ahi | Alo | Bhi | Blo]
+    const uint32_t sbo = (kChunkK / 4) * 128;                    // 1024 B between 8-row core-matrix groups, both operands
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                     "r"((uint32_t)tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(&s_empty[i]), 1);
+            mbar_init(smem_u32(&s_full[i]), 1);
+        }
+        mbar_init(smem_u32(&s_acc), 1);
+        fence_mbar_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    const int chunks = K / kChunkK;
+    const int64_t tiles = (M + kTileM - 1) / kTileM;
+    uint32_t c = 0, acc_phase = 0;
+
+    auto fetch = [&](int64_t tile, int kc, float4 (&v)[4]) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int u = p * kDenseThreads + tid;
+            const int r8 = u & 7, kq = (u >> 3) & 7, rb = u >> 6;
+            const int64_t row = tile * kTileM + rb * 8 + r8;
+            v[p] = (tile < tiles && row < M) ? ldg_f4(A + (size_t)row * K + kc * kChunkK + kq * 4)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    float4 cur[4], nxt[4];
+    fetch(blockIdx.x, 0, cur);
+
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int64_t row0 = tile * kTileM;
+        for (int kc = 0; kc < chunks; ++kc, ++c) {
+            if (kc + 1 < chunks)
+                fetch(tile, kc + 1, nxt);
+            else
+                fetch(tile + gridDim.x, 0, nxt);
+            const uint32_t stage = c & 1;
+            if (c >= 2) mbar_wait(smem_u32(&s_empty[stage]), ((c >> 1) - 1) & 1);  // MMAs of chunk c-2 retired
+            uint8_t *aHi = smem + stage * stage_bytes, *aLo = aHi + kStageBytes;
+            uint8_t *bHi = aLo + kStageBytes, *bLo = bHi + b_chunk;
+            if (tid == 0) {  // the W chunks of this K step travel while the threads convert A
+                const uint32_t full = smem_u32(&s_full[stage]);
+                mbar_expect_tx(full, 2u * b_chunk);
+                bulk_g2s(smem_u32(bHi), Whi + (size_t)kc * N * 32, b_chunk, full);
+                bulk_g2s(smem_u32(bLo), Wlo + (size_t)kc * N * 32, b_chunk, full);
+            }
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const int u = p * kDenseThreads + tid;
+                const int r8 = u & 7, kq = (u >> 3) & 7, rb = u >> 6;
+                const float4 v = cur[p];
+                const float4 h = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
+                const float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                const uint32_t off = (uint32_t)rb * sbo + (uint32_t)kq * 128u + (uint32_t)r8 * 16u;
+                *reinterpret_cast<float4 *>(aHi + off) = h;
+                *reinterpret_cast<float4 *>(aLo + off) = l;
+            }
+#pragma unroll
+            for (int p = 0; p < 4; ++p) cur[p] = nxt[p];
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) {
+                mbar_wait(smem_u32(&s_full[stage]), (c >> 1) & 1);  // W chunks landed
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(aHi), a_lo = smem_u32(aLo), b_hi = smem_u32(bHi), b_lo = smem_u32(bLo);
+#pragma unroll
+                for (int j = 0; j < kChunkK / 8; ++j) {
+                    const uint64_t dah = smem_desc(a_hi + j * 256, 128, sbo), dal = smem_desc(a_lo + j * 256, 128, sbo);
+                    const uint64_t dbh = smem_desc(b_hi + j * 256, 128, sbo), dbl = smem_desc(b_lo + j * 256, 128, sbo);
+                    tc_mma_tf32(tmem, dal, dbh, idesc, (kc | j) ? 1u : 0u);
+                    tc_mma_tf32(tmem, dah, dbl, idesc, 1u);
+                    tc_mma_tf32(tmem, dah, dbh, idesc, 1u);
+                }
+                tc_commit(smem_u32(&s_empty[stage]));
+                if (kc == chunks - 1) tc_commit(smem_u32(&s_acc));
+            }
+        }
+        mbar_wait(smem_u32(&s_acc), acc_phase);
+        acc_phase ^= 1;
+        tc_fence_after();
+        {
+            const int q = warp & 3, half = warp >> 2;
+            const int64_t row = row0 + q * 32 + lane;
+            const int cbeg = half * (N / 2), cend = cbeg + N / 2;
+            for (int col = cbeg; col < cend; col += 16) {
+                uint32_t r[16];
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < M) {
+                    float *dst = C + (size_t)row * N + col;
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4)
+                        stg_f4(dst + i, make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
+                                                    __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])));
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+    }
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)tmem_cols) : "memory");
+}
+
 int dense_nn_launch(const float *A, const float *B, float *C, int64_t M, int N, int K, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
@@ -224,10 +376,31 @@ int dense_nn_launch(const float *A, const float *B, float *C, int64_t M, int N, 
     if (cudaGetDevice(&dev) != cudaSuccess ||
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
         return set_error(GNNAGG_ERR_CUDA, "dense combination: no CUDA device");
-    // N is processed in slabs so that Bhi+Blo of a slab fit beside the A ring
-    int Ns = N;
-    while (Ns * K > kMaxNK) Ns /= 2;
-    if (Ns % 32) return set_error(GNNAGG_ERR_ARG, "dense combination: unsupported (feat_in, feat_out)");
+    const int64_t tiles_all = (M + kTileM - 1) / kTileM;
+    if (N * K > kMaxNK) {
+        // W's split does not fit in shared memory next to the A ring: stream it (see dense_tf32x3_stream_kernel)
+        float *wsplit = nullptr;
+        if (cudaMallocAsync((void **)&wsplit, (size_t)2 * K * N * sizeof(float), st) != cudaSuccess)
+            return set_error(GNNAGG_ERR_CUDA, "dense combination: cannot allocate the W split");
+        float *whi = wsplit, *wlo = wsplit + (size_t)K * N;
+        split_w_kernel<<<(K * N + 255) / 256, 256, 0, st>>>(B, whi, wlo, K, N);
+        int cols = 32;
+        while (cols < N) cols *= 2;
+        const size_t smem_s = 2 * ((size_t)2 * kStageBytes + (size_t)2 * N * 128);
+        static size_t configured_s = 0;
+        if (smem_s > configured_s) {
+            if (cudaFuncSetAttribute(dense_tf32x3_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s) !=
+                cudaSuccess)
+                return set_error(GNNAGG_ERR_CUDA, "dense combination: cannot raise dynamic shared memory");
+            configured_s = smem_s;
+        }
+        const unsigned grid_s = (unsigned)(tiles_all < sms ? tiles_all : sms);
+        dense_tf32x3_stream_kernel<<<grid_s, kDenseThreads, smem_s, st>>>(A, whi, wlo, C, M, N, K, cols);
+        const cudaError_t e = cudaPeekAtLastError();
+        cudaFreeAsync(wsplit, st);
+        return e == cudaSuccess ? GNNAGG_OK : set_error(GNNAGG_ERR_CUDA, cudaGetErrorString(e));
+    }
+    const int Ns = N;  // W resident in shared memory
     int tmem_cols = 32;
     while (tmem_cols < Ns) tmem_cols *= 2;
     const size_t smem = (size_t)2 * Ns * K * 4 + 4 * kStageBytes;
@@ -239,8 +412,7 @@ int dense_nn_launch(const float *A, const float *B, float *C, int64_t M, int N, 
     }
     const int64_t tiles = (M + kTileM - 1) / kTileM;
     const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-    for (int n_off = 0; n_off < N; n_off += Ns)
-        dense_tf32x3_kernel<<<grid, kDenseThreads, smem, st>>>(A, B, C, M, N, K, n_off, Ns, tmem_cols);
+    dense_tf32x3_kernel<<<grid, kDenseThreads, smem, st>>>(A, B, C, M, N, K, 0, Ns, tmem_cols);
     return cudaPeekAtLastError() == cudaSuccess ? GNNAGG_OK : set_error(GNNAGG_ERR_CUDA, cudaGetErrorString(cudaGetLastError()));
 }
 

@@ -37,7 +37,7 @@ static int build_neighbor_grouping(const int *ptr, const int *idx, int num_v, in
     for (int i = 0; i < num_v; ++i) total += ((int64_t)ptr[i + 1] - ptr[i] + ng - 1) / ng;
     s->ptr.resize((size_t)total + 1);
     s->target.resize((size_t)total);
-    if (idx) s->idx.assign(idx, idx + num_e);  // verbatim copy (:123-124); internal callers that alias idx pass NULL
+    s->idx.assign(idx, idx + num_e);  // verbatim copy (:123-124)
     int64_t g = 0;
     s->ptr[0] = 0;
     for (int i = 0; i < num_v; ++i) {
@@ -83,7 +83,6 @@ static int build_locality(const int *ptr, const int *idx, const float *val, int 
     s->target.resize((size_t)tg);
     s->idx.resize((size_t)te);
     if (val) s->val.resize((size_t)te);
-    if (s->want_perm) s->perm.resize((size_t)te);
     s->has_val = val != nullptr;
     s->ptr[0] = 0;
     // pass 2: scatter edges to their slice (stable), then close this row's groups in every slice
@@ -95,7 +94,6 @@ static int build_locality(const int *ptr, const int *idx, const float *val, int 
             if (p < 0) continue;
             s->idx[edge_cur[p]] = idx[j];
             if (val) s->val[edge_cur[p]] = val[j];
-            if (s->want_perm) s->perm[edge_cur[p]] = j;
             ++edge_cur[p];
         }
         for (int p = 0; p < par_num; ++p) {

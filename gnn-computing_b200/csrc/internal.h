@@ -8,8 +8,7 @@
 struct gnnagg_schedule {
     int kind = 3;
     bool has_val = false;
-    bool want_perm = false;          // also record perm[k] = CSR edge id stored at scheduled position k
-    std::vector<int> ptr, idx, target, perm;
+    std::vector<int> ptr, idx, target;
     std::vector<float> val;
 };
 
