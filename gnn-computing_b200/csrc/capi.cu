@@ -88,6 +88,14 @@ struct gnnagg_aggregator {
     bool s_idx_owned = false;  // neighbour grouping keeps the edge order: its idx aliases d_idx
     int64_t launches = 0;
     int warp_edges = 0;  // 0 = automatic
+    // backward pass (gnnagg_transpose_build): the transposed CSR and a child aggregator that runs over it
+    int num_src = 0;
+    int *t_ptr = nullptr, *t_idx = nullptr, *t_perm = nullptr;
+    gnnagg_aggregator *tr = nullptr;
+    float *t_val = nullptr;    // edge values in transposed order (owned, m floats)
+    const float *t_val_of = nullptr;  // which d_val t_val currently mirrors (NULL: none / attention weights)
+    float *bwd_g = nullptr, *bwd_c = nullptr;
+    size_t bwd_g_cap = 0, bwd_c_cap = 0;
     // host-buffer entry points: the result is copied back per row chunk on a second stream while the next chunk computes
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -113,18 +121,6 @@ static EdgeParams edge_params(const gnnagg_aggregator *a)
     g.num_rows = a->n;
     g.num_edges = a->m;
     g.num_items = a->num_items;
-    return g;
-}
-
-static EdgeParams edge_params_sched(const gnnagg_aggregator *a)
-{
-    EdgeParams g;
-    g.ptr = a->s_ptr;
-    g.idx = a->s_idx;
-    g.item_row = a->s_item_row;
-    g.num_rows = a->num_target;
-    g.num_edges = a->sched_edges;
-    g.num_items = a->sched_items;
     return g;
 }
 
@@ -455,26 +451,55 @@ static int gat_run_impl(gnnagg_aggregator *a, const float *X, const float *att, 
     return GNNAGG_OK;
 }
 
-// out[v] = sum over row v of in[e]; deterministic
-static int rowsum_impl(gnnagg_aggregator *a, const float *in, float *out, cudaStream_t st)
+// out[v * ostride] = sum over row v of in[e], rows and edges as described by g; deterministic.
+// `a` owns the carry scratch (sized for ITS item count: g must describe a's graph).
+static int rowsum_impl(gnnagg_aggregator *a, const float *in, float *out, cudaStream_t st, int ostride = 1)
 {
     if (a->m == 0) {
-        CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)a->n * sizeof(float), st));
+        if (ostride == 1)
+            CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)a->n * sizeof(float), st));
+        else if (a->n > 0)
+            CUDA_TRY(cudaMemset2DAsync(out, (size_t)ostride * sizeof(float), 0, sizeof(float), (size_t)a->n, st));
         return GNNAGG_OK;
     }
     if (int rc = ensure(a->carry_den, a->carry_den_cap, (size_t)a->num_items)) return rc;
     const EdgeParams g = edge_params(a);
     const unsigned grid = (unsigned)cdiv(a->num_items, 256);
-    rowsum_kernel<<<grid, 256, 0, st>>>(g, in, out, a->carry_den);
+    rowsum_kernel<<<grid, 256, 0, st>>>(g, in, out, a->carry_den, ostride);
     LAUNCH_CHECK(a);
     if (a->num_items > 1) {
-        rowsum_fixup_kernel<1><<<grid, 256, 0, st>>>(g, out, a->carry_den);
+        rowsum_fixup_kernel<1><<<grid, 256, 0, st>>>(g, out, a->carry_den, ostride);
         LAUNCH_CHECK(a);
         if (a->num_items > kRowsumChunk + 1) {
-            rowsum_fixup_kernel<2><<<grid, 256, 0, st>>>(g, out, a->carry_den);
+            rowsum_fixup_kernel<2><<<grid, 256, 0, st>>>(g, out, a->carry_den, ostride);
             LAUNCH_CHECK(a);
         }
     }
+    return GNNAGG_OK;
+}
+
+static void free_transpose(gnnagg_aggregator *a)
+{
+    if (a->tr) {
+        cudaFree(a->tr->d_item_row);
+        cudaFree(a->tr->carry);
+        cudaFree(a->tr->carry_den);
+        delete a->tr;
+        a->tr = nullptr;
+    }
+    cudaFree(a->t_ptr), cudaFree(a->t_idx), cudaFree(a->t_perm), cudaFree(a->t_val);
+    a->t_ptr = a->t_idx = a->t_perm = nullptr;
+    a->t_val = nullptr;
+    a->t_val_of = nullptr;
+    a->num_src = 0;
+}
+
+// t_val[j] = src[t_perm[j]]: edge data into transposed order
+static int to_transposed(gnnagg_aggregator *a, const float *src, float *dst, cudaStream_t st)
+{
+    if (a->m == 0) return GNNAGG_OK;
+    gather_val_kernel<<<(unsigned)cdiv(a->m, 256), 256, 0, st>>>(src, a->t_perm, dst, a->m);
+    LAUNCH_CHECK(a);
     return GNNAGG_OK;
 }
 
@@ -526,6 +551,9 @@ int gnnagg_destroy(gnnagg_aggregator *a)
 {
     if (!a) return GNNAGG_OK;
     free_schedule(a);
+    free_transpose(a);
+    cudaFree(a->bwd_g);
+    cudaFree(a->bwd_c);
     cudaFree(a->d_item_row);
     cudaFree(a->carry);
     cudaFree(a->den_row);
@@ -550,6 +578,7 @@ int gnnagg_set_val(gnnagg_aggregator *a, const float *d_val)
 {
     if (!a) return set_error(GNNAGG_ERR_ARG, "gnnagg_set_val: NULL aggregator");
     a->d_val = d_val;
+    a->t_val_of = nullptr;  // same pointer, possibly new contents (aggr_gcn.h:540-544): re-mirror on the next backward
     if (a->sched_kind == GNNAGG_SCHED_NOP) return GNNAGG_OK;
     if (a->s_perm) {  // locality kinds keep a permuted copy (aggr_gcn.h:522-537)
         if (!a->s_val) CUDA_TRY(cudaMalloc((void **)&a->s_val, (size_t)(a->sched_edges ? a->sched_edges : 1) * sizeof(float)));
@@ -823,6 +852,108 @@ int gnnagg_sddmm(gnnagg_aggregator *a, const float *X1, const float *X2, float *
     p.num_fine_items = a->num_items;
     p.bulk_ok = aligned16(p.idx);
     return launch_agg<kModeSDDMM, false>(a, p, st);
+}
+
+int gnnagg_transpose_build(gnnagg_aggregator *a, int num_src, void *stream)
+{
+    if (!a || num_src < 0) return set_error(GNNAGG_ERR_ARG, "gnnagg_transpose_build: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    free_transpose(a);
+    if (int rc = transpose_build_device(a->d_ptr, a->d_idx, a->d_item_row, a->num_items, a->n, a->m, num_src, &a->t_ptr,
+                                        &a->t_idx, &a->t_perm, st))
+        return rc;
+    a->num_src = num_src;
+    a->tr = new gnnagg_aggregator();
+    a->tr->d_ptr = a->t_ptr;
+    a->tr->d_idx = a->t_idx;
+    a->tr->n = num_src;
+    a->tr->m = a->m;
+    a->tr->warp_edges = a->warp_edges;
+    if (int rc = build_item_rows(a->tr, a->t_ptr, num_src, a->m, &a->tr->d_item_row, &a->tr->num_items, st)) return rc;
+    CUDA_TRY(cudaMalloc((void **)&a->t_val, (size_t)(a->m ? a->m : 1) * sizeof(float)));
+    a->tr->d_val = a->t_val;
+    a->launches += 5;  // iota, radix sort (counted once), rows, pointers, item table
+    return GNNAGG_OK;
+}
+
+int gnnagg_transpose_dev(const gnnagg_aggregator *a, int *num_src, const int **t_ptr, const int **t_idx, const int **t_perm)
+{
+    if (!a || !a->tr) return set_error(GNNAGG_ERR_STATE, "gnnagg_transpose_dev: gnnagg_transpose_build has not run");
+    if (num_src) *num_src = a->num_src;
+    if (t_ptr) *t_ptr = a->t_ptr;
+    if (t_idx) *t_idx = a->t_idx;
+    if (t_perm) *t_perm = a->t_perm;
+    return GNNAGG_OK;
+}
+
+int gnnagg_gcn_backward(gnnagg_aggregator *a, const float *dY, float *dX, int feat, void *stream)
+{
+    if (!a || !dY || !dX) return set_error(GNNAGG_ERR_ARG, "gnnagg_gcn_backward: NULL argument");
+    if (!a->tr) return set_error(GNNAGG_ERR_STATE, "gnnagg_gcn_backward: gnnagg_transpose_build has not run");
+    if (!a->d_val && a->m > 0) return set_error(GNNAGG_ERR_STATE, "gnnagg_gcn_backward: edge values not set (gnnagg_set_val)");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a->t_val_of != a->d_val) {
+        if (int rc = to_transposed(a, a->d_val, a->t_val, st)) return rc;
+        a->t_val_of = a->d_val;
+    }
+    const int64_t before = a->tr->launches;
+    const int rc = gcn_run_core(a->tr, dY, dX, feat, 0, st);
+    a->launches += a->tr->launches - before;
+    return rc;
+}
+
+int gnnagg_gat_backward(gnnagg_aggregator *a, const float *X, const float *att, const float *w, const float *den,
+                        const float *Y, const float *dY, float *dX, float *datt, int feat, float slope, void *stream)
+{
+    if (!a || !X || !Y || !dY || !dX || !datt || (!att && !(w && den)))
+        return set_error(GNNAGG_ERR_ARG, "gnnagg_gat_backward: NULL argument (att, or w and den, must be given)");
+    if (!a->tr) return set_error(GNNAGG_ERR_STATE, "gnnagg_gat_backward: gnnagg_transpose_build has not run");
+    if (int rc = check_feat(feat)) return rc;
+    if (!aligned16(X) || !aligned16(Y) || !aligned16(dY) || !aligned16(dX))
+        return set_error(GNNAGG_ERR_ARG, "X, Y, dY and dX must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rows = a->n > a->num_src ? a->n : a->num_src;
+    CUDA_TRY(cudaMemsetAsync(datt, 0, (size_t)rows * 2 * sizeof(float), st));
+    if (a->m == 0) {
+        CUDA_TRY(cudaMemsetAsync(dX, 0, (size_t)a->num_src * feat * sizeof(float), st));
+        return GNNAGG_OK;
+    }
+    if (int rc = ensure(a->newval, a->newval_cap, (size_t)a->m)) return rc;
+    if (int rc = ensure(a->bwd_g, a->bwd_g_cap, (size_t)a->m)) return rc;
+    if (int rc = ensure(a->bwd_c, a->bwd_c_cap, (size_t)a->n)) return rc;
+    if (int rc = ensure(a->den_row, a->den_row_cap, (size_t)a->n)) return rc;
+    const EdgeParams g = edge_params(a);
+    const unsigned egrid = (unsigned)cdiv(a->m, 256);
+    // 1. un-normalised weights and their row sums (recomputed from the attention table unless handed in)
+    if (w) {
+        CUDA_TRY(cudaMemcpyAsync(a->newval, w, (size_t)a->m * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    } else {
+        edge_map_kernel<kEdgeWeight><<<egrid, 256, 0, st>>>(g, att, a->newval, slope);
+        LAUNCH_CHECK(a);
+    }
+    const float *dn = den;
+    if (!dn) {
+        if (int rc = rowsum_impl(a, a->newval, a->den_row, st)) return rc;
+        dn = a->den_row;
+    }
+    // 2. g_e = <X[u], dY[v]>: the SDDMM traversal;  c_v = <Y[v], dY[v]>
+    if (int rc = gnnagg_sddmm(a, X, dY, a->bwd_g, feat, 0, stream)) return rc;
+    rowdot_kernel<<<(unsigned)cdiv((int64_t)a->n * 8, 256), 256, 0, st>>>(Y, dY, a->bwd_c, a->n, feat);
+    LAUNCH_CHECK(a);
+    // 3. per edge: alpha_e (into newval) and ds_e (into bwd_g)
+    gat_bwd_edge_kernel<<<egrid, 256, 0, st>>>(g, w ? nullptr : att, dn, a->bwd_c, a->newval, a->bwd_g, slope);
+    LAUNCH_CHECK(a);
+    // 4. attention gradient: destination half = row sums of ds; source half = row sums over the transposed CSR
+    if (int rc = rowsum_impl(a, a->bwd_g, datt, st, 2)) return rc;
+    if (int rc = to_transposed(a, a->newval, a->t_val, st)) return rc;  // alpha in transposed order
+    a->t_val_of = nullptr;
+    if (int rc = to_transposed(a, a->bwd_g, a->newval, st)) return rc;  // ds in transposed order (alpha no longer needed)
+    const int64_t before = a->tr->launches;
+    int rc = rowsum_impl(a->tr, a->newval, datt + 1, st, 2);
+    // 5. dX[u] = sum_e alpha_e dY[v]: the aggregation kernel over the transposed CSR
+    if (rc == GNNAGG_OK) rc = gcn_run_core(a->tr, dY, dX, feat, 0, st);
+    a->launches += a->tr->launches - before;
+    return rc;
 }
 
 int gnnagg_gather_rows(const float *X, const int64_t *rows, float *out, int64_t count, int feat, void *stream)

@@ -44,8 +44,9 @@ __global__ void __launch_bounds__(256) edge_map_kernel(const EdgeParams g, const
 // out[v] = sum of in[e] over the edges of row v (add_to_center, aggr_gat.h:50-74; the row-sum
 // half of attGat, :19-25).  One thread walks one kFineItem-edge item; rows crossing item
 // boundaries leave a partial in carry[item] that rowsum_fixup_kernel adds in item order.
+// Row v is written to out[v * ostride] (ostride = 2 fills one column of an [n,2] attention-gradient table).
 __global__ void __launch_bounds__(256) rowsum_kernel(const EdgeParams g, const float *__restrict__ in,
-                                                     float *__restrict__ out, float *__restrict__ carry)
+                                                     float *__restrict__ out, float *__restrict__ carry, int ostride)
 {
     const int item = blockIdx.x * blockDim.x + threadIdx.x;
     if (item >= g.num_items) return;
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(256) rowsum_kernel(const EdgeParams g, const f
             carry[item] = acc;
             carry_in = false;
         } else {
-            out[row] = acc;
+            out[(size_t)row * ostride] = acc;
         }
         acc = 0.f;
         ++row;
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(256) rowsum_kernel(const EdgeParams g, const f
     } else if (carry_in) {
         carry[item] = acc;
     } else {
-        out[row] = acc;
+        out[(size_t)row * ostride] = acc;
     }
 }
 
@@ -102,7 +103,7 @@ constexpr int kRowsumChunk = 64;
 
 template <int PHASE>
 __global__ void __launch_bounds__(256) rowsum_fixup_kernel(const EdgeParams g, float *__restrict__ out,
-                                                           float *__restrict__ carry)
+                                                           float *__restrict__ carry, int ostride)
 {
     const int item = blockIdx.x * blockDim.x + threadIdx.x;
     if (item < 1 || item >= g.num_items) return;
@@ -124,9 +125,48 @@ __global__ void __launch_bounds__(256) rowsum_fixup_kernel(const EdgeParams g, f
     float acc = 0.f;
     for (int b = b0; b <= b1; b += step) acc += carry[b];
     if (PHASE == 2 || !long_span)
-        out[row] += acc;
+        out[(size_t)row * ostride] += acc;
     else
         carry[item] = acc;
+}
+
+// c[v] = <A[v,:], B[v,:]>: 8 lanes per row, float4 per lane (the <dY, Y> term of the GAT backward)
+__global__ void __launch_bounds__(256) rowdot_kernel(const float *__restrict__ A, const float *__restrict__ B,
+                                                     float *__restrict__ out, int num_rows, int F)
+{
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int sub = threadIdx.x & 7;
+    float acc = 0.f;
+    if (row < num_rows)
+        for (int col = sub * 4; col < F; col += 32) acc += dot4(ldg_f4(A + (size_t)row * F + col), ldg_f4(B + (size_t)row * F + col));
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (row < num_rows && sub == 0) out[row] = acc;
+}
+
+// Edge pass of the GAT backward (the part of aggr_gat_fine_bwd, aggr_gat.h:279-291, that is per edge):
+//   in : w[e] = exp(lrelu(s_e)) (un-normalised), den[v] = sum_e w, g[e] = <X[u], dY[v]>, c[v] = <Y[v], dY[v]>
+//   out: w[e] <- alpha_e = w_e / den[v];  g[e] <- ds_e = alpha_e (g_e - c_v) * lrelu'(s_e)
+// lrelu'(s) = s > 0 ? 1 : slope.  With the attention table the sign is read from s itself; without it
+// (att == NULL: the run_bwd signature only passes w) from w > 1, which is the same predicate because
+// w = exp(max(s, slope s)) and 0 <= slope < 1.
+__global__ void __launch_bounds__(256) gat_bwd_edge_kernel(const EdgeParams g, const float *__restrict__ att,
+                                                           const float *__restrict__ den, const float *__restrict__ c,
+                                                           float *__restrict__ w, float *__restrict__ gd, float slope)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= g.num_edges) return;
+    const int v = row_of_edge(g.ptr, g.item_row, g.num_items, g.num_rows, e);
+    const float we = w[e];
+    const float alpha = we / __ldg(den + v);
+    bool pos;
+    if (att)
+        pos = (__ldg(att + 2 * (size_t)v) + __ldg(att + 2 * (size_t)__ldg(g.idx + e) + 1)) > 0.f;
+    else
+        pos = we > 1.f;
+    w[e] = alpha;
+    gd[e] = alpha * (gd[e] - __ldg(c + v)) * (pos ? 1.f : slope);
 }
 
 // edge-wise GCN aggregation: Y[dst] += X[src]*val[e], one virtual warp per edge and 128-bit

@@ -26,6 +26,10 @@ int schedule_build_device(int kind, const int *d_ptr, const int *d_idx, const in
                           int par_num, int ng, int total, int **s_ptr, int **s_idx, int **s_target, int **s_perm,
                           int *num_target, int *sched_edges, cudaStream_t st);
 
+// transposed CSR (edges stably sorted by source) for the backward pass (sched_device.cu); outputs are cudaMalloc'ed
+int transpose_build_device(const int *d_ptr, const int *d_idx, const int *d_item_row, int num_items, int n, int m,
+                           int num_src, int **t_ptr, int **t_idx, int **t_perm, cudaStream_t st);
+
 // dense combination on tcgen05 (dense_tc.cu); stream is a cudaStream_t
 int dense_nn_launch(const float *A, const float *B, float *C, int64_t M, int N, int K, void *stream);
 

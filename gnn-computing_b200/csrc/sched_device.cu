@@ -223,4 +223,84 @@ fail:
     return GNNAGG_ERR_CUDA;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Transposed CSR for the backward pass (gnnagg_transpose_build): edges grouped by SOURCE, inside a source in
+// CSR order (a stable sort), so the gradient w.r.t. the gathered rows is again a gather-side aggregation
+//   dX[u,:] = sum over edges (v <- u) of w_e dY[v,:]
+// that runs through the same deterministic agg_kernel instead of the float atomics of the reference's
+// aggr_gat_fine_bwd (aggr_gat.h:264).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) iota_kernel(int *__restrict__ out, int count)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = i;
+}
+
+__global__ void __launch_bounds__(256) edge_rows_kernel(const int *__restrict__ ptr, const int *__restrict__ item_row,
+                                                        int num_items, int n, const int *__restrict__ perm, int m,
+                                                        int *__restrict__ out)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < m) out[j] = row_of_edge(ptr, item_row, num_items, n, __ldg(perm + j));
+}
+
+// row pointers from the sorted keys: t_ptr[u] = first position whose key is >= u
+__global__ void __launch_bounds__(256) ptr_from_sorted_kernel(const int *__restrict__ keys, int m, int num_src,
+                                                              int *__restrict__ t_ptr)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > m) return;
+    const int lo = (j == 0) ? 0 : __ldg(keys + j - 1) + 1;
+    const int hi = (j == m) ? num_src : __ldg(keys + j);
+    for (int u = lo; u <= hi; ++u) t_ptr[u] = j;
+}
+
+int transpose_build_device(const int *d_ptr, const int *d_idx, const int *d_item_row, int num_items, int n, int m,
+                           int num_src, int **t_ptr, int **t_idx, int **t_perm, cudaStream_t st)
+{
+    *t_ptr = *t_idx = *t_perm = nullptr;
+    int *edge_id = nullptr, *keys_sorted = nullptr;
+    void *tmp = nullptr;
+    size_t need = 0;
+    int ends[2] = {0, 0};
+    const size_t me = (size_t)(m > 0 ? m : 1);
+    SD_TRY(cudaMalloc((void **)t_ptr, ((size_t)num_src + 1) * sizeof(int)));
+    SD_TRY(cudaMalloc((void **)t_idx, me * sizeof(int)));
+    SD_TRY(cudaMalloc((void **)t_perm, me * sizeof(int)));
+    if (m == 0) {
+        SD_TRY(cudaMemsetAsync(*t_ptr, 0, ((size_t)num_src + 1) * sizeof(int), st));
+    } else {
+        SD_TRY(cudaMalloc((void **)&edge_id, me * sizeof(int)));
+        SD_TRY(cudaMalloc((void **)&keys_sorted, me * sizeof(int)));
+        iota_kernel<<<blocks(m), 256, 0, st>>>(edge_id, m);
+        SD_TRY(cub::DeviceRadixSort::SortPairs(nullptr, need, d_idx, keys_sorted, edge_id, *t_perm, m, 0, 32, st));
+        SD_TRY(cudaMalloc(&tmp, need ? need : 1));
+        SD_TRY(cub::DeviceRadixSort::SortPairs(tmp, need, d_idx, keys_sorted, edge_id, *t_perm, m, 0, 32, st));  // stable
+        SD_TRY(cudaMemcpyAsync(&ends[0], keys_sorted, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SD_TRY(cudaMemcpyAsync(&ends[1], keys_sorted + (m - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+        SD_TRY(cudaStreamSynchronize(st));
+        if (ends[0] < 0 || ends[1] >= num_src) {
+            set_error(GNNAGG_ERR_ARG, "gnnagg_transpose_build: a source id lies outside [0, num_src)");
+            goto fail_keep_error;
+        }
+        edge_rows_kernel<<<blocks(m), 256, 0, st>>>(d_ptr, d_item_row, num_items, n, *t_perm, m, *t_idx);
+        ptr_from_sorted_kernel<<<blocks((int64_t)m + 1), 256, 0, st>>>(keys_sorted, m, num_src, *t_ptr);
+    }
+    SD_TRY(cudaGetLastError());
+    SD_TRY(cudaStreamSynchronize(st));
+    cudaFree(edge_id), cudaFree(keys_sorted), cudaFree(tmp);
+    return GNNAGG_OK;
+fail:
+    cudaFree(edge_id), cudaFree(keys_sorted), cudaFree(tmp);
+    cudaFree(*t_ptr), cudaFree(*t_idx), cudaFree(*t_perm);
+    *t_ptr = *t_idx = *t_perm = nullptr;
+    return GNNAGG_ERR_CUDA;
+fail_keep_error:
+    cudaFree(edge_id), cudaFree(keys_sorted), cudaFree(tmp);
+    cudaFree(*t_ptr), cudaFree(*t_idx), cudaFree(*t_perm);
+    *t_ptr = *t_idx = *t_perm = nullptr;
+    return GNNAGG_ERR_ARG;
+}
+
 }  // namespace gnnagg

@@ -201,6 +201,31 @@ int gnnagg_mlp_run(gnnagg_aggregator *a, const float *X, const float *W, float *
 int gnnagg_sddmm(gnnagg_aggregator *a, const float *X1, const float *X2, float *out_val, int feat, int scheduled,
                  void *stream);
 
+/* ---- backward of the aggregation ---------------------------------------------------
+ * The reference has one experimental backward kernel, aggr_gat_fine_bwd behind Aggregator_GAT::run_bwd
+ * (include/aggr_gat.h:222-294, :426-434): float atomics into d_feat (:264), F = 32 only (:245), LeakyReLU
+ * derivative keyed on `newval < 0` (never true, :289), source half of the attention gradient only (:290).
+ * These entry points compute the full, deterministic derivative of gnnagg_gcn_run / gnnagg_gat_run instead.
+ *
+ * gnnagg_transpose_build  once per graph: the CSR transposed ON THE GPU (edges stably sorted by source;
+ *                         num_src = number of source rows, = num_v for a square graph), kept in the handle.
+ * gnnagg_transpose_dev    device views of it: t_ptr[num_src+1], t_idx[m] = destination rows,
+ *                         t_perm[m] = CSR edge id at every transposed position.
+ * gnnagg_gcn_backward     dX[u,:] = sum over edges (v <- u) of val_e dY[v,:]   (= A^T dY), dX is [num_src, feat].
+ * gnnagg_gat_backward     for Y = gnnagg_gat_run(X, att) and dL/dY = dY:
+ *                           alpha_e = w_e / D_v, ds_e = alpha_e (<X[u],dY[v]> - <Y[v],dY[v]>) * (s_e > 0 ? 1 : slope)
+ *                           dX[u,:] = sum_e alpha_e dY[v,:]            (:264)
+ *                           datt[2v] = sum_e ds_e,  datt[2u+1] = sum_e ds_e   (:287-290; att/datt have max(num_v,num_src) rows)
+ *                         Either `att` is given (w, den may be NULL: weights are recomputed), or w[m] (un-normalised
+ *                         weights in CSR order, what aggr_gat_fine leaves in newval, :193) and den[num_v] (`div` of
+ *                         run_bwd) -- then att may be NULL and the sign of s_e is read from w_e > 1.
+ *                         Outputs are overwritten (the reference accumulates into caller-zeroed arrays). */
+int gnnagg_transpose_build(gnnagg_aggregator *a, int num_src, void *stream);
+int gnnagg_transpose_dev(const gnnagg_aggregator *a, int *num_src, const int **t_ptr, const int **t_idx, const int **t_perm);
+int gnnagg_gcn_backward(gnnagg_aggregator *a, const float *dY, float *dX, int feat, void *stream);
+int gnnagg_gat_backward(gnnagg_aggregator *a, const float *X, const float *att, const float *w, const float *den,
+                        const float *Y, const float *dY, float *dX, float *datt, int feat, float slope, void *stream);
+
 /* naive reference-style SpMM + validators of include/spmm.h:
  *   gnnagg_spmm_naive        replaces spmm<LENFEATURE> (spmm.h:223-265; thread per row; rows
  *                            with no edge are left untouched as there, :236-237)

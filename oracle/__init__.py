@@ -178,6 +178,42 @@ def sddmm_f64(ptr, idx, X1, X2):
     return out, S
 
 
+# ------------------------------------------------------------------ backward
+def transpose_csr(ptr, idx, num_src):
+    m = len(idx)
+    t_ptr, t_idx, t_perm = np.empty(num_src + 1, np.int32), np.empty(m, np.int32), np.empty(m, np.int32)
+    lib().orc_transpose_csr(C.c_int64(len(ptr) - 1), _vp(ptr), _vp(idx), C.c_int(num_src), _vp(t_ptr), _vp(t_idx), _vp(t_perm))
+    return t_ptr, t_idx, t_perm
+
+
+def spmm_t_f64(ptr, idx, val, dY, num_src):
+    F = dY.shape[1]
+    dX, S = np.empty((num_src, F), np.float32), np.empty((num_src, F), np.float32)
+    lib().orc_spmm_t_f64(C.c_int64(len(ptr) - 1), _vp(ptr), _vp(idx), _vp(val), _vp(dY), C.c_int(F), C.c_int(num_src),
+                         _vp(dX), _vp(S))
+    return dX, S
+
+
+def gat_backward_f64(ptr, idx, att, X, dY, slope=0.2):
+    """(dX, datt, dX_scale, datt_scale); att / datt have X.shape[0] = max(n, num_src) rows"""
+    n, (num_src, F) = len(ptr) - 1, X.shape
+    rows = att.shape[0]
+    assert rows >= n and rows >= num_src
+    dX, SX = np.empty((num_src, F), np.float32), np.empty((num_src, F), np.float32)
+    dA, SA = np.empty((rows, 2), np.float32), np.empty((rows, 2), np.float32)
+    lib().orc_gat_backward_f64(C.c_int64(n), _vp(ptr), _vp(idx), _vp(att), C.c_float(slope), _vp(X), _vp(dY), C.c_int(F),
+                               C.c_int(num_src), C.c_int64(rows), _vp(dX), _vp(dA), _vp(SX), _vp(SA))
+    return dX, dA, SX, SA
+
+
+def gat_loss_f64(ptr, idx, att64, X64, dY64, slope=0.2):
+    """sum(dY * Y(att, X)) with fp64 inputs: the scalar the finite-difference test differentiates"""
+    f = lib().orc_gat_loss_f64
+    f.restype = C.c_double
+    return f(C.c_int64(len(ptr) - 1), _vp(ptr), _vp(idx), _vp(att64), C.c_double(slope), _vp(X64), _vp(dY64),
+             C.c_int(X64.shape[1]))
+
+
 # ------------------------------------------------------------------ integer path
 def neighbor_grouping(ptr, idx, neighbor_num):
     n, m = len(ptr) - 1, len(idx)

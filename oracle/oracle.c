@@ -538,3 +538,140 @@ int orc_validate_reordered(const float *ref, const float *ans, const int *map, i
         if (fabsf(ref[t] - ans[(size_t)map[t / F] * F + t % F]) > 1e-2f) ++diff;
     return diff;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Backward of the aggregation.  The reference only has the experimental
+ * aggr_gat_fine_bwd (aggr_gat.h:222-294, run_bwd :426-434), used by no driver: F = 32 only
+ * (`doutput[which_v*INFEATURE + lane]`, :245), the LeakyReLU derivative is keyed on
+ * `newval < 0` which never holds for newval = exp(.) (:289), and only the source half of the
+ * attention gradient is produced (:290).  What follows is the full derivative of the forward
+ * oracle above; it coincides with that kernel where the kernel is right (F = 32, all pre-
+ * activations positive, source half) -- tests/test_backward_gpu.py checks exactly that on the
+ * GPU, tests/test_backward.py checks it against finite differences of orc_gat_f64.
+ * ------------------------------------------------------------------------------------------ */
+
+/* stable transpose of a CSR: edges grouped by source, inside a source in CSR order (hence by
+ * ascending destination).  t_ptr[num_src+1], t_idx[m] = destination rows, t_perm[m] = CSR edge id. */
+void orc_transpose_csr(int64_t n, const int *ptr, const int *idx, int num_src, int *t_ptr, int *t_idx, int *t_perm)
+{
+    const int m = ptr[n];
+    memset(t_ptr, 0, ((size_t)num_src + 1) * sizeof(int));
+    for (int e = 0; e < m; ++e) ++t_ptr[idx[e] + 1];
+    for (int u = 0; u < num_src; ++u) t_ptr[u + 1] += t_ptr[u];
+    int *fill = (int *)malloc(((size_t)num_src + 1) * sizeof(int));
+    memcpy(fill, t_ptr, ((size_t)num_src + 1) * sizeof(int));
+    for (int64_t v = 0; v < n; ++v)
+        for (int e = ptr[v]; e < ptr[v + 1]; ++e) {
+            const int pos = fill[idx[e]]++;
+            t_idx[pos] = (int)v;
+            t_perm[pos] = e;
+        }
+    free(fill);
+}
+
+/* dX[u,:] = sum over edges (v <- u) of val_e * dY[v,:]   (gradient of orc_spmm w.r.t. X); fp64 */
+void orc_spmm_t_f64(int64_t n, const int *ptr, const int *idx, const float *val, const float *dY, int F, int num_src,
+                    float *dX, float *scale)
+{
+    double *acc = (double *)calloc((size_t)num_src * F * 2, sizeof(double));
+    double *mag = acc + (size_t)num_src * F;
+    for (int64_t v = 0; v < n; ++v)
+        for (int e = ptr[v]; e < ptr[v + 1]; ++e) {
+            const double w = val[e];
+            double *a = acc + (size_t)idx[e] * F, *g = mag + (size_t)idx[e] * F;
+            const float *d = dY + (size_t)v * F;
+            for (int c = 0; c < F; ++c) {
+                a[c] += w * (double)d[c];
+                g[c] += fabs(w * (double)d[c]);
+            }
+        }
+    for (size_t i = 0; i < (size_t)num_src * F; ++i) {
+        dX[i] = (float)acc[i];
+        if (scale) scale[i] = (float)mag[i];
+    }
+    free(acc);
+}
+
+/* Backward of orc_gat_f64 for a loss with dL/dY = dY:
+ *   alpha_e = w_e / D_v,  g_e = <X[u], dY[v]>,  c_v = <Y[v], dY[v]>
+ *   ds_e    = alpha_e (g_e - c_v) * (s_e > 0 ? 1 : slope)            [= aggr_gat.h:287-289 where that is right]
+ *   dX[u]  += alpha_e dY[v]                                          [:264]
+ *   datt[2v] += ds_e (destination term), datt[2u+1] += ds_e (source term, :290)
+ * att and datt have `att_rows` = max(n, num_src) rows.  dX_scale / datt_scale receive the sums of the
+ * magnitudes of the terms (error bounds for the fp32 implementation). */
+void orc_gat_backward_f64(int64_t n, const int *ptr, const int *idx, const float *att, float slope, const float *X,
+                          const float *dY, int F, int num_src, int64_t att_rows, float *dX, float *datt, float *dX_scale,
+                          float *datt_scale)
+{
+    double *ax = (double *)calloc((size_t)num_src * F * 2, sizeof(double));
+    double *mx = ax + (size_t)num_src * F;
+    double *da = (double *)calloc((size_t)att_rows * 4, sizeof(double));
+    double *ma = da + (size_t)att_rows * 2;
+    double *y = (double *)malloc((size_t)F * sizeof(double));
+    for (int64_t v = 0; v < n; ++v) {
+        if (ptr[v] == ptr[v + 1]) continue;
+        const float *d = dY + (size_t)v * F;
+        double D = 0.0;
+        for (int c = 0; c < F; ++c) y[c] = 0.0;
+        for (int e = ptr[v]; e < ptr[v + 1]; ++e) {
+            const double w = gat_w(att, v, idx[e], slope);
+            const float *x = X + (size_t)idx[e] * F;
+            D += w;
+            for (int c = 0; c < F; ++c) y[c] += w * (double)x[c];
+        }
+        double cv = 0.0, cmag = 0.0;
+        for (int c = 0; c < F; ++c) {
+            cv += y[c] / D * (double)d[c];
+            cmag += fabs(y[c] / D * (double)d[c]);
+        }
+        for (int e = ptr[v]; e < ptr[v + 1]; ++e) {
+            const int u = idx[e];
+            const double alpha = gat_w(att, v, u, slope) / D;
+            const float *x = X + (size_t)u * F;
+            double g = 0.0, gmag = 0.0;
+            for (int c = 0; c < F; ++c) {
+                g += (double)x[c] * (double)d[c];
+                gmag += fabs((double)x[c] * (double)d[c]);
+                ax[(size_t)u * F + c] += alpha * (double)d[c];
+                mx[(size_t)u * F + c] += fabs(alpha * (double)d[c]);
+            }
+            const float s = att[2 * v] + att[2 * (size_t)u + 1];
+            const double lr = (s > 0.0f) ? 1.0 : (double)slope;
+            const double ds = alpha * (g - cv) * lr, dm = alpha * (gmag + cmag) * lr;
+            da[2 * v] += ds, ma[2 * v] += dm;
+            da[2 * (size_t)u + 1] += ds, ma[2 * (size_t)u + 1] += dm;
+        }
+    }
+    for (size_t i = 0; i < (size_t)num_src * F; ++i) {
+        dX[i] = (float)ax[i];
+        if (dX_scale) dX_scale[i] = (float)mx[i];
+    }
+    for (size_t i = 0; i < (size_t)att_rows * 2; ++i) {
+        datt[i] = (float)da[i];
+        if (datt_scale) datt_scale[i] = (float)ma[i];
+    }
+    free(ax), free(da), free(y);
+}
+
+/* scalar loss L = sum(dY * Y) of the forward oracle, all in fp64 with fp64 inputs: the function the
+ * finite-difference test differentiates (tests/test_backward.py) */
+double orc_gat_loss_f64(int64_t n, const int *ptr, const int *idx, const double *att, double slope, const double *X,
+                        const double *dY, int F)
+{
+    double L = 0.0;
+    double *y = (double *)malloc((size_t)F * sizeof(double));
+    for (int64_t v = 0; v < n; ++v) {
+        if (ptr[v] == ptr[v + 1]) continue;
+        double D = 0.0;
+        for (int c = 0; c < F; ++c) y[c] = 0.0;
+        for (int e = ptr[v]; e < ptr[v + 1]; ++e) {
+            const double s = att[2 * v] + att[2 * (size_t)idx[e] + 1];
+            const double w = exp(s > s * slope ? s : s * slope);
+            D += w;
+            for (int c = 0; c < F; ++c) y[c] += w * X[(size_t)idx[e] * F + c];
+        }
+        for (int c = 0; c < F; ++c) L += y[c] / D * dY[(size_t)v * F + c];
+    }
+    free(y);
+    return L;
+}
