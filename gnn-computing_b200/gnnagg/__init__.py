@@ -77,6 +77,10 @@ _SIGS = {
     "gnnagg_each_div": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gnnagg_mlp_run": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_void_p]),
     "gnnagg_sddmm": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_void_p]),
+    "gnnagg_transpose_build": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "gnnagg_transpose_dev": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)] + [C.POINTER(C.c_void_p)] * 3),
+    "gnnagg_gcn_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "gnnagg_gat_backward": (C.c_int, [C.c_void_p] * 9 + [C.c_int, C.c_float, C.c_void_p]),
     "gnnagg_gather_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "gnnagg_spmm_naive": (C.c_int, [C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p]),
     "gnnagg_validate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int), C.c_void_p]),
@@ -353,6 +357,34 @@ class Aggregator:
     def sddmm(self, X1, X2, out_val, scheduled=False):
         check(lib().gnnagg_sddmm(self.h, _dp(X1), _dp(X2), _dp(out_val), X1.shape[1], int(scheduled), _stream()))
         return out_val
+
+    # --- backward (transposed CSR built once on the GPU, then gather-side aggregation over it)
+    def transpose_build(self, num_src=None):
+        self.num_src = self.n if num_src is None else int(num_src)
+        check(lib().gnnagg_transpose_build(self.h, self.num_src, _stream()))
+
+    def transposed_arrays(self):
+        """(t_ptr, t_idx, t_perm) copied back as numpy"""
+        L = lib()
+        ns, tp, ti, tq = C.c_int(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(L.gnnagg_transpose_dev(self.h, C.byref(ns), C.byref(tp), C.byref(ti), C.byref(tq)))
+
+        def back(p, count):
+            out = np.empty(count, np.int32)
+            if p.value and count:
+                check(L.gnnagg_memcpy_d2h(out.ctypes.data, p, count * 4))
+            return out
+
+        return back(tp, ns.value + 1), back(ti, self.m), back(tq, self.m)
+
+    def gcn_backward(self, dY, dX):
+        check(lib().gnnagg_gcn_backward(self.h, _dp(dY), _dp(dX), dY.shape[1], _stream()))
+        return dX
+
+    def gat_backward(self, X, att, Y, dY, dX, datt, slope=0.2, w=None, den=None):
+        check(lib().gnnagg_gat_backward(self.h, _dp(X), _dp(att), _dp(w), _dp(den), _dp(Y), _dp(dY), _dp(dX), _dp(datt),
+                                        X.shape[1], slope, _stream()))
+        return dX, datt
 
     # --- host-buffer entry points (pinned CPU tensors or numpy arrays)
     def gcn_run_host(self, hX, hY, scheduled=False):

@@ -41,11 +41,22 @@ public:
     {
         checkGnnagg(gnnagg_each_div(handle, in_att, in_out_val, NULL));
     }
-    // the experimental backward kernel (aggr_gat_fine_bwd, :222-294) is used by no driver of the
-    // reference and is outside the forward hot path
-    void run_bwd(float *, float *, float *, float *, float *, float *, float *, float, int)
+    // backward of the scheduled fused aggregation (run_bwd + aggr_gat_fine_bwd, :222-294, :426-434): output = the
+    // normalised forward result, newval = the un-normalised edge weights aggr_gat_fine left behind (:193), div = their
+    // row sums (`scalar`).  Differences from the experimental reference kernel, all documented in gnnagg.h: any
+    // feat_in (there 32 only), correct LeakyReLU derivative, BOTH halves of d_a_b, deterministic, and the two
+    // outputs are overwritten rather than accumulated into caller-zeroed arrays.
+    void run_bwd(float *output, float *doutput, float *newval, float *div, float *infeat, float *d_a_b, float *d_feat,
+                 float relu_l, int BLOCK_SIZE)
     {
-        FatalError("Aggregator_GAT::run_bwd is not part of the forward aggregation path");
+        if (!transposed) {
+            checkGnnagg(gnnagg_transpose_build(handle, vertex_count(), NULL));
+            transposed = true;
+        }
+        checkGnnagg(gnnagg_gat_backward(handle, infeat, NULL, newval, div, output, doutput, d_feat, d_a_b, feat_in, relu_l, NULL));
     }
+
+private:
+    bool transposed = false;
 };
 #endif

@@ -172,6 +172,13 @@ void ref_gat_run_div_each(void *h, float *in_att, float *inout_val, int block)
     ((Aggregator_GAT *)h)->run_div_each(in_att, inout_val, block);
 }
 
+// the experimental backward (aggr_gat.h:426-434); needs a neighbor_grouping schedule (it walks the scheduled arrays)
+void ref_gat_run_bwd(void *h, float *output, float *doutput, float *newval, float *div, float *infeat, float *d_a_b,
+                     float *d_feat, float relu_l, int block)
+{
+    ((Aggregator_GAT *)h)->run_bwd(output, doutput, newval, div, infeat, d_a_b, d_feat, relu_l, block);
+}
+
 void *ref_sddmm_create(int *d_ptr, int *d_idx, int num_v, int num_e, int feat)
 {
     registerPtr(d_ptr);

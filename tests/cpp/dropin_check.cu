@@ -97,6 +97,39 @@ int main(int argc, char **argv)
     expect("attGat+aggr_gcn_target vs fused aggr_gat_fine", valid(y, y2, n * F));
     atgcn->updateval(val);
 
+    // ---- GAT backward (run_bwd, aggr_gat.h:426-434) with newval = the normalised edge softmax and div = 1:
+    // the weights of a row add up to 1, so  sum_u d_feat[u,:] == sum over non-empty rows v of doutput[v,:],
+    // and both halves of d_a_b hold the same total (each edge contributes ds_e once to either half)
+    {
+        std::vector<float> ones(n, 1.0f), h_dfeat(nf), h_dy(nf), h_dab(2 * (size_t)n);
+        std::vector<int> h_ptr(n + 1);
+        float *div = NULL, *d_ab = NULL;
+        checkCudaErrors(cudaMalloc2((void **)&div, n * sizeof(float)));
+        checkCudaErrors(cudaMalloc2((void **)&d_ab, 2 * (size_t)n * sizeof(float)));
+        checkCudaErrors(cudaMemcpy(div, ones.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+        atgat->run(x, att, y2, 128, 0);
+        atgat->run_bwd(y2, y_naive, eval, div, x, d_ab, y, 1.0f, 128);  // doutput = y_naive, d_feat -> y
+        checkCudaErrors(cudaDeviceSynchronize());
+        checkCudaErrors(cudaMemcpy(h_dfeat.data(), y, nf * sizeof(float), cudaMemcpyDeviceToHost));
+        checkCudaErrors(cudaMemcpy(h_dy.data(), y_naive, nf * sizeof(float), cudaMemcpyDeviceToHost));
+        checkCudaErrors(cudaMemcpy(h_dab.data(), d_ab, 2 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+        checkCudaErrors(cudaMemcpy(h_ptr.data(), gptrs[0], (n + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+        int bad = 0;
+        for (int c = 0; c < F; ++c) {
+            double lhs = 0, rhs = 0, mag = 0;
+            for (int v = 0; v < n; ++v) {
+                lhs += h_dfeat[(size_t)v * F + c];
+                if (h_ptr[v + 1] > h_ptr[v]) rhs += h_dy[(size_t)v * F + c], mag += fabs(h_dy[(size_t)v * F + c]);
+            }
+            if (fabs(lhs - rhs) > 1e-4 * (mag + 1)) ++bad;
+        }
+        double dst_half = 0, src_half = 0, amag = 0;
+        for (int v = 0; v < n; ++v) dst_half += h_dab[2 * (size_t)v], src_half += h_dab[2 * (size_t)v + 1], amag += fabs(h_dab[2 * (size_t)v + 1]);
+        if (fabs(dst_half - src_half) > 1e-4 * (amag + 1)) ++bad;
+        expect("run_bwd: column sums of d_feat, totals of the two d_a_b halves", bad);
+        cudaFree(div), cudaFree(d_ab);
+    }
+
     // ---- fused layer vs aggregation + matmul_NN (Figure10/main_b.cu:84-101)
     float *t1 = dev_random(curand, (size_t)n * OUT + 64, true), *t2 = dev_random(curand, (size_t)n * OUT + 64, true);
     cublasCreate(&cublasHs[0]);

@@ -11,7 +11,9 @@ mkdir -p "$OUT"
 CCBIN=""; [ -x /usr/bin/g++ ] && CCBIN="-ccbin /usr/bin/g++"
 FLAGS="$CCBIN -std=c++17 -O2 -w -gencode arch=compute_100a,code=sm_100a -I$ROOT/include -L$ROOT/gnn-computing_b200/lib -lgnnagg -lcurand -lcublas -Xlinker -rpath,$ROOT/gnn-computing_b200/lib -Xlinker -rpath,\$ORIGIN/../../gnn-computing_b200/lib"
 build() { # src out
-  if [ ! -f "$2" ] || [ "$1" -nt "$2" ] || [ "$ROOT/include/util.h" -nt "$2" ] || [ "$ROOT/include/aggr_gcn.h" -nt "$2" ]; then
+  local stale=0
+  for h in "$ROOT"/include/*.h; do [ "$h" -nt "$2" ] && stale=1; done
+  if [ ! -f "$2" ] || [ "$1" -nt "$2" ] || [ $stale = 1 ]; then
     nvcc $FLAGS "$1" -o "$2"
   fi
 }
