@@ -40,7 +40,9 @@ struct AggParams {
     float *__restrict__ carry;           // [num_items, F] partials of rows entering an item
     float *__restrict__ den_row;         // GAT: [n] denominator of rows that start in an item and leave it
     float *__restrict__ carry_den;       // GAT: [num_items]
-    float *__restrict__ newval;          // GAT scheduled: un-normalised edge weights (aggr_gat.h:192)
+    float *__restrict__ newval;          // GAT scheduled: un-normalised edge weights (aggr_gat.h:192); GAT backward: alpha_e
+    const float2 *__restrict__ bwd_c;    // GAT backward: per row (1 / D_v, c_v = <Y[v], dY[v]>)
+    float *__restrict__ bwd_ds;          // GAT backward: ds_e (gradient of the pre-activation of edge e)
     int num_rows;
     int num_edges;
     int F;
@@ -53,8 +55,12 @@ struct AggParams {
     int row_lo, row_hi, edge_lo, edge_hi;
 };
 
-enum { kModeGCN = 0, kModeGAT = 1, kModeMLP = 2, kModeSDDMM = 3 };
-__host__ __device__ constexpr bool mode_has_dst(int mode) { return mode == kModeMLP || mode == kModeSDDMM; }  // keeps P[dst,:] in registers
+// kModeGATBWD: the SDDMM traversal with X2 = dY whose per-edge epilogue turns g_e = <X[u], dY[v]> into the
+// softmax-normalised weight alpha_e and the pre-activation gradient ds_e (edge pass of aggr_gat_fine_bwd,
+// aggr_gat.h:266-290): att (or val = un-normalised weights), den_row = D_v and bwd_c are inputs.
+enum { kModeGCN = 0, kModeGAT = 1, kModeMLP = 2, kModeSDDMM = 3, kModeGATBWD = 4 };
+__host__ __device__ constexpr bool mode_emits_edges(int mode) { return mode == kModeSDDMM || mode == kModeGATBWD; }  // per-edge outputs, no row sums
+__host__ __device__ constexpr bool mode_has_dst(int mode) { return mode == kModeMLP || mode_emits_edges(mode); }  // keeps P[dst,:] in registers
 __host__ __device__ constexpr bool mode_stages_val(int mode) { return mode == kModeGCN; }
 
 // row that contains edge e0 (start of an item): direct lookup when items are aligned with the
@@ -95,20 +101,22 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
     int first_row = 0, first_row_end = 0, first_row_begin = 0;
     {
         const int nb = p.bulk_ok ? (wcnt & ~3) : 0;  // bulk copies need 16-byte multiples
+        // edge values travel with idx for GCN, and for the GAT backward when the weights are handed in (no table)
+        const bool stage_val = (MODE == kModeGCN) || (MODE == kModeGATBWD && p.att == nullptr);
         const uint32_t bar = smem_u32(&s_bar[warp]);
         if (nb > 0) {
             if (lane == 0) {
                 mbar_init(bar, 1);
                 fence_proxy_async();  // init visible to the async proxy; CTA scope (no L1 invalidate)
                 const uint32_t bytes = (uint32_t)nb * 4u;
-                mbar_expect_tx(bar, (MODE == kModeGCN) ? 2u * bytes : bytes);  // GAT / MLP stage idx only
+                mbar_expect_tx(bar, stage_val ? 2u * bytes : bytes);  // GAT / MLP / SDDMM stage idx only
                 bulk_g2s(smem_u32(my_idx), p.idx + wbase, bytes, bar);
-                if (MODE == kModeGCN) bulk_g2s(smem_u32(my_val), p.val + wbase, bytes, bar);
+                if (stage_val) bulk_g2s(smem_u32(my_val), p.val + wbase, bytes, bar);
             }
         }
         for (int i = nb + lane; i < wcnt; i += 32) {
             my_idx[i] = __ldg(p.idx + wbase + i);
-            if (MODE == kModeGCN) my_val[i] = __ldg(p.val + wbase + i);
+            if (stage_val) my_val[i] = __ldg(p.val + wbase + i);
         }
         // the start row of this lane's item is looked up while the bulk copy is in flight
         {
@@ -121,7 +129,7 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
         }
         __syncwarp();
         if (nb > 0) mbar_wait(bar, 0);
-        if (MODE == kModeGAT) {
+        if (MODE == kModeGAT || (MODE == kModeGATBWD && !stage_val)) {
             // source half of the attention logit, gathered once per edge: att[2u+1] (aggr_gat.h:138)
 #pragma unroll 4
             for (int i = lane; i < wcnt; i += 32) my_val[i] = __ldg(p.att + 2 * (size_t)my_idx[i] + 1);
@@ -163,7 +171,7 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
 
         // closes `row`: writes / accumulates its result and moves to the next row
         auto flush = [&](bool at_item_end) {
-            if (MODE == kModeSDDMM) {
+            if (mode_emits_edges(MODE)) {
                 // nothing is accumulated per row: the flush only advances to the next row / group
             } else if (SCHED) {
                 const int t = __ldg(p.target + row);
@@ -225,12 +233,14 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
 
         // per-edge combination of the gathered row (u is a compile-time constant after unrolling)
         float dd[U];  // SDDMM: this lane's partial dot products of the batch
+        int drow[U];  // GAT backward: destination row of every edge of the batch (uniform over the virtual warp)
         auto combine = [&](const int u, const float wu, const float4 &a0, const float4 &a1) {
             if (MODE == kModeMLP) {
                 relu_add4(acc0, pd0, a0);
                 if (NV > 1) relu_add4(acc1, pd1, a1);
-            } else if (MODE == kModeSDDMM) {
+            } else if (mode_emits_edges(MODE)) {
                 dd[u] = (act0 ? dot4(pd0, a0) : 0.f) + ((NV > 1 && act1) ? dot4(pd1, a1) : 0.f);
+                if (MODE == kModeGATBWD) drow[u] = row;
             } else {
                 fma4(acc0, wu, a0);
                 if (NV > 1) fma4(acc1, wu, a1);
@@ -238,11 +248,43 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
         };
         // SDDMM: totals of the batch's dot products (reduce-scatter over the virtual warp) -> out[e .. e+nb)
         auto sddmm_emit = [&](const int nb) {
-            VwReduceScatter<LPR, LPR / 2, U>::run(dd, vl, vw_mask);
             const int id = vl / (LPR / U);
-            if ((vl % (LPR / U)) == 0 && id < nb) {
-                float *o = p.newval + e + id;
-                *o = (cb == 0) ? dd[0] : *o + dd[0];  // wide rows: column chunks accumulate
+            const bool writer = (vl % (LPR / U)) == 0 && id < nb;
+            // GAT backward: everything the epilogue needs besides g_e is fetched before the shuffles
+            float sv = 0.f, a_v = 0.f;
+            float2 ri = make_float2(0.f, 0.f);
+            if (MODE == kModeGATBWD && writer && cb + CHUNK >= F) {
+                int v = drow[0];
+#pragma unroll
+                for (int u = 1; u < U; ++u)
+                    if (id == u) v = drow[u];
+                sv = my_val[e + id - wbase];  // att[2u+1], or the handed-in weight
+                ri = __ldg(p.bwd_c + v);
+                if (p.att != nullptr) a_v = __ldg(p.att + 2 * (size_t)v);
+            }
+            VwReduceScatter<LPR, LPR / 2, U>::run(dd, vl, vw_mask);
+            if (writer) {
+                if (MODE == kModeSDDMM) {
+                    float *o = p.newval + e + id;
+                    *o = (cb == 0) ? dd[0] : *o + dd[0];  // wide rows: column chunks accumulate
+                } else {
+                    float *o = p.bwd_ds + e + id;
+                    const float g = (cb == 0) ? dd[0] : *o + dd[0];
+                    if (cb + CHUNK < F) {
+                        *o = g;  // more column chunks to come
+                    } else {
+                        float w = sv;         // handed in: newval of aggr_gat_fine; s > 0 <=> w > 1
+                        bool pos = sv > 1.f;
+                        if (p.att != nullptr) {
+                            const float sc = a_v + sv;
+                            pos = sc > 0.f;
+                            w = __expf(fmaxf(sc, sc * p.slope));  // aggr_gat.h:190
+                        }
+                        const float alpha = w * ri.x;
+                        p.newval[e + id] = alpha;
+                        *o = alpha * (g - ri.y) * (pos ? 1.f : p.slope);  // :287-289
+                    }
+                }
             }
         };
 
@@ -277,14 +319,14 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
                         if (SCHED && vl == u % LPR) wout = wu;
                     }
                     combine(u, wu, v0[u], v1[u]);
-                } else if (MODE == kModeSDDMM) {
+                } else if (mode_emits_edges(MODE)) {
                     dd[u] = 0.f;
                 }
             }
             if (MODE == kModeGAT && SCHED && cb == 0 && p.newval != nullptr) {
                 if (vl < nb) p.newval[e + vl] = wout;
             }
-            if (MODE == kModeSDDMM) sddmm_emit(nb);
+            if (mode_emits_edges(MODE)) sddmm_emit(nb);
             e += nb;
         };
 
@@ -352,14 +394,14 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
                 // one coalesced store per batch instead of one per edge (U <= LPR always holds)
                 if (vl < U) p.newval[e + vl] = wout;
             }
-            if (MODE == kModeSDDMM) sddmm_emit(U);
+            if (mode_emits_edges(MODE)) sddmm_emit(U);
             e += U;
         }
 
         if (e < e1) short_batch(e1 - e);
 
         // item end
-        if (MODE == kModeSDDMM) {
+        if (mode_emits_edges(MODE)) {
             // per-edge outputs were written batch by batch
         } else if (row_end == e1) {
             while (row < p.row_hi && row_end == e1) flush(true);  // row closes here (+ trailing empty rows)

@@ -94,8 +94,8 @@ struct gnnagg_aggregator {
     gnnagg_aggregator *tr = nullptr;
     float *t_val = nullptr;    // edge values in transposed order (owned, m floats)
     const float *t_val_of = nullptr;  // which d_val t_val currently mirrors (NULL: none / attention weights)
-    float *bwd_g = nullptr, *bwd_c = nullptr;
-    size_t bwd_g_cap = 0, bwd_c_cap = 0;
+    float *bwd_g = nullptr, *bwd_c = nullptr, *bwd_t = nullptr;
+    size_t bwd_g_cap = 0, bwd_c_cap = 0, bwd_t_cap = 0;
     // host-buffer entry points: the result is copied back per row chunk on a second stream while the next chunk computes
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -213,7 +213,7 @@ static int launch_agg(gnnagg_aggregator *a, AggParams p, cudaStream_t st)
         launch_agg_we<MODE, SCHED, kWarpEdges>(p, st);
     LAUNCH_CHECK(a);
     PROF_RECORD(a, 2, st);
-    if (!SCHED && MODE != kModeSDDMM) {
+    if (!SCHED && !mode_emits_edges(MODE)) {
         const int EB = item_edges_for(a, p.F, p.num_edges);
         const int64_t items = cdiv(p.num_edges, EB);
         const int64_t range_items = cdiv(p.edge_hi, EB) - p.edge_lo / EB;  // items touched by the launched range
@@ -453,7 +453,8 @@ static int gat_run_impl(gnnagg_aggregator *a, const float *X, const float *att, 
 
 // out[v * ostride] = sum over row v of in[e], rows and edges as described by g; deterministic.
 // `a` owns the carry scratch (sized for ITS item count: g must describe a's graph).
-static int rowsum_impl(gnnagg_aggregator *a, const float *in, float *out, cudaStream_t st, int ostride = 1)
+template <int SRC = kSumArray>
+static int rowsum_impl(gnnagg_aggregator *a, const float *in, float *out, cudaStream_t st, int ostride = 1, float slope = 0.f)
 {
     if (a->m == 0) {
         if (ostride == 1)
@@ -462,15 +463,16 @@ static int rowsum_impl(gnnagg_aggregator *a, const float *in, float *out, cudaSt
             CUDA_TRY(cudaMemset2DAsync(out, (size_t)ostride * sizeof(float), 0, sizeof(float), (size_t)a->n, st));
         return GNNAGG_OK;
     }
-    if (int rc = ensure(a->carry_den, a->carry_den_cap, (size_t)a->num_items)) return rc;
+    const int64_t items = cdiv(a->m, kRowsumItem);
+    if (int rc = ensure(a->carry_den, a->carry_den_cap, (size_t)items)) return rc;
     const EdgeParams g = edge_params(a);
-    const unsigned grid = (unsigned)cdiv(a->num_items, 256);
-    rowsum_kernel<<<grid, 256, 0, st>>>(g, in, out, a->carry_den, ostride);
+    const unsigned grid = (unsigned)cdiv(items, 256);
+    rowsum_kernel<SRC><<<grid, 256, 0, st>>>(g, in, slope, out, a->carry_den, ostride);
     LAUNCH_CHECK(a);
-    if (a->num_items > 1) {
+    if (items > 1) {
         rowsum_fixup_kernel<1><<<grid, 256, 0, st>>>(g, out, a->carry_den, ostride);
         LAUNCH_CHECK(a);
-        if (a->num_items > kRowsumChunk + 1) {
+        if (items > kRowsumChunk + 1) {
             rowsum_fixup_kernel<2><<<grid, 256, 0, st>>>(g, out, a->carry_den, ostride);
             LAUNCH_CHECK(a);
         }
@@ -554,6 +556,7 @@ int gnnagg_destroy(gnnagg_aggregator *a)
     free_transpose(a);
     cudaFree(a->bwd_g);
     cudaFree(a->bwd_c);
+    cudaFree(a->bwd_t);
     cudaFree(a->d_item_row);
     cudaFree(a->carry);
     cudaFree(a->den_row);
@@ -920,37 +923,50 @@ int gnnagg_gat_backward(gnnagg_aggregator *a, const float *X, const float *att, 
     }
     if (int rc = ensure(a->newval, a->newval_cap, (size_t)a->m)) return rc;
     if (int rc = ensure(a->bwd_g, a->bwd_g_cap, (size_t)a->m)) return rc;
-    if (int rc = ensure(a->bwd_c, a->bwd_c_cap, (size_t)a->n)) return rc;
+    if (int rc = ensure(a->bwd_c, a->bwd_c_cap, (size_t)a->n * 2)) return rc;
+    if (int rc = ensure(a->bwd_t, a->bwd_t_cap, (size_t)a->m)) return rc;
     if (int rc = ensure(a->den_row, a->den_row_cap, (size_t)a->n)) return rc;
-    const EdgeParams g = edge_params(a);
-    const unsigned egrid = (unsigned)cdiv(a->m, 256);
-    // 1. un-normalised weights and their row sums (recomputed from the attention table unless handed in)
-    if (w) {
-        CUDA_TRY(cudaMemcpyAsync(a->newval, w, (size_t)a->m * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    } else {
-        edge_map_kernel<kEdgeWeight><<<egrid, 256, 0, st>>>(g, att, a->newval, slope);
-        LAUNCH_CHECK(a);
-    }
+    // 1. D_v = row sums of the un-normalised weights, computed on the fly from the attention table (or from w)
     const float *dn = den;
     if (!dn) {
-        if (int rc = rowsum_impl(a, a->newval, a->den_row, st)) return rc;
+        if (int rc = att ? rowsum_impl<kSumWeights>(a, att, a->den_row, st, 1, slope) : rowsum_impl(a, w, a->den_row, st))
+            return rc;
         dn = a->den_row;
     }
-    // 2. g_e = <X[u], dY[v]>: the SDDMM traversal;  c_v = <Y[v], dY[v]>
-    if (int rc = gnnagg_sddmm(a, X, dY, a->bwd_g, feat, 0, stream)) return rc;
-    rowdot_kernel<<<(unsigned)cdiv((int64_t)a->n * 8, 256), 256, 0, st>>>(Y, dY, a->bwd_c, a->n, feat);
+    // 2. per row: (1 / D_v, c_v = <Y[v], dY[v]>)
+    gat_bwd_rowinfo_kernel<<<(unsigned)cdiv((int64_t)a->n * 8, 256), 256, 0, st>>>(Y, dY, dn, reinterpret_cast<float2 *>(a->bwd_c),
+                                                                                 a->n, feat);
     LAUNCH_CHECK(a);
-    // 3. per edge: alpha_e (into newval) and ds_e (into bwd_g)
-    gat_bwd_edge_kernel<<<egrid, 256, 0, st>>>(g, w ? nullptr : att, dn, a->bwd_c, a->newval, a->bwd_g, slope);
-    LAUNCH_CHECK(a);
-    // 4. attention gradient: destination half = row sums of ds; source half = row sums over the transposed CSR
+    // 3. the SDDMM traversal g_e = <X[u], dY[v]> with the edge epilogue fused in: alpha_e -> newval, ds_e -> bwd_g
+    {
+        AggParams p{};
+        p.X = X;
+        p.P = dY;
+        p.att = att;
+        p.val = w;
+        p.bwd_c = reinterpret_cast<const float2 *>(a->bwd_c);
+        p.bwd_ds = a->bwd_g;
+        p.newval = a->newval;
+        p.F = feat;
+        p.slope = slope;
+        p.ptr = a->d_ptr;
+        p.idx = a->d_idx;
+        p.item_row = a->d_item_row;
+        p.num_rows = a->n;
+        p.num_edges = a->m;
+        p.num_fine_items = a->num_items;
+        p.bulk_ok = aligned16(p.idx) && (att || aligned16(w));
+        if (int rc = launch_agg<kModeGATBWD, false>(a, p, st)) return rc;
+    }
+    // 4. destination half of the attention gradient: row sums of ds
     if (int rc = rowsum_impl(a, a->bwd_g, datt, st, 2)) return rc;
-    if (int rc = to_transposed(a, a->newval, a->t_val, st)) return rc;  // alpha in transposed order
+    // 5. alpha and ds into the edge order of the transposed CSR (one pass over the permutation)
+    gather2_kernel<<<(unsigned)cdiv(a->m, 256), 256, 0, st>>>(a->newval, a->bwd_g, a->t_perm, a->t_val, a->bwd_t, a->m);
+    LAUNCH_CHECK(a);
     a->t_val_of = nullptr;
-    if (int rc = to_transposed(a, a->bwd_g, a->newval, st)) return rc;  // ds in transposed order (alpha no longer needed)
+    // 6. source half = row sums over the transposed CSR;  dX[u] = sum_e alpha_e dY[v] = the aggregation kernel over it
     const int64_t before = a->tr->launches;
-    int rc = rowsum_impl(a->tr, a->newval, datt + 1, st, 2);
-    // 5. dX[u] = sum_e alpha_e dY[v]: the aggregation kernel over the transposed CSR
+    int rc = rowsum_impl(a->tr, a->bwd_t, datt + 1, st, 2);
     if (rc == GNNAGG_OK) rc = gcn_run_core(a->tr, dY, dX, feat, 0, st);
     a->launches += a->tr->launches - before;
     return rc;

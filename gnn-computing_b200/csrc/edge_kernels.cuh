@@ -41,21 +41,38 @@ __global__ void __launch_bounds__(256) edge_map_kernel(const EdgeParams g, const
     }
 }
 
-// out[v] = sum of in[e] over the edges of row v (add_to_center, aggr_gat.h:50-74; the row-sum
-// half of attGat, :19-25).  One thread walks one kFineItem-edge item; rows crossing item
-// boundaries leave a partial in carry[item] that rowsum_fixup_kernel adds in item order.
-// Row v is written to out[v * ostride] (ostride = 2 fills one column of an [n,2] attention-gradient table).
-__global__ void __launch_bounds__(256) rowsum_kernel(const EdgeParams g, const float *__restrict__ in,
+// out[v] = sum over the edges e of row v of x_e (add_to_center, aggr_gat.h:50-74; the row-sum half of attGat,
+// :19-25).  One thread walks one kRowsumItem-edge item; rows crossing item boundaries leave a partial in
+// carry[item] that rowsum_fixup_kernel adds in item order.  Row v is written to out[v * ostride]
+// (ostride = 2 fills one column of an [n,2] attention-gradient table).  What x_e is:
+//   kSumArray   : in[e]
+//   kSumWeights : exp(lrelu(att[2v] + att[2 idx[e] + 1])), the GAT edge weight computed on the fly (no m-float temporary)
+enum { kSumArray = 0, kSumWeights = 1 };
+
+// edges per thread of the row-sum kernels: a quarter of the item_row granularity, so that a 1 M-edge graph still
+// gives every SM a few hundred threads (one thread per 128 edges left a 148-SM part at 36 CTAs)
+constexpr int kRowsumItem = 32;
+static_assert(kFineItem % kRowsumItem == 0, "row-sum items must nest inside item_row blocks");
+
+__device__ __forceinline__ int rowsum_start_row(const EdgeParams &g, int e0)
+{
+    if (e0 % kFineItem == 0) return (e0 == 0) ? 0 : __ldg(g.item_row + e0 / kFineItem);
+    return row_of_edge(g.ptr, g.item_row, g.num_items, g.num_rows, e0);
+}
+
+template <int SRC>
+__global__ void __launch_bounds__(256) rowsum_kernel(const EdgeParams g, const float *__restrict__ in, float slope,
                                                      float *__restrict__ out, float *__restrict__ carry, int ostride)
 {
     const int item = blockIdx.x * blockDim.x + threadIdx.x;
-    if (item >= g.num_items) return;
-    const int e0 = item * kFineItem;
-    const int e1 = min(g.num_edges, e0 + kFineItem);
-    int row = (item == 0) ? 0 : __ldg(g.item_row + item);
+    if ((int64_t)item * kRowsumItem >= g.num_edges) return;
+    const int e0 = item * kRowsumItem;
+    const int e1 = (int)min((int64_t)g.num_edges, (int64_t)e0 + kRowsumItem);
+    int row = rowsum_start_row(g, e0);
     int row_end = __ldg(g.ptr + row + 1);
     bool carry_in = __ldg(g.ptr + row) < e0;
     float acc = 0.f;
+    float a_dst = (SRC == kSumWeights) ? __ldg(in + 2 * (size_t)row) : 0.f;
     auto flush = [&]() {
         if (carry_in) {
             carry[item] = acc;
@@ -66,25 +83,41 @@ __global__ void __launch_bounds__(256) rowsum_kernel(const EdgeParams g, const f
         acc = 0.f;
         ++row;
         row_end = (row < g.num_rows) ? __ldg(g.ptr + row + 1) : INT_MAX;
+        if (SRC == kSumWeights && row < g.num_rows) a_dst = __ldg(in + 2 * (size_t)row);
     };
+    // the array streamed in edge order: values or source ids; 16-byte aligned at e0 when its base is
+    const void *stream = (SRC == kSumArray) ? (const void *)in : (const void *)g.idx;
+    const bool vec = ((reinterpret_cast<uintptr_t>(stream) & 15) == 0);
     int e = e0;
     while (row_end == e) flush();
-    const bool vec = ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
     while (e < e1) {
-        float v[4];
+        uint32_t raw[4];
         const int nb = min(4, e1 - e);
         if (vec && nb == 4) {
-            const float4 t = __ldg(reinterpret_cast<const float4 *>(in + e));
-            v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+            const uint4 t = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(stream) + e));
+            raw[0] = t.x, raw[1] = t.y, raw[2] = t.z, raw[3] = t.w;
         } else {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = (u < nb) ? __ldg(in + e + u) : 0.f;
+            for (int u = 0; u < 4; ++u) raw[u] = (u < nb) ? __ldg(reinterpret_cast<const uint32_t *>(stream) + e + u) : 0u;
+        }
+        float src_term[4];  // gathers issued together, ahead of the row walk
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (SRC == kSumWeights)
+                src_term[u] = (u < nb) ? __ldg(in + 2 * (size_t)raw[u] + 1) : 0.f;
+            else
+                src_term[u] = __uint_as_float(raw[u]);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             if (u < nb) {
                 while (row_end == e + u) flush();
-                acc += v[u];
+                if (SRC == kSumWeights) {
+                    const float sc = a_dst + src_term[u];
+                    acc += __expf(fmaxf(sc, sc * slope));  // aggr_gat.h:16-18
+                } else {
+                    acc += src_term[u];
+                }
             }
         }
         e += nb;
@@ -99,20 +132,20 @@ __global__ void __launch_bounds__(256) rowsum_kernel(const EdgeParams g, const f
 }
 
 // two-pass, fixed-order combination of the per-item partials (see agg_fixup_kernel)
-constexpr int kRowsumChunk = 64;
+constexpr int kRowsumChunk = 256;
 
 template <int PHASE>
 __global__ void __launch_bounds__(256) rowsum_fixup_kernel(const EdgeParams g, float *__restrict__ out,
                                                            float *__restrict__ carry, int ostride)
 {
     const int item = blockIdx.x * blockDim.x + threadIdx.x;
-    if (item < 1 || item >= g.num_items) return;
-    const int e0 = item * kFineItem;
-    const int row = __ldg(g.item_row + item);
+    if (item < 1 || (int64_t)item * kRowsumItem >= g.num_edges) return;
+    const int e0 = item * kRowsumItem;
+    const int row = rowsum_start_row(g, e0);
     const int rs = __ldg(g.ptr + row);
     if (rs >= e0) return;
-    const int first = rs / kFineItem + 1;
-    const int last = (__ldg(g.ptr + row + 1) - 1) / kFineItem;
+    const int first = rs / kRowsumItem + 1;
+    const int last = (__ldg(g.ptr + row + 1) - 1) / kRowsumItem;
     const bool long_span = (last - first) >= kRowsumChunk;
     int b0, b1, step;
     if (PHASE == 1) {
@@ -130,43 +163,36 @@ __global__ void __launch_bounds__(256) rowsum_fixup_kernel(const EdgeParams g, f
         carry[item] = acc;
 }
 
-// c[v] = <A[v,:], B[v,:]>: 8 lanes per row, float4 per lane (the <dY, Y> term of the GAT backward)
-__global__ void __launch_bounds__(256) rowdot_kernel(const float *__restrict__ A, const float *__restrict__ B,
-                                                     float *__restrict__ out, int num_rows, int F)
+// Per-row terms of the GAT backward, out[v] = (1 / D_v, c_v = <Y[v,:], dY[v,:]>): 8 lanes per row, float4 per lane
+// (the `res` of aggr_gat_fine_bwd, aggr_gat.h:275-283, and the division by `thediv`, :244).  Rows without edges get 0.
+__global__ void __launch_bounds__(256) gat_bwd_rowinfo_kernel(const float *__restrict__ Y, const float *__restrict__ dY,
+                                                              const float *__restrict__ den, float2 *__restrict__ out,
+                                                              int num_rows, int F)
 {
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     const int sub = threadIdx.x & 7;
     float acc = 0.f;
     if (row < num_rows)
-        for (int col = sub * 4; col < F; col += 32) acc += dot4(ldg_f4(A + (size_t)row * F + col), ldg_f4(B + (size_t)row * F + col));
+        for (int col = sub * 4; col < F; col += 32) acc += dot4(ldg_f4(Y + (size_t)row * F + col), ldg_f4(dY + (size_t)row * F + col));
     acc += __shfl_xor_sync(0xffffffffu, acc, 4);
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    if (row < num_rows && sub == 0) out[row] = acc;
+    if (row < num_rows && sub == 0) {
+        const float d = __ldg(den + row);
+        out[row] = make_float2(d != 0.f ? __fdividef(1.f, d) : 0.f, acc);
+    }
 }
 
-// Edge pass of the GAT backward (the part of aggr_gat_fine_bwd, aggr_gat.h:279-291, that is per edge):
-//   in : w[e] = exp(lrelu(s_e)) (un-normalised), den[v] = sum_e w, g[e] = <X[u], dY[v]>, c[v] = <Y[v], dY[v]>
-//   out: w[e] <- alpha_e = w_e / den[v];  g[e] <- ds_e = alpha_e (g_e - c_v) * lrelu'(s_e)
-// lrelu'(s) = s > 0 ? 1 : slope.  With the attention table the sign is read from s itself; without it
-// (att == NULL: the run_bwd signature only passes w) from w > 1, which is the same predicate because
-// w = exp(max(s, slope s)) and 0 <= slope < 1.
-__global__ void __launch_bounds__(256) gat_bwd_edge_kernel(const EdgeParams g, const float *__restrict__ att,
-                                                           const float *__restrict__ den, const float *__restrict__ c,
-                                                           float *__restrict__ w, float *__restrict__ gd, float slope)
+// out0[j] = in0[perm[j]], out1[j] = in1[perm[j]]: two edge arrays into another edge order with one read of perm
+__global__ void __launch_bounds__(256) gather2_kernel(const float *__restrict__ in0, const float *__restrict__ in1,
+                                                      const int *__restrict__ perm, float *__restrict__ out0,
+                                                      float *__restrict__ out1, int count)
 {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= g.num_edges) return;
-    const int v = row_of_edge(g.ptr, g.item_row, g.num_items, g.num_rows, e);
-    const float we = w[e];
-    const float alpha = we / __ldg(den + v);
-    bool pos;
-    if (att)
-        pos = (__ldg(att + 2 * (size_t)v) + __ldg(att + 2 * (size_t)__ldg(g.idx + e) + 1)) > 0.f;
-    else
-        pos = we > 1.f;
-    w[e] = alpha;
-    gd[e] = alpha * (gd[e] - __ldg(c + v)) * (pos ? 1.f : slope);
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    const int e = __ldg(perm + j);
+    out0[j] = __ldg(in0 + e);
+    out1[j] = __ldg(in1 + e);
 }
 
 // edge-wise GCN aggregation: Y[dst] += X[src]*val[e], one virtual warp per edge and 128-bit

@@ -177,3 +177,88 @@ def test_gat_backward_vs_reference_kernel(gn, orc, cuda):
     if worst_a <= 4.0:
         assert rel_gate(dA.cpu().numpy()[:, 1], d_ab.cpu().numpy()[:, 1], sa[:, 1], TOL_A * 5)[0] == 0
     assert (d_ab.cpu().numpy()[:, 0] == 0).all()  # the destination half is never written there (:290)
+
+
+import os
+
+
+@pytest.mark.skipif(os.environ.get("GNNAGG_HEAVY") != "1", reason="full-size timing run: set GNNAGG_HEAVY=1")
+@pytest.mark.parametrize("shape,F", [("arxiv", 32), ("reddit", 32), ("reddit", 128), ("proteins", 64)])
+def test_backward_timing_full_size(gn, orc, cuda, shape, F):
+    """backward at the BASELINE.json shapes, timed beside the forward and (F = 32) beside the reference's
+    aggr_gat_fine_bwd; one JSON line per case into gpurun_out/backward.jsonl"""
+    import json
+    import time
+
+    n, m = synth.shape_of(shape)
+    ptr, idx = synth.rmat_csr(n, m, seed=123, device=cuda)
+    val = synth.gcn_norm_val(ptr, idx)
+    g = torch.Generator(device=cuda).manual_seed(123)
+    X = torch.randn((n, F), device=cuda, generator=g)
+    dY = torch.randn((n, F), device=cuda, generator=g)
+    att = torch.rand((n, 2), device=cuda, generator=g) * 0.9 + 0.05  # positive: the regime where the reference kernel is right
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=cuda)
+
+    def timeit(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+
+    agg = gn.Aggregator(ptr, idx, val)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    agg.transpose_build()
+    torch.cuda.synchronize()
+    out = {"shape": shape, "n": n, "m": m, "F": F, "transpose_build_s": time.time() - t0}
+    Y, dX, dA = torch.empty((n, F), device=cuda), torch.empty((n, F), device=cuda), torch.empty((n, 2), device=cuda)
+    out["gcn_forward_ms"] = timeit(lambda: agg.gcn_run(X, Y))
+    out["gcn_backward_ms"] = timeit(lambda: agg.gcn_backward(dY, dX))
+    out["gat_forward_ms"] = timeit(lambda: agg.gat_run(X, att, Y))
+    out["gat_backward_ms"] = timeit(lambda: agg.gat_backward(X, att, Y, dY, dX, dA))
+    # every entry point is free of host synchronisation and (after the first call) of allocation, so a caller can
+    # capture it in a CUDA graph: what that buys on the launch-bound small graph
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        agg.gat_backward(X, att, Y, dY, dX, dA)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            agg.gat_backward(X, att, Y, dY, dX, dA)
+    torch.cuda.synchronize()
+    ref_dX, ref_dA = dX.clone(), dA.clone()
+    dX.zero_(), dA.zero_()
+    out["gat_backward_graph_ms"] = timeit(graph.replay)
+    assert torch.equal(dX, ref_dX) and torch.equal(dA, ref_dA)
+    # size-independent parity property: <A X, dY> == <X, A^T dY>
+    Yg = agg.gcn_run(X, torch.empty((n, F), device=cuda))
+    dXg = agg.gcn_backward(dY, torch.empty((n, F), device=cuda))
+    lhs, rhs = float((Yg.double() * dY.double()).sum()), float((X.double() * dXg.double()).sum())
+    mag = float((Yg.double().abs() * dY.double().abs()).sum())
+    out["adjoint_rel_err"] = abs(lhs - rhs) / mag
+    assert out["adjoint_rel_err"] <= 1e-6
+    if F == 32 and orc.ref_available():
+        ref = orc.ref()
+        P = lambda t: C.c_void_p(t.data_ptr())
+        ref.ref_set_globals(n, m)
+        h = C.c_void_p(ref.ref_gat_create(P(ptr), P(idx), n, m, F))
+        ref.ref_gat_schedule(h, 1, 32, 0)
+        w = torch.empty(m, device=cuda)
+        agg.edge_softmax(att, w)           # alpha with div = 1 is an equally valid (newval, div) pair
+        ones = torch.ones(n, device=cuda)
+        d_ab, d_feat = torch.zeros((n, 2), device=cuda), torch.zeros((n, F), device=cuda)
+        Yf = agg.gat_run(X, att, torch.empty((n, F), device=cuda))
+        out["ref_aggr_gat_fine_bwd_ms"] = timeit(
+            lambda: ref.ref_gat_run_bwd(h, P(Yf), P(dY), P(w), P(ones), P(X), P(d_ab), P(d_feat), C.c_float(0.2), 128), reps=3)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(root, "gpurun_out", "backward.jsonl"), "a") as f:
+        f.write(json.dumps(out) + "\n")
+    print(json.dumps(out))
