@@ -972,6 +972,23 @@ int gnnagg_gat_backward(gnnagg_aggregator *a, const float *X, const float *att, 
     return rc;
 }
 
+int gnnagg_sample_subgraph(gnnagg_aggregator *a, int *d_active, int fanout, int layer_num, uint64_t seed, int **d_vertexset,
+                           int **d_sub_ptr, int **d_sub_idx, int *num_v, int *num_e, void *stream)
+{
+    if (!a || (!d_active && a->n > 0) || !d_vertexset || !d_sub_ptr || !d_sub_idx || !num_v || !num_e || layer_num < 1)
+        return set_error(GNNAGG_ERR_ARG, "gnnagg_sample_subgraph: bad argument");
+    const int rc = sample_subgraph_device(a->d_ptr, a->d_idx, a->d_item_row, a->num_items, a->n, a->m, d_active, fanout,
+                                          layer_num, seed, d_vertexset, d_sub_ptr, d_sub_idx, num_v, num_e, (cudaStream_t)stream);
+    if (rc == GNNAGG_OK) a->launches += 5 + 2 * (layer_num - 1);
+    return rc;
+}
+
+int gnnagg_device_free(void *d_ptr)
+{
+    CUDA_TRY(cudaFree(d_ptr));
+    return GNNAGG_OK;
+}
+
 int gnnagg_gather_rows(const float *X, const int64_t *rows, float *out, int64_t count, int feat, void *stream)
 {
     if (count == 0) return GNNAGG_OK;

@@ -30,6 +30,11 @@ int schedule_build_device(int kind, const int *d_ptr, const int *d_idx, const in
 int transpose_build_device(const int *d_ptr, const int *d_idx, const int *d_item_row, int num_items, int n, int m,
                            int num_src, int **t_ptr, int **t_idx, int **t_perm, cudaStream_t st);
 
+// sub-graph samplers of include/sample.h (sample_device.cu); outputs are cudaMalloc'ed
+int sample_subgraph_device(const int *d_ptr, const int *d_idx, const int *d_item_row, int num_items, int n, int m,
+                           int *d_active, int fanout, int layer_num, uint64_t seed, int **vertexset, int **sub_ptr,
+                           int **sub_idx, int *num_v, int *num_e, cudaStream_t st);
+
 // dense combination on tcgen05 (dense_tc.cu); stream is a cudaStream_t
 int dense_nn_launch(const float *A, const float *B, float *C, int64_t M, int N, int K, void *stream);
 

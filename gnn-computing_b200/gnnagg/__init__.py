@@ -81,6 +81,9 @@ _SIGS = {
     "gnnagg_transpose_dev": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)] + [C.POINTER(C.c_void_p)] * 3),
     "gnnagg_gcn_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "gnnagg_gat_backward": (C.c_int, [C.c_void_p] * 9 + [C.c_int, C.c_float, C.c_void_p]),
+    "gnnagg_sample_subgraph": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64] + [C.POINTER(C.c_void_p)] * 3 +
+                               [C.POINTER(C.c_int)] * 2 + [C.c_void_p]),
+    "gnnagg_device_free": (C.c_int, [C.c_void_p]),
     "gnnagg_gather_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "gnnagg_spmm_naive": (C.c_int, [C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p]),
     "gnnagg_validate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int), C.c_void_p]),
@@ -385,6 +388,28 @@ class Aggregator:
         check(lib().gnnagg_gat_backward(self.h, _dp(X), _dp(att), _dp(w), _dp(den), _dp(Y), _dp(dY), _dp(dX), _dp(datt),
                                         X.shape[1], slope, _stream()))
         return dX, datt
+
+    # --- sub-graph samplers (sample.h)
+    def sample_subgraph(self, active, fanout=0, layer_num=1, seed=123):
+        """active: int32 CUDA tensor [n] of seed flags, updated in place to the expanded set.  Returns
+        (vertexset, sub_ptr, sub_idx) as int32 CUDA tensors (copies; the library's arrays are released)."""
+        import torch
+
+        L = lib()
+        vs, sp, si = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nv, ne = C.c_int(), C.c_int()
+        check(L.gnnagg_sample_subgraph(self.h, _dp(active), int(fanout), int(layer_num), C.c_uint64(seed), C.byref(vs),
+                                       C.byref(sp), C.byref(si), C.byref(nv), C.byref(ne), _stream()))
+        out = []
+        for p_, count in ((vs, nv.value), (sp, nv.value + 1), (si, ne.value)):
+            t = torch.empty(count, dtype=torch.int32, device=active.device)
+            if count:
+                h = np.empty(count, np.int32)
+                check(L.gnnagg_memcpy_d2h(h.ctypes.data, p_, count * 4))
+                t.copy_(torch.from_numpy(h))
+            check(L.gnnagg_device_free(p_))
+            out.append(t)
+        return tuple(out)
 
     # --- host-buffer entry points (pinned CPU tensors or numpy arrays)
     def gcn_run_host(self, hX, hY, scheduled=False):

@@ -226,6 +226,23 @@ int gnnagg_gcn_backward(gnnagg_aggregator *a, const float *dY, float *dX, int fe
 int gnnagg_gat_backward(gnnagg_aggregator *a, const float *X, const float *att, const float *w, const float *den,
                         const float *Y, const float *dY, float *dX, float *datt, int feat, float slope, void *stream);
 
+/* ---- sub-graph samplers -------------------------------------------------------------
+ * replaces sampleVertex (include/sample.h:131-200) and sampleVertexSampleNeighbor (:274-357).
+ * d_active [num_v]: non-zero marks the seed vertices; on return it holds the 0/1 set after layer_num - 1 hops
+ * (the reference updates its `int *&active_vertex` the same way).  The rows of the active vertices are extracted in
+ * ascending vertex order: *d_vertexset [*num_v] their ids, *d_sub_ptr [*num_v + 1], *d_sub_idx [*num_e] GLOBAL source
+ * ids -- the three arrays of a CSRSubGraph (util.h:15-36), cudaMalloc'ed here and owned by the caller
+ * (gnnagg_device_free, or hand them to an aggregator shim that frees them as the reference's does).
+ *   fanout <= 0 : complete neighbour lists; bit-identical to sampleVertex.
+ *   fanout  > 0 : rows longer than fanout keep exactly fanout neighbours, the j-th drawn uniformly from the j-th of
+ *                 fanout equal strata of the row as a pure function of (seed, vertex, j) -- CSR order kept, inclusion
+ *                 probability fanout/deg, reproducible on CPU and GPU.  This RE-SPECIFIES sampleVertexSampleNeighbor,
+ *                 whose mark test is inverted / matches nothing for rows longer than the limit (sample.h:97-104 vs
+ *                 :229-246) and which no driver calls; see gnn-computing_b200/csrc/sample_device.cu. */
+int gnnagg_sample_subgraph(gnnagg_aggregator *a, int *d_active, int fanout, int layer_num, uint64_t seed, int **d_vertexset,
+                           int **d_sub_ptr, int **d_sub_idx, int *num_v, int *num_e, void *stream);
+int gnnagg_device_free(void *d_ptr);
+
 /* naive reference-style SpMM + validators of include/spmm.h:
  *   gnnagg_spmm_naive        replaces spmm<LENFEATURE> (spmm.h:223-265; thread per row; rows
  *                            with no edge are left untouched as there, :236-237)

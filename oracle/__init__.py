@@ -178,6 +178,23 @@ def sddmm_f64(ptr, idx, X1, X2):
     return out, S
 
 
+# ------------------------------------------------------------------ samplers
+def sample_subgraph(ptr, idx, active, fanout=0, layer_num=1, seed=123):
+    """(active_after, vertexset, sub_ptr, sub_idx); fanout <= 0 restates sampleVertex (sample.h:131-200)"""
+    n = len(ptr) - 1
+    act = np.ascontiguousarray(active, np.int32).copy()
+    vs, sp, si = np.empty(max(n, 1), np.int32), np.empty(n + 1, np.int32), np.empty(max(len(idx), 1), np.int32)
+    ne = C.c_int()
+    rows = lib().orc_sample_subgraph(C.c_int(n), _vp(ptr), _vp(idx), _vp(act), C.c_int(fanout), C.c_int(layer_num),
+                                     C.c_uint64(seed), _vp(vs), _vp(sp), _vp(si), C.c_int64(len(si)), C.byref(ne))
+    assert rows >= 0
+    return act, vs[:rows].copy(), sp[: rows + 1].copy(), si[: ne.value].copy()
+
+
+def sample_pos(seed, v, j, deg, fanout):
+    return lib().orc_sample_pos(C.c_uint64(seed), C.c_int(v), C.c_int(j), C.c_int(deg), C.c_int(fanout))
+
+
 # ------------------------------------------------------------------ backward (SURVEY §8(f) rank 3)
 def transpose_csr(ptr, idx, num_src):
     m = len(idx)

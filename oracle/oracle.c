@@ -675,3 +675,67 @@ double orc_gat_loss_f64(int64_t n, const int *ptr, const int *idx, const double 
     free(y);
     return L;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Sub-graph samplers (include/sample.h).  orc_sample_subgraph with fanout <= 0 restates sampleVertex
+ * (:131-200): expandActive hops (:109-124) then rows of the active vertices in ascending order with
+ * complete neighbour lists.  With fanout > 0 it is the SPECIFICATION of the product's fixed-fanout
+ * sampler (gnn-computing_b200/csrc/sample_device.cu explains why sampleVertexSampleNeighbor,
+ * :274-357, is not reproduced): parity unpinned against the reference for that mode.
+ * ------------------------------------------------------------------------------------------ */
+static uint64_t orc_splitmix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+int orc_sample_pos(uint64_t seed, int v, int j, int deg, int fanout)
+{
+    const int lo = (int)(((int64_t)j * deg) / fanout);
+    const int hi = (int)(((int64_t)(j + 1) * deg) / fanout);
+    const uint64_t r = orc_splitmix64(seed ^ ((uint64_t)(uint32_t)v * 0x9E3779B97F4A7C15ull) ^
+                                      ((uint64_t)(uint32_t)j * 0xD1B54A32D192ED03ull));
+    return lo + (int)(r % (uint64_t)(hi - lo));
+}
+
+/* active [n] in/out (0/1 after the call); vertexset [n], sub_ptr [n+1], sub_idx [cap] caller-allocated
+ * (cap >= the number of extracted edges; m always suffices).  Returns the number of extracted rows,
+ * *num_e the number of extracted edges, or -1 when sub_idx is too small. */
+int orc_sample_subgraph(int n, const int *ptr, const int *idx, int *active, int fanout, int layer_num, uint64_t seed,
+                        int *vertexset, int *sub_ptr, int *sub_idx, int64_t cap, int *num_e)
+{
+    int *next = (int *)malloc(((size_t)n + 1) * sizeof(int));
+    for (int v = 0; v < n; ++v) active[v] = active[v] != 0;
+    for (int hop = 0; hop < layer_num - 1; ++hop) {
+        memcpy(next, active, (size_t)n * sizeof(int));
+        for (int v = 0; v < n; ++v) {
+            if (!active[v]) continue;
+            const int deg = ptr[v + 1] - ptr[v];
+            if (fanout <= 0 || deg <= fanout)
+                for (int e = ptr[v]; e < ptr[v + 1]; ++e) next[idx[e]] = 1;
+            else
+                for (int j = 0; j < fanout; ++j) next[idx[ptr[v] + orc_sample_pos(seed, v, j, deg, fanout)]] = 1;
+        }
+        memcpy(active, next, (size_t)n * sizeof(int));
+    }
+    free(next);
+    int rows = 0;
+    int64_t edges = 0;
+    sub_ptr[0] = 0;
+    for (int v = 0; v < n; ++v) {
+        if (!active[v]) continue;
+        const int deg = ptr[v + 1] - ptr[v];
+        const int take = (fanout > 0 && deg > fanout) ? fanout : deg;
+        if (edges + take > cap) return -1;
+        for (int j = 0; j < take; ++j)
+            sub_idx[edges + j] = idx[ptr[v] + ((take == deg) ? j : orc_sample_pos(seed, v, j, deg, fanout))];
+        edges += take;
+        vertexset[rows] = v;
+        sub_ptr[++rows] = (int)edges;
+    }
+    *num_e = (int)edges;
+    return rows;
+}

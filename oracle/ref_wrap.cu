@@ -17,6 +17,7 @@
 #include "aggr_sddmm.h"
 #include "aggr_nn.h"
 #include "dense.h"
+#include "sample.h"
 
 #include <cstring>
 // defined in src/data.cu:4 but not declared by include/data.h (its prototype there has 4 parameters)
@@ -177,6 +178,18 @@ void ref_gat_run_bwd(void *h, float *output, float *doutput, float *newval, floa
                      float *d_feat, float relu_l, int block)
 {
     ((Aggregator_GAT *)h)->run_bwd(output, doutput, newval, div, infeat, d_a_b, d_feat, relu_l, block);
+}
+
+// sampleVertex (sample.h:131-200) on device arrays; outputs are the reference's own cudaMalloc2'ed arrays
+int ref_sample_vertex(int *d_active, int *d_ptr, int *d_idx, int layer_num, int **vertexset, int **sub_ptr, int **sub_idx,
+                      int *num_e)
+{
+    CSRSubGraph g = sampleVertex(d_active, d_ptr, d_idx, layer_num);
+    *vertexset = g.vertexset;
+    *sub_ptr = g.ptr;
+    *sub_idx = g.idx;
+    *num_e = g.num_e;
+    return g.num_v;
 }
 
 void *ref_sddmm_create(int *d_ptr, int *d_idx, int num_v, int num_e, int feat)

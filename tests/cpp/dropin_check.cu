@@ -160,6 +160,29 @@ int main(int argc, char **argv)
         dbg(t_mlp);
     }
 
+    // ---- samplers (sample.h:131-200, :274-357): with every vertex active the sub-graph is the graph itself, and the
+    // aggregator built from the CSRSubGraph reproduces the full result; a fan-out of 4 keeps min(deg, 4) edges per row
+    {
+        std::vector<int> all(n, 1), h_ptr(n + 1), h_sub(n + 1);
+        int *active = NULL;
+        checkCudaErrors(cudaMalloc2((void **)&active, n * sizeof(int)));
+        checkCudaErrors(cudaMemcpy(active, all.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+        CSRSubGraph sg = sampleVertex(active, gptrs[0], gidxs[0], 2);
+        expect("sampleVertex(all active): rows and edges kept", (sg.num_v != n) + (sg.num_e != m));
+        Aggregator_GCN *atsub = new Aggregator_GCN(sg, F, OUT, val);
+        atsub->run(x, y2, 128, 0);
+        checkCudaErrors(cudaDeviceSynchronize());
+        expect("aggr_gcn over the sampled CSRSubGraph vs spmm<>", valid(y_naive, y2, n * F));
+        CSRSubGraph sf = sampleVertexSampleNeighbor(active, gptrs[0], gidxs[0], 4, 1);
+        checkCudaErrors(cudaMemcpy(h_ptr.data(), gptrs[0], (n + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+        checkCudaErrors(cudaMemcpy(h_sub.data(), sf.ptr, (n + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+        int bad = (sf.num_v != n);
+        for (int v = 0; v < n && !bad; ++v) bad += (h_sub[v + 1] - h_sub[v]) != std::min(h_ptr[v + 1] - h_ptr[v], 4);
+        expect("sampleVertexSampleNeighbor(4): min(deg, 4) neighbours per row", bad);
+        sf.free();
+        cudaFree(active);
+    }
+
     if (failures) {
         std::cerr << "DROPIN_CHECK FAILED (" << failures << " comparisons)\n";
         return 1;
