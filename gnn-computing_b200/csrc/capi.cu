@@ -651,6 +651,7 @@ int gnnagg_set_warp_edges(gnnagg_aggregator *a, int warp_edges)
     if (!a || (warp_edges != 0 && warp_edges != 128 && warp_edges != 512))
         return set_error(GNNAGG_ERR_ARG, "gnnagg_set_warp_edges: 0, 128 or 512");
     a->warp_edges = warp_edges;
+    if (a->tr) a->tr->warp_edges = warp_edges;
     return GNNAGG_OK;
 }
 
@@ -872,8 +873,13 @@ int gnnagg_transpose_build(gnnagg_aggregator *a, int num_src, void *stream)
     a->tr->n = num_src;
     a->tr->m = a->m;
     a->tr->warp_edges = a->warp_edges;
-    if (int rc = build_item_rows(a->tr, a->t_ptr, num_src, a->m, &a->tr->d_item_row, &a->tr->num_items, st)) return rc;
-    CUDA_TRY(cudaMalloc((void **)&a->t_val, (size_t)(a->m ? a->m : 1) * sizeof(float)));
+    int rc = build_item_rows(a->tr, a->t_ptr, num_src, a->m, &a->tr->d_item_row, &a->tr->num_items, st);
+    if (rc == GNNAGG_OK && cudaMalloc((void **)&a->t_val, (size_t)(a->m ? a->m : 1) * sizeof(float)) != cudaSuccess)
+        rc = set_error(GNNAGG_ERR_CUDA, "gnnagg_transpose_build: out of device memory");
+    if (rc != GNNAGG_OK) {
+        free_transpose(a);  // never leave a half-built transpose behind
+        return rc;
+    }
     a->tr->d_val = a->t_val;
     a->launches += 5;  // iota, radix sort (counted once), rows, pointers, item table
     return GNNAGG_OK;

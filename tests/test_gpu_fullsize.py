@@ -109,3 +109,72 @@ def test_full_size_gat_properties(gn, orc, cuda):
     agg.schedule(1, [32])
     Ys = agg.gat_run(X, att, torch.empty((n, F), device=cuda), scheduled=True)
     assert bool(((Ys - Y).abs() <= 3e-5 * absY + 1e-30).all())
+
+
+@pytest.mark.parametrize("shape,F", [("reddit", 128), ("proteins", 64)])
+def test_full_size_backward_properties(gn, orc, cuda, shape, F):
+    """backward at full size: transposed CSR is a permutation sorted by source, <AX,dY> == <X,A^T dY>, the GAT
+    backward is deterministic, its attention halves carry the same total, sum_u dX[u] == sum over non-empty rows of
+    dY (softmax weights of a row add up to 1), and sampled source rows agree with the fp64 oracle of the sub-problem"""
+    n, m = synth.shape_of(shape)
+    ptr, idx = synth.rmat_csr(n, m, seed=123, device=cuda)
+    val = synth.gcn_norm_val(ptr, idx)
+    g = torch.Generator(device=cuda).manual_seed(7)
+    X = torch.randn((n, F), device=cuda, generator=g)
+    dY = torch.randn((n, F), device=cuda, generator=g)
+    att = torch.randn((n, 2), device=cuda, generator=g)
+    agg = gn.Aggregator(ptr, idx, val)
+    agg.transpose_build()
+    t_ptr, t_idx, t_perm = (torch.from_numpy(a).to(cuda) for a in agg.transposed_arrays())
+    assert int(t_ptr[-1]) == m and bool((t_ptr[1:] >= t_ptr[:-1]).all())
+    src_sorted = idx[t_perm.long()]
+    assert bool((src_sorted[1:] >= src_sorted[:-1]).all())                      # grouped by source
+    same = src_sorted[1:] == src_sorted[:-1]
+    assert bool((t_perm[1:][same] > t_perm[:-1][same]).all())                   # stable inside a source
+    assert torch.equal(torch.sort(t_perm)[0], torch.arange(m, device=cuda, dtype=torch.int32))
+    assert torch.equal(torch.bincount(idx.long(), minlength=n).cumsum(0).to(torch.int32), t_ptr[1:])
+
+    Y = agg.gcn_run(X, torch.empty((n, F), device=cuda))
+    dX = agg.gcn_backward(dY, torch.empty((n, F), device=cuda))
+    lhs, rhs = float((Y.double() * dY.double()).sum()), float((X.double() * dX.double()).sum())
+    mag = float((Y.double().abs() * dY.double().abs()).sum())
+    assert abs(lhs - rhs) <= 1e-6 * mag
+
+    Yg = agg.gat_run(X, att, torch.empty((n, F), device=cuda))
+    dXg, dA = agg.gat_backward(X, att, Yg, dY, torch.empty((n, F), device=cuda), torch.empty((n, 2), device=cuda))
+    dXg2, dA2 = agg.gat_backward(X, att, Yg, dY, torch.empty((n, F), device=cuda), torch.empty((n, 2), device=cuda))
+    assert torch.equal(dXg, dXg2) and torch.equal(dA, dA2)
+    assert bool(torch.isfinite(dXg).all()) and bool(torch.isfinite(dA).all())
+    nonempty = (ptr[1:] > ptr[:-1])
+    col_l, col_r = dXg.double().sum(0), dY[nonempty].double().sum(0)
+    col_mag = dY[nonempty].double().abs().sum(0)
+    assert bool(((col_l - col_r).abs() <= 1e-5 * col_mag).all())
+    tot_dst, tot_src = float(dA[:, 0].double().sum()), float(dA[:, 1].double().sum())
+    assert abs(tot_dst - tot_src) <= 1e-5 * float(dA.double().abs().sum())
+    # oracle on the sub-problem of the first rows: destination halves of those rows depend on nothing else
+    rows = 1500
+    hp = np.ascontiguousarray(ptr[: rows + 1].cpu().numpy())
+    e = int(hp[-1])
+    _, a64, _, sa = orc.gat_backward_f64(hp, idx[:e].cpu().numpy(), att.cpu().numpy(), X.cpu().numpy(), dY[:rows].cpu().numpy())
+    assert rel_gate(dA[:rows, 0].cpu().numpy(), a64[:rows, 0], sa[:rows, 0], 2.5e-5)[0] == 0
+
+
+def test_full_size_sampler_properties(gn, orc, cuda):
+    """samplers on the reddit-shaped graph: all vertices active -> the graph itself; fixed fan-out -> min(deg, k)
+    neighbours per row, each an element of the original row; sampled rows agree with the oracle"""
+    n, m = synth.shape_of("reddit")
+    ptr, idx = synth.rmat_csr(n, m, seed=123, device=cuda)
+    agg = gn.Aggregator(ptr, idx)
+    vs, sp, si = agg.sample_subgraph(torch.ones(n, dtype=torch.int32, device=cuda), 0, 2)
+    assert torch.equal(vs, torch.arange(n, device=cuda, dtype=torch.int32)) and torch.equal(sp, ptr) and torch.equal(si, idx)
+    k = 16
+    active = torch.zeros(n, dtype=torch.int32, device=cuda)
+    active[::97] = 1
+    seeds = active.clone()
+    vs, sp, si = agg.sample_subgraph(active, k, 2, seed=5)
+    deg = (ptr[1:] - ptr[:-1])[vs.long()]
+    assert torch.equal(sp[1:] - sp[:-1], torch.clamp(deg, max=k))
+    assert bool((active[seeds.bool()] == 1).all()) and int(active.sum()) == vs.numel()
+    o_act, o_vs, o_sp, o_si = orc.sample_subgraph(ptr.cpu().numpy(), idx.cpu().numpy(), seeds.cpu().numpy(), k, 2, seed=5)
+    assert np.array_equal(vs.cpu().numpy(), o_vs) and np.array_equal(sp.cpu().numpy(), o_sp)
+    assert np.array_equal(si.cpu().numpy(), o_si) and np.array_equal(active.cpu().numpy(), o_act)
