@@ -403,11 +403,13 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     agg_ms = float(np.mean([p["agg"] for p in prof]))
-    traffic = None
+    traffic, ncu_units = None, {}
     try:  # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this workload
         summ = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
         key = args.workload + ("_sched" if args.scheduled else "") + ("_uniform" if args.sources == "uniform" else "")
         traffic = summ.get(key, {}).get("dram_bytes_per_launch")
+        ncu_units = {k: summ[key][k] for k in ("l1tex_throughput_pct", "lts_throughput_pct", "dram_GBps", "l2_hit_pct",
+                                               "l1_hit_pct", "duration_ms", "source") if k in summ.get(key, {})}
     except Exception:
         pass
     achieved = spmm_bytes(n, m, fin) / (agg_ms * 1e-3) / 1e9
@@ -416,6 +418,9 @@ def main():
                     lpr, nv, "sched" if args.scheduled else "csr", 128 if m < 4000000 else 512),
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": traffic, "peak_source": peak_src,
+                # which unit binds, from the committed `ncu --set full` capture of this kernel on this workload (percent of
+                # the unit's peak throughput; DRAM in GB/s): the gathers run out of L1/L2, so HBM is not the binding unit here
+                "ncu": ncu_units,
                 "algorithmic_bytes_per_launch": spmm_bytes(n, m, fin), "kernel_ms": round(agg_ms, 4),
                 "step_breakdown_ms": {k: round(float(np.mean([p[k] for p in prof])), 4) for k in ("agg", "agg_rest", "dense", "total")},
                 "note": "gather model: one F-float source row per edge; X (%.0f MB) is L2-resident to a large degree, so this is an "

@@ -17,6 +17,8 @@
 //     the stage; the epilogue reads TMEM with tcgen05.ld (32 lanes x 32 bit x 16 columns) and
 //     stores rows straight to global memory.
 #include <cuda_runtime.h>
+
+#include <mutex>
 #include <stdint.h>
 
 #include <cstdio>
@@ -365,6 +367,31 @@ dense_tf32x3_stream_kernel(const float *__restrict__ A, const float *__restrict_
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)tmem_cols) : "memory");
 }
 
+// Stream-ordered pool for the W split of the streamed kernel.  The device's default pool hands freed memory back to
+// the driver at every synchronisation (release threshold 0), which made each call re-map its 2*K*N floats; a private
+// pool that keeps what it has turns the allocation into a pointer bump.  One pool per device, created on first use.
+static cudaMemPool_t split_pool(int dev)
+{
+    static std::mutex lock;
+    static cudaMemPool_t pools[64] = {};
+    if (dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> guard(lock);
+    if (!pools[dev]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        if (cudaMemPoolCreate(&pools[dev], &props) != cudaSuccess) {
+            pools[dev] = nullptr;
+            return nullptr;
+        }
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    return pools[dev];
+}
+
 int dense_nn_launch(const float *A, const float *B, float *C, int64_t M, int N, int K, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
@@ -380,7 +407,8 @@ int dense_nn_launch(const float *A, const float *B, float *C, int64_t M, int N, 
     if (N * K > kMaxNK) {
         // W's split does not fit in shared memory next to the A ring: stream it (see dense_tf32x3_stream_kernel)
         float *wsplit = nullptr;
-        if (cudaMallocAsync((void **)&wsplit, (size_t)2 * K * N * sizeof(float), st) != cudaSuccess)
+        cudaMemPool_t pool = split_pool(dev);
+        if (!pool || cudaMallocFromPoolAsync((void **)&wsplit, (size_t)2 * K * N * sizeof(float), pool, st) != cudaSuccess)
             return set_error(GNNAGG_ERR_CUDA, "dense combination: cannot allocate the W split");
         float *whi = wsplit, *wlo = wsplit + (size_t)K * N;
         split_w_kernel<<<(K * N + 255) / 256, 256, 0, st>>>(B, whi, wlo, K, N);
