@@ -100,6 +100,18 @@ struct gnnagg_aggregator {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t copies_done = nullptr;
+    // host-buffer entry points, large graphs: the CSR split by source-id ranges so that slice c can be aggregated while
+    // the rows of X that slice c+1 gathers are still on their way from the host (source_slices_build_device)
+    int host_slices = 0;  // 0 = automatic, > 0 forced slice count, < 0 row-chunk pipeline only (gnnagg_set_host_pipeline)
+    int num_slices = 0, slice_width = 0;
+    gnnagg_aggregator *slice[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int *sl_ptr = nullptr, *sl_idx = nullptr, *sl_perm = nullptr;
+    float *sl_val = nullptr;
+    const float *sl_val_of = nullptr;
+    int sl_off[8] = {0}, sl_cnt[8] = {0};
+    cudaStream_t in_stream = nullptr;
+    cudaEvent_t in_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t in_free = nullptr;
     // optional per-kernel timing (gnnagg_profile_enable)
     bool prof = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // begin, agg0, agg1, agg_end, end
@@ -480,6 +492,22 @@ static int rowsum_impl(gnnagg_aggregator *a, const float *in, float *out, cudaSt
     return GNNAGG_OK;
 }
 
+static void free_slices(gnnagg_aggregator *a)
+{
+    for (int c = 0; c < 8; ++c) {
+        if (!a->slice[c]) continue;
+        cudaFree(a->slice[c]->d_item_row);
+        cudaFree(a->slice[c]->carry);
+        delete a->slice[c];
+        a->slice[c] = nullptr;
+    }
+    cudaFree(a->sl_ptr), cudaFree(a->sl_idx), cudaFree(a->sl_perm), cudaFree(a->sl_val);
+    a->sl_ptr = a->sl_idx = a->sl_perm = nullptr;
+    a->sl_val = nullptr;
+    a->sl_val_of = nullptr;
+    a->num_slices = 0;
+}
+
 static void free_transpose(gnnagg_aggregator *a)
 {
     if (a->tr) {
@@ -554,6 +582,11 @@ int gnnagg_destroy(gnnagg_aggregator *a)
     if (!a) return GNNAGG_OK;
     free_schedule(a);
     free_transpose(a);
+    free_slices(a);
+    for (int i = 0; i < 8; ++i)
+        if (a->in_done[i]) cudaEventDestroy(a->in_done[i]);
+    if (a->in_free) cudaEventDestroy(a->in_free);
+    if (a->in_stream) cudaStreamDestroy(a->in_stream);
     cudaFree(a->bwd_g);
     cudaFree(a->bwd_c);
     cudaFree(a->bwd_t);
@@ -582,6 +615,7 @@ int gnnagg_set_val(gnnagg_aggregator *a, const float *d_val)
     if (!a) return set_error(GNNAGG_ERR_ARG, "gnnagg_set_val: NULL aggregator");
     a->d_val = d_val;
     a->t_val_of = nullptr;  // same pointer, possibly new contents (aggr_gcn.h:540-544): re-mirror on the next backward
+    a->sl_val_of = nullptr;
     if (a->sched_kind == GNNAGG_SCHED_NOP) return GNNAGG_OK;
     if (a->s_perm) {  // locality kinds keep a permuted copy (aggr_gcn.h:522-537)
         if (!a->s_val) CUDA_TRY(cudaMalloc((void **)&a->s_val, (size_t)(a->sched_edges ? a->sched_edges : 1) * sizeof(float)));
@@ -1053,11 +1087,70 @@ int gnnagg_validate_reordered(const float *d_ref, const float *d_ans, const int 
 }
 
 // ------------------------------------------------------------------ host-buffer entry points
-// Host-buffer GCN aggregation / layer.  The un-scheduled path is pipelined over kHostChunks edge-balanced row
-// chunks: chunk c is aggregated (and combined) on `stream` while the finished rows of chunk c-1 travel back to
-// the host on a second stream, so only the input copy and one chunk of the output copy are exposed.
 constexpr int kHostChunks = 4;
+constexpr int kHostSlices = 4;
 
+// builds the source slices on first use and (re)mirrors the edge values into slice order
+static int ensure_slices(gnnagg_aggregator *a, int want, cudaStream_t st)
+{
+    if (a->num_slices != want) {
+        free_slices(a);
+        const int width = (int)cdiv(a->n, want);
+        if (int rc = source_slices_build_device(a->d_ptr, a->d_idx, a->d_item_row, a->num_items, a->n, a->m, want, width,
+                                                &a->sl_ptr, &a->sl_idx, &a->sl_perm, a->sl_off, a->sl_cnt, st))
+            return rc;
+        const size_t padded = (size_t)a->m + 4 * (size_t)want;
+        if (cudaMalloc((void **)&a->sl_val, padded * sizeof(float)) != cudaSuccess) {
+            free_slices(a);
+            return set_error(GNNAGG_ERR_CUDA, "host pipeline: out of device memory for the source slices");
+        }
+        for (int c = 0; c < want; ++c) {
+            gnnagg_aggregator *s = new gnnagg_aggregator();
+            a->slice[c] = s;
+            s->d_ptr = a->sl_ptr + (size_t)c * ((size_t)a->n + 1);
+            s->d_idx = a->sl_idx + a->sl_off[c];
+            s->d_val = a->sl_val + a->sl_off[c];
+            s->n = a->n;
+            s->m = a->sl_cnt[c];
+            s->warp_edges = a->warp_edges ? a->warp_edges : (a->m < kSmallGraphEdges ? 128 : kWarpEdges);  // as the whole graph
+            if (int rc = build_item_rows(s, s->d_ptr, s->n, s->m, &s->d_item_row, &s->num_items, st)) {
+                free_slices(a);
+                return rc;
+            }
+        }
+        a->num_slices = want;
+        a->slice_width = width;
+        a->launches += 6 + 3 * want;
+    }
+    if (a->sl_val_of != a->d_val) {
+        for (int c = 0; c < want; ++c) {
+            if (a->sl_cnt[c] == 0) continue;
+            gather_val_kernel<<<(unsigned)cdiv(a->sl_cnt[c], 256), 256, 0, st>>>(a->d_val, a->sl_perm + a->sl_off[c],
+                                                                              a->sl_val + a->sl_off[c], a->sl_cnt[c]);
+            LAUNCH_CHECK(a);
+        }
+        a->sl_val_of = a->d_val;
+    }
+    return GNNAGG_OK;
+}
+
+static int ensure_in_stream(gnnagg_aggregator *a)
+{
+    if (a->in_stream) return GNNAGG_OK;
+    CUDA_TRY(cudaStreamCreateWithFlags(&a->in_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; ++i) CUDA_TRY(cudaEventCreateWithFlags(&a->in_done[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&a->in_free, cudaEventDisableTiming));
+    return GNNAGG_OK;
+}
+
+// Host-buffer GCN aggregation / layer.  Three regimes:
+//   * scheduled runs and tiny graphs: copy in, run, copy out;
+//   * medium graphs: one input copy, then edge-balanced ROW chunks -- chunk c is aggregated (and combined) on `stream`
+//     while the finished rows of chunk c-1 travel back on a second stream;
+//   * large graphs (>= kSmallGraphEdges edges, or forced): SOURCE slices on top of that.  X arrives in S row blocks on a
+//     third stream; slice c (the edges whose source lies in block c) is accumulated into the output as soon as block c
+//     is resident, so the aggregation hides behind the input copy; the last two slices run row chunk by row chunk, each
+//     chunk followed by its combination and its copy back, so the output copy starts soon after the input copy ends.
 static int gcn_host_pipeline(gnnagg_aggregator *a, const float *h_X, const float *h_W, float *h_out, int feat_in,
                              int feat_out, int scheduled, cudaStream_t st)
 {
@@ -1066,7 +1159,6 @@ static int gcn_host_pipeline(gnnagg_aggregator *a, const float *h_X, const float
     const size_t cin = (size_t)a->n * feat_in, cout = (size_t)a->n * fo;
     if (int rc = ensure(a->st_in, a->st_in_cap, cin)) return rc;
     if (int rc = ensure(a->st_out, a->st_out_cap, cout)) return rc;
-    CUDA_TRY(cudaMemcpyAsync(a->st_in, h_X, cin * sizeof(float), cudaMemcpyHostToDevice, st));
     if (layer) {
         if (int rc = ensure(a->st_w, a->st_w_cap, (size_t)feat_in * feat_out)) return rc;
         if (int rc = ensure(a->ax, a->ax_cap, cin)) return rc;
@@ -1074,6 +1166,7 @@ static int gcn_host_pipeline(gnnagg_aggregator *a, const float *h_X, const float
     }
     float *agg_out = layer ? a->ax : a->st_out;
     if (scheduled || a->n < 4096) {  // scheduled order is not row-contiguous; tiny graphs are not worth chunking
+        CUDA_TRY(cudaMemcpyAsync(a->st_in, h_X, cin * sizeof(float), cudaMemcpyHostToDevice, st));
         if (int rc = gcn_run_impl(a, a->st_in, agg_out, feat_in, scheduled, st, !layer)) return rc;
         if (layer && a->n > 0) {
             if (int rc = dense_nn_launch(a->ax, a->st_w, a->st_out, a->n, feat_out, feat_in, st)) return rc;
@@ -1085,15 +1178,61 @@ static int gcn_host_pipeline(gnnagg_aggregator *a, const float *h_X, const float
     }
     if (int rc = check_feat(feat_in)) return rc;
     if (!a->d_val && a->m > 0) return set_error(GNNAGG_ERR_STATE, "edge values not set (gnnagg_set_val)");
-    const int *hp = nullptr;
-    if (int rc = host_ptr(a, &hp)) return rc;
     if (int rc = ensure_copy_stream(a)) return rc;
+    const int S = a->host_slices > 0 ? a->host_slices : (a->host_slices == 0 && a->m >= kSmallGraphEdges ? kHostSlices : 1);
+    // the aggregators whose rows are chunked for the copy back: the graph itself, or the trailing slices
+    gnnagg_aggregator *tail[2] = {a, nullptr};
+    int tail_first = 0, tail_count = 1;
+    if (S > 1) {
+        if (int rc = ensure_slices(a, S, st)) return rc;
+        if (int rc = ensure_in_stream(a)) return rc;
+        // input blocks on their own stream, after everything already queued on `st` (a previous call may still read st_in)
+        CUDA_TRY(cudaEventRecord(a->in_free, st));
+        CUDA_TRY(cudaStreamWaitEvent(a->in_stream, a->in_free, 0));
+        for (int c = 0; c < S; ++c) {
+            const int64_t r0 = std::min<int64_t>((int64_t)c * a->slice_width, a->n), r1 = std::min<int64_t>(r0 + a->slice_width, a->n);
+            if (r1 > r0)
+                CUDA_TRY(cudaMemcpyAsync(a->st_in + (size_t)r0 * feat_in, h_X + (size_t)r0 * feat_in,
+                                         (size_t)(r1 - r0) * feat_in * sizeof(float), cudaMemcpyHostToDevice, a->in_stream));
+            CUDA_TRY(cudaEventRecord(a->in_done[c], a->in_stream));
+        }
+        // The aggregation is longer than the input copy, so when the last block lands part of the second-to-last slice
+        // is still to do: the last TWO slices run row chunk by row chunk (both slices of a chunk, its combination, its
+        // copy back), the slices before them over all rows as their block arrives.
+        tail_count = 2;
+        tail_first = S - tail_count;
+        for (int c = 0; c < tail_first; ++c) {
+            CUDA_TRY(cudaStreamWaitEvent(st, a->in_done[c], 0));
+            gnnagg_aggregator *s = a->slice[c];
+            const int64_t before = s->launches;
+            if (int rc = gcn_run_core(s, a->st_in, agg_out, feat_in, 0, st, c > 0)) return rc;
+            a->launches += s->launches - before;
+        }
+        tail[0] = a->slice[tail_first];
+        tail[1] = a->slice[tail_first + 1];
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(a->st_in, h_X, cin * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    const int *hp[2] = {nullptr, nullptr};
+    for (int t = 0; t < tail_count; ++t)
+        if (int rc = host_ptr(tail[t], &hp[t])) return rc;
     int bounds[kHostChunks + 1];
-    row_chunks(hp, a->n, a->m, kHostChunks, bounds);
+    if (S > 1) {  // equal ROW counts: the chunks are sized for the copy back
+        for (int c = 0; c <= kHostChunks; ++c) bounds[c] = (int)((int64_t)a->n * c / kHostChunks);
+    } else {
+        row_chunks(hp[0], a->n, a->m, kHostChunks, bounds);
+    }
     for (int c = 0; c < kHostChunks; ++c) {
         const int r0 = bounds[c], r1 = bounds[c + 1];
         if (r1 <= r0) continue;
-        if (int rc = gcn_run_core(a, a->st_in, agg_out, feat_in, 0, st, 0, r0, r1, hp[r0], hp[r1])) return rc;
+        for (int t = 0; t < tail_count; ++t) {
+            if (S > 1 && c == 0) CUDA_TRY(cudaStreamWaitEvent(st, a->in_done[tail_first + t], 0));
+            const int64_t before = tail[t]->launches;
+            if (int rc = gcn_run_core(tail[t], a->st_in, agg_out, feat_in, 0, st, S > 1 && (tail_first + t) > 0, r0, r1,
+                                      hp[t][r0], hp[t][r1]))
+                return rc;
+            if (tail[t] != a) a->launches += tail[t]->launches - before;
+        }
         if (layer) {
             if (int rc = dense_nn_launch(a->ax + (size_t)r0 * feat_in, a->st_w, a->st_out + (size_t)r0 * fo, r1 - r0, feat_out,
                                          feat_in, st))
@@ -1108,6 +1247,13 @@ static int gcn_host_pipeline(gnnagg_aggregator *a, const float *h_X, const float
     CUDA_TRY(cudaEventRecord(a->copies_done, a->copy_stream));
     CUDA_TRY(cudaStreamWaitEvent(st, a->copies_done, 0));  // the caller's stream is ordered after the copies as well
     CUDA_TRY(cudaStreamSynchronize(st));
+    return GNNAGG_OK;
+}
+
+int gnnagg_set_host_pipeline(gnnagg_aggregator *a, int slices)
+{
+    if (!a || slices > 8) return set_error(GNNAGG_ERR_ARG, "gnnagg_set_host_pipeline: at most 8 source slices");
+    a->host_slices = slices;
     return GNNAGG_OK;
 }
 

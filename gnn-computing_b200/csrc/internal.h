@@ -30,6 +30,11 @@ int schedule_build_device(int kind, const int *d_ptr, const int *d_idx, const in
 int transpose_build_device(const int *d_ptr, const int *d_idx, const int *d_item_row, int num_items, int n, int m,
                            int num_src, int **t_ptr, int **t_idx, int **t_perm, cudaStream_t st);
 
+// the CSR split by source-id ranges into num_slices sub-CSRs over the same rows (sched_device.cu)
+int source_slices_build_device(const int *d_ptr, const int *d_idx, const int *d_item_row, int num_items, int n, int m,
+                               int num_slices, int width, int **sl_ptr, int **sl_idx, int **sl_perm, int *edge_off,
+                               int *edge_cnt, cudaStream_t st);
+
 // sub-graph samplers of include/sample.h (sample_device.cu); outputs are cudaMalloc'ed
 int sample_subgraph_device(const int *d_ptr, const int *d_idx, const int *d_item_row, int num_items, int n, int m,
                            int *d_active, int fanout, int layer_num, uint64_t seed, int **vertexset, int **sub_ptr,

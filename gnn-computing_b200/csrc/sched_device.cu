@@ -303,4 +303,86 @@ fail_keep_error:
     return GNNAGG_ERR_ARG;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Source slices for the host-buffer pipeline (capi.cu: gcn_host_pipeline): the CSR split by ranges of the SOURCE
+// id into S sub-CSRs over the same rows -- the locality slices of graph_schedule.h:24-29, kept as complete CSRs so
+// that each one runs through the deterministic un-scheduled kernel in accumulate mode.  Slice c only gathers rows
+// [src_bounds[c], src_bounds[c+1]) of X, so its aggregation can start as soon as that part of X has arrived from
+// the host.  Edge order inside a slice is CSR order (stable sort).  Outputs (cudaMalloc'ed, owned by the caller):
+//   *sl_ptr  [S*(n+1)]  row pointers of every slice, relative to the slice's own edge array
+//   *sl_idx, *sl_perm   source ids / CSR edge ids; slice c occupies [edge_off[c], edge_off[c] + edge_cnt[c]),
+//                       edge_off[c] a multiple of 4 (16-byte aligned slices keep the bulk-copy staging usable)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) slice_key_kernel(const int *__restrict__ idx, int m, int num_slices, int width,
+                                                        int *__restrict__ keys, int *__restrict__ edge_id)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= m) return;
+    keys[e] = min(__ldg(idx + e) / width, num_slices - 1);
+    edge_id[e] = e;
+}
+
+int source_slices_build_device(const int *d_ptr, const int *d_idx, const int *d_item_row, int num_items, int n, int m,
+                               int num_slices, int width, int **sl_ptr, int **sl_idx, int **sl_perm, int *edge_off,
+                               int *edge_cnt, cudaStream_t st)
+{
+    *sl_ptr = *sl_idx = *sl_perm = nullptr;
+    int *keys = nullptr, *keys_sorted = nullptr, *edge_id = nullptr, *perm = nullptr, *rows_sorted = nullptr, *bounds_d = nullptr;
+    void *tmp = nullptr;
+    size_t need = 0;
+    int bounds[65] = {0};
+    const size_t me = (size_t)(m > 0 ? m : 1);
+    const size_t padded = me + 4 * (size_t)num_slices;
+    int end_bit = 1;
+    while ((1 << end_bit) < num_slices) ++end_bit;
+    if (num_slices < 1 || num_slices > 64 || width < 1) return set_error(GNNAGG_ERR_ARG, "source slices: bad slice count");
+    SD_TRY(cudaMalloc((void **)sl_ptr, (size_t)num_slices * ((size_t)n + 1) * sizeof(int)));
+    SD_TRY(cudaMalloc((void **)sl_idx, padded * sizeof(int)));
+    SD_TRY(cudaMalloc((void **)sl_perm, padded * sizeof(int)));
+    SD_TRY(cudaMemsetAsync(*sl_perm, 0, padded * sizeof(int), st));
+    SD_TRY(cudaMalloc((void **)&keys, me * sizeof(int)));
+    SD_TRY(cudaMalloc((void **)&keys_sorted, me * sizeof(int)));
+    SD_TRY(cudaMalloc((void **)&edge_id, me * sizeof(int)));
+    SD_TRY(cudaMalloc((void **)&perm, me * sizeof(int)));
+    SD_TRY(cudaMalloc((void **)&rows_sorted, me * sizeof(int)));
+    SD_TRY(cudaMalloc((void **)&bounds_d, ((size_t)num_slices + 1) * sizeof(int)));
+    if (m > 0) {
+        slice_key_kernel<<<blocks(m), 256, 0, st>>>(d_idx, m, num_slices, width, keys, edge_id);
+        SD_TRY(cub::DeviceRadixSort::SortPairs(nullptr, need, keys, keys_sorted, edge_id, perm, m, 0, end_bit, st));
+        SD_TRY(cudaMalloc(&tmp, need ? need : 1));
+        SD_TRY(cub::DeviceRadixSort::SortPairs(tmp, need, keys, keys_sorted, edge_id, perm, m, 0, end_bit, st));  // stable
+        ptr_from_sorted_kernel<<<blocks((int64_t)m + 1), 256, 0, st>>>(keys_sorted, m, num_slices, bounds_d);
+        edge_rows_kernel<<<blocks(m), 256, 0, st>>>(d_ptr, d_item_row, num_items, n, perm, m, rows_sorted);
+        SD_TRY(cudaMemcpyAsync(bounds, bounds_d, ((size_t)num_slices + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+        SD_TRY(cudaStreamSynchronize(st));
+    }
+    {
+        int off = 0;
+        for (int c = 0; c < num_slices; ++c) {
+            const int cnt = bounds[c + 1] - bounds[c];
+            edge_off[c] = off;
+            edge_cnt[c] = cnt;
+            int *ptr_c = *sl_ptr + (size_t)c * ((size_t)n + 1);
+            if (cnt > 0) {
+                ptr_from_sorted_kernel<<<blocks((int64_t)cnt + 1), 256, 0, st>>>(rows_sorted + bounds[c], cnt, n, ptr_c);
+                gather_idx_kernel<<<blocks(cnt), 256, 0, st>>>(d_idx, perm + bounds[c], *sl_idx + off, cnt);
+                SD_TRY(cudaMemcpyAsync(*sl_perm + off, perm + bounds[c], (size_t)cnt * sizeof(int), cudaMemcpyDeviceToDevice, st));
+            } else {
+                SD_TRY(cudaMemsetAsync(ptr_c, 0, ((size_t)n + 1) * sizeof(int), st));
+            }
+            off += (cnt + 3) & ~3;
+        }
+    }
+    SD_TRY(cudaGetLastError());
+    SD_TRY(cudaStreamSynchronize(st));
+    cudaFree(keys), cudaFree(keys_sorted), cudaFree(edge_id), cudaFree(perm), cudaFree(rows_sorted), cudaFree(bounds_d), cudaFree(tmp);
+    return GNNAGG_OK;
+fail:
+    cudaFree(keys), cudaFree(keys_sorted), cudaFree(edge_id), cudaFree(perm), cudaFree(rows_sorted), cudaFree(bounds_d), cudaFree(tmp);
+    cudaFree(*sl_ptr), cudaFree(*sl_idx), cudaFree(*sl_perm);
+    *sl_ptr = *sl_idx = *sl_perm = nullptr;
+    return GNNAGG_ERR_CUDA;
+}
+
 }  // namespace gnnagg

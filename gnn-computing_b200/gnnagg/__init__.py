@@ -94,6 +94,7 @@ _SIGS = {
     "gnnagg_gat_run_host": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_float, C.c_int, C.c_void_p]),
     "gnnagg_launch_count": (C.c_int64, [C.c_void_p]),
     "gnnagg_set_warp_edges": (C.c_int, [C.c_void_p, C.c_int]),
+    "gnnagg_set_host_pipeline": (C.c_int, [C.c_void_p, C.c_int]),
     "gnnagg_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "gnnagg_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "gnnagg_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
@@ -276,6 +277,9 @@ class Aggregator:
 
     def set_warp_edges(self, warp_edges):
         check(lib().gnnagg_set_warp_edges(self.h, int(warp_edges)))
+
+    def set_host_pipeline(self, slices):
+        check(lib().gnnagg_set_host_pipeline(self.h, int(slices)))
 
     def profile(self, on=True):
         check(lib().gnnagg_profile_enable(self.h, int(on)))

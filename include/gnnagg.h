@@ -267,6 +267,15 @@ int gnnagg_gcn_layer_host(gnnagg_aggregator *a, const float *h_X, const float *h
 int gnnagg_gat_run_host(gnnagg_aggregator *a, const float *h_X, const float *h_att, float *h_Y, int feat,
                         float slope, int scheduled, void *stream);
 
+/* how the two GCN host-buffer entry points overlap copies and kernels (X must be [num_v, feat], square graph):
+ *   0  automatic: graphs of >= 4M edges use 4 SOURCE slices -- X travels in 4 row blocks and the sub-CSR of the edges
+ *      whose source lies in block c (built once on the GPU, the locality slices of graph_schedule.h:24-29 kept as CSRs)
+ *      is accumulated as soon as block c is resident; the last slice runs in row chunks so the copy back starts one
+ *      chunk after the input copy ends.  Smaller graphs: one input copy, then row chunks.
+ *  >0  force that many source slices (<= 8);   <0  row chunks only.
+ * Results are deterministic for a given setting; slices change the fp32 summation order (slice by slice). */
+int gnnagg_set_host_pipeline(gnnagg_aggregator *a, int slices);
+
 /* tuning knob (the reference's analogue is the BLOCK_SIZE argument of run(), aggr_gcn.h:381-386):
  * edges staged per warp by the aggregation kernels: 0 = automatic (128 below 4M edges, else 512),
  * or force 128 / 512.  Results do not depend on it beyond fp32 summation order. */

@@ -178,3 +178,30 @@ def test_full_size_sampler_properties(gn, orc, cuda):
     o_act, o_vs, o_sp, o_si = orc.sample_subgraph(ptr.cpu().numpy(), idx.cpu().numpy(), seeds.cpu().numpy(), k, 2, seed=5)
     assert np.array_equal(vs.cpu().numpy(), o_vs) and np.array_equal(sp.cpu().numpy(), o_sp)
     assert np.array_equal(si.cpu().numpy(), o_si) and np.array_equal(active.cpu().numpy(), o_act)
+
+
+def test_full_size_host_pipeline_matches_device(gn, cuda):
+    """reddit-shaped layer through the host-buffer entry point (automatic: 4 source slices + row chunks) against the
+    single-launch device path: same terms in another summation order, gated by |A|·|X| (and by |AX|·|W| after the
+    combination)"""
+    n, m = synth.shape_of("reddit")
+    F = 128
+    ptr, idx = synth.rmat_csr(n, m, seed=123, device=cuda)
+    val = synth.gcn_norm_val(ptr, idx)
+    g = torch.Generator(device=cuda).manual_seed(11)
+    X = torch.randn((n, F), device=cuda, generator=g)
+    W = torch.randn((F, F), device=cuda, generator=g) / F ** 0.5
+    agg = gn.Aggregator(ptr, idx, val)
+    hX, hW = X.cpu().pin_memory(), W.cpu().pin_memory()
+    hY, hH = torch.empty((n, F)).pin_memory(), torch.empty((n, F)).pin_memory()
+    agg.gcn_run_host(hX, hY)
+    Yd = agg.gcn_run(X, torch.empty((n, F), device=cuda))
+    absY = agg.gcn_run(X.abs(), torch.empty((n, F), device=cuda))
+    assert rel_gate(hY.numpy(), Yd.cpu().numpy(), absY.cpu().numpy(), 2e-5)[0] == 0
+    agg.gcn_layer_host(hX, hW, hH)
+    Hd = agg.gcn_layer(X, W, torch.empty((n, F), device=cuda), torch.empty((n, F), device=cuda))
+    scale = (absY @ W.abs()).cpu().numpy()
+    assert rel_gate(hH.numpy(), Hd.cpu().numpy(), scale, 2e-5)[0] == 0
+    first = hH.numpy().copy()
+    agg.gcn_layer_host(hX, hW, hH)
+    assert np.array_equal(first, hH.numpy())

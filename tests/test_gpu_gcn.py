@@ -166,6 +166,53 @@ def test_host_entry_points_pipelined_row_chunks(gn, orc, cuda, F, we):
         assert rel_gate(hH.numpy(), h64, hs, TOL)[0] == 0
 
 
+@pytest.mark.parametrize("slices", [2, 3, 4, 8])
+@pytest.mark.parametrize("F", [32, 128])
+def test_host_entry_points_source_slices(gn, orc, cuda, slices, F):
+    """large graphs (forced here): X travels in `slices` row blocks and the sub-CSR of the edges whose source lies in a
+    block is accumulated as soon as the block is resident; the last slice runs in row chunks.  Hubs, empty rows, a
+    source range with no edge at all, new edge values through set_val, repeated calls"""
+    from gnnagg import synth
+
+    n = 9001  # not a multiple of any slice count
+    ptr, idx = synth.small_random_csr(n, 14.0, F + slices, empty_frac=0.3, hub=30000)
+    idx = idx.copy()
+    lo, hi = (n // slices) * (slices - 1), n   # leave the last source block almost unused: an (almost) empty slice
+    idx[idx >= lo] = idx[idx >= lo] % max(lo, 1)
+    ptr, idx = ptr.astype(np.int32), idx.astype(np.int32)
+    m = len(idx)
+    X, val = rand_inputs(n, m, F, seed=3)
+    dval = dev(val)
+    agg = gn.Aggregator(dev(ptr), dev(idx), dval)
+    agg.set_host_pipeline(slices)
+    hX = torch.from_numpy(X).pin_memory()
+    hY = torch.full((n, F), float("nan")).pin_memory()
+    y64, scale = orc.spmm_f64(ptr, idx, val, X)
+    for _ in range(2):
+        hY.fill_(float("nan"))
+        agg.gcn_run_host(hX, hY)
+        assert rel_gate(hY.numpy(), y64, scale, TOL)[0] == 0
+    first = hY.numpy().copy()
+    agg.gcn_run_host(hX, hY)
+    assert np.array_equal(first, hY.numpy())  # deterministic
+    W = (np.random.default_rng(4).standard_normal((F, 64)) / np.sqrt(F)).astype(np.float32)
+    hH = torch.full((n, 64), float("nan")).pin_memory()
+    agg.gcn_layer_host(hX, torch.from_numpy(W).pin_memory(), hH)
+    _, h64, hs = orc.gcn_layer_f64(ptr, idx, val, X, W)
+    assert rel_gate(hH.numpy(), h64, hs, TOL)[0] == 0
+    # new edge values are mirrored into slice order
+    val2 = (val * 0.25 - 1.0).astype(np.float32)
+    dval2 = dev(val2)
+    agg.set_val(dval2)
+    agg.gcn_run_host(hX, hY)
+    y64b, scale_b = orc.spmm_f64(ptr, idx, val2, X)
+    assert rel_gate(hY.numpy(), y64b, scale_b, TOL)[0] == 0
+    # back to row chunks only: bit-identical to the device path again
+    agg.set_host_pipeline(-1)
+    agg.gcn_run_host(hX, hY)
+    assert np.array_equal(hY.numpy(), agg.gcn_run(dev(X), torch.empty((n, F), device=cuda)).cpu().numpy())
+
+
 def test_naive_spmm_and_validators(gn, orc, cuda):
     """include/spmm.h: spmm<>, valid(), validReordered()"""
     ptr, idx = make_graph("medium", seed=5)
