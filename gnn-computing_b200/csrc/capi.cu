@@ -86,6 +86,13 @@ struct gnnagg_aggregator {
     int *s_ptr = nullptr, *s_idx = nullptr, *s_target = nullptr, *s_perm = nullptr, *s_item_row = nullptr;
     float *s_val = nullptr;  // owned only when s_perm != nullptr (locality kinds); NG aliases d_val
     bool s_idx_owned = false;  // neighbour grouping keeps the edge order: its idx aliases d_idx
+    // rows spanning more than kFixChunk carry items, per item size (second fix-up pass; built on first use)
+    struct LongRows {
+        int item_edges = 0, count = 0;
+        int *list = nullptr;
+        int2 *records = nullptr;  // per item: what the first fix-up pass does there (fixup_records_kernel)
+    };
+    std::vector<LongRows> long_rows;
     int64_t launches = 0;
     int warp_edges = 0;  // 0 = automatic
     // backward pass (gnnagg_transpose_build): the transposed CSR and a child aggregator that runs over it
@@ -211,6 +218,48 @@ static void launch_agg_we(const AggParams &p, cudaStream_t st)
         agg_kernel<32, 2, MODE, SCHED, WE><<<grid, kCtaThreads, 0, st>>>(p);
 }
 
+// rows of a's CSR with more than kFixChunk carry items of EB edges, found once per item size (one host synchronisation)
+static int long_rows_of(gnnagg_aggregator *a, const AggParams &p, int EB, cudaStream_t st, const int **list, int *count,
+                        const int2 **records)
+{
+    for (auto &e : a->long_rows)
+        if (e.item_edges == EB) {
+            *list = e.list;
+            *count = e.count;
+            *records = e.records;
+            return GNNAGG_OK;
+        }
+    gnnagg_aggregator::LongRows e;
+    e.item_edges = EB;
+    const size_t cap = (size_t)a->m / ((size_t)kFixChunk * EB) + 2;
+    int *counter = nullptr;
+    const int64_t items = cdiv(a->m, EB);
+    CUDA_TRY(cudaMalloc((void **)&e.list, cap * sizeof(int)));
+    if (cudaMalloc((void **)&counter, sizeof(int)) != cudaSuccess ||
+        cudaMalloc((void **)&e.records, (size_t)(items + 1) * sizeof(int2)) != cudaSuccess) {
+        cudaFree(e.list);
+        cudaFree(counter);
+        return set_error(GNNAGG_ERR_CUDA, "out of device memory");
+    }
+    cudaMemsetAsync(counter, 0, sizeof(int), st);
+    long_rows_kernel<<<(unsigned)cdiv(a->n, 256), 256, 0, st>>>(a->d_ptr, a->n, EB, e.list, counter);
+    fixup_records_kernel<<<(unsigned)cdiv(items, 256), 256, 0, st>>>(p, EB, items, e.records);
+    cudaError_t err = cudaMemcpyAsync(&e.count, counter, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+    cudaFree(counter);
+    if (err != cudaSuccess) {
+        cudaFree(e.list);
+        cudaFree(e.records);
+        return set_error(GNNAGG_ERR_CUDA, cudaGetErrorString(err));
+    }
+    a->launches += 2;
+    a->long_rows.push_back(e);
+    *list = e.list;
+    *count = e.count;
+    *records = e.records;
+    return GNNAGG_OK;
+}
+
 template <int MODE, bool SCHED>
 static int launch_agg(gnnagg_aggregator *a, AggParams p, cudaStream_t st)
 {
@@ -230,10 +279,14 @@ static int launch_agg(gnnagg_aggregator *a, AggParams p, cudaStream_t st)
         const int64_t items = cdiv(p.num_edges, EB);
         const int64_t range_items = cdiv(p.edge_hi, EB) - p.edge_lo / EB;  // items touched by the launched range
         if (range_items > 1) {
-            agg_fixup_kernel<MODE, 1><<<(unsigned)cdiv(range_items, 8), 256, 0, st>>>(p, EB, items);
+            const int *list = nullptr;
+            const int2 *records = nullptr;
+            int num_long = 0;
+            if (int rc = long_rows_of(a, p, EB, st, &list, &num_long, &records)) return rc;
+            agg_fixup_kernel<MODE><<<(unsigned)cdiv(range_items, 8), 256, 0, st>>>(p, EB, items, records);
             LAUNCH_CHECK(a);
-            if (range_items > kFixChunk + 1) {  // a row can only span more than kFixChunk carry items then
-                agg_fixup_kernel<MODE, 2><<<(unsigned)cdiv(range_items, 8), 256, 0, st>>>(p, EB, items);
+            if (num_long > 0) {
+                agg_fixup_long_kernel<MODE><<<(unsigned)cdiv(num_long, 8), 256, 0, st>>>(p, EB, list, num_long);
                 LAUNCH_CHECK(a);
             }
         }
@@ -492,12 +545,19 @@ static int rowsum_impl(gnnagg_aggregator *a, const float *in, float *out, cudaSt
     return GNNAGG_OK;
 }
 
+static void free_long_rows(gnnagg_aggregator *a)
+{
+    for (auto &e : a->long_rows) cudaFree(e.list), cudaFree(e.records);
+    a->long_rows.clear();
+}
+
 static void free_slices(gnnagg_aggregator *a)
 {
     for (int c = 0; c < 8; ++c) {
         if (!a->slice[c]) continue;
         cudaFree(a->slice[c]->d_item_row);
         cudaFree(a->slice[c]->carry);
+        free_long_rows(a->slice[c]);
         delete a->slice[c];
         a->slice[c] = nullptr;
     }
@@ -514,6 +574,7 @@ static void free_transpose(gnnagg_aggregator *a)
         cudaFree(a->tr->d_item_row);
         cudaFree(a->tr->carry);
         cudaFree(a->tr->carry_den);
+        free_long_rows(a->tr);
         delete a->tr;
         a->tr = nullptr;
     }
@@ -583,6 +644,7 @@ int gnnagg_destroy(gnnagg_aggregator *a)
     free_schedule(a);
     free_transpose(a);
     free_slices(a);
+    free_long_rows(a);
     for (int i = 0; i < 8; ++i)
         if (a->in_done[i]) cudaEventDestroy(a->in_done[i]);
     if (a->in_free) cudaEventDestroy(a->in_free);
