@@ -129,12 +129,10 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
         }
         __syncwarp();
         if (nb > 0) mbar_wait(bar, 0);
-        if (MODE == kModeGAT || (MODE == kModeGATBWD && !stage_val)) {
-            // source half of the attention logit, gathered once per edge: att[2u+1] (aggr_gat.h:138)
-#pragma unroll 4
-            for (int i = lane; i < wcnt; i += 32) my_val[i] = __ldg(p.att + 2 * (size_t)my_idx[i] + 1);
-            __syncwarp();
-        }
+        // GAT: the source half of the attention logit, att[2u+1] (aggr_gat.h:138), is NOT staged here: a separate
+        // gather phase per warp (16 dependent-free loads per lane, then the walk) left the walk without loads in flight
+        // while it ran.  Lane u < U of a virtual warp fetches the term of edge u of each batch together with the batch's
+        // row gathers instead, and the virtual warp shares it by shuffle.
     }
 
     // ---------------- the walk: one virtual warp per item ----------------
@@ -258,7 +256,8 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
 #pragma unroll
                 for (int u = 1; u < U; ++u)
                     if (id == u) v = drow[u];
-                sv = my_val[e + id - wbase];  // att[2u+1], or the handed-in weight
+                sv = (p.att != nullptr) ? __ldg(p.att + 2 * (size_t)my_idx[e + id - wbase] + 1)  // source attention term
+                                        : my_val[e + id - wbase];                                  // handed-in weight
                 ri = __ldg(p.bwd_c + v);
                 if (p.att != nullptr) a_v = __ldg(p.att + 2 * (size_t)v);
             }
@@ -298,8 +297,10 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
             for (int u = 0; u < U; ++u) {
                 const int k = min(e + u, e1 - 1) - wbase;
                 src[u] = my_idx[k];
-                w[u] = mode_has_dst(MODE) ? 0.f : my_val[k];
+                w[u] = (mode_has_dst(MODE) || MODE == kModeGAT) ? 0.f : my_val[k];
             }
+            float a_src = 0.f;  // GAT: source attention term of edge min(e + vl, e1 - 1), lanes vl < U
+            if (MODE == kModeGAT && vl < U) a_src = __ldg(p.att + 2 * (size_t)my_idx[min(e + vl, e1 - 1) - wbase] + 1);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const char *x = xb + (size_t)(uint32_t)src[u] * row_bytes;
@@ -309,9 +310,10 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
             float wout = 0.f;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
+                float wu = w[u];
+                if (MODE == kModeGAT) wu = __shfl_sync(vw_mask, a_src, u, LPR);  // all lanes of the virtual warp, every u
                 if (u < nb) {
                     while (row_end == e + u) flush(false);
-                    float wu = w[u];
                     if (MODE == kModeGAT) {
                         const float sc = a_dst + wu;
                         wu = __expf(fmaxf(sc, sc * p.slope));
@@ -343,11 +345,14 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
 #pragma unroll
             for (int q = 0; q < U / 4; ++q) {
                 const int4 i4 = lds_i4(s_base + 4u * (uint32_t)(k + 4 * q));
-                const float4 w4 = mode_has_dst(MODE) ? make_float4(0.f, 0.f, 0.f, 0.f)
-                                                     : lds_f4(s_base + 4u * (uint32_t)(k + 4 * q + kWarpEdges));
+                const float4 w4 = (mode_has_dst(MODE) || MODE == kModeGAT)
+                                      ? make_float4(0.f, 0.f, 0.f, 0.f)
+                                      : lds_f4(s_base + 4u * (uint32_t)(k + 4 * q + kWarpEdges));
                 src[4 * q] = i4.x, src[4 * q + 1] = i4.y, src[4 * q + 2] = i4.z, src[4 * q + 3] = i4.w;
                 w[4 * q] = w4.x, w[4 * q + 1] = w4.y, w[4 * q + 2] = w4.z, w[4 * q + 3] = w4.w;
             }
+            float a_src = 0.f;  // GAT: source attention term of edge e + vl (lanes vl < U), in flight with the row gathers
+            if (MODE == kModeGAT && vl < U) a_src = __ldg(p.att + 2 * (size_t)my_idx[k + vl] + 1);
             float4 v0[U], v1[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -361,7 +366,7 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
                 // (one MUFU per edge instead of one per edge-lane) and the virtual warp shares it by shuffle
                 float wgt = 0.f;
                 if (vl < U) {
-                    const float sc = a_dst + my_val[k + vl];
+                    const float sc = a_dst + a_src;
                     wgt = __expf(fmaxf(sc, sc * p.slope));  // aggr_gat.h:143
                 }
 #pragma unroll
@@ -382,7 +387,7 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
                     while (row_end == e + u) flush(false);
                     float wu = w[u];
                     if (MODE == kModeGAT) {
-                        const float sc = a_dst + wu;
+                        const float sc = a_dst + __shfl_sync(vw_mask, a_src, u, LPR);
                         wu = __expf(fmaxf(sc, sc * p.slope));  // aggr_gat.h:143
                         den += wu;
                         if (SCHED && vl == u % LPR) wout = wu;
