@@ -5,10 +5,10 @@
 set -u
 tool="${1:-memcheck}"
 mkdir -p gpurun_out
-sel='test_gcn_unscheduled_parity and (tiny or hub or exact_items) and (32 or 128)'
 timeout 1500 compute-sanitizer --tool "$tool" --error-exitcode 66 --target-processes application-only \
-  python -m pytest tests/test_gpu_gcn.py tests/test_gpu_gat.py tests/test_gpu_layer.py tests/test_gpu_mlp.py -m gpu -q -x -p no:cacheprovider \
-  -k "(unscheduled and (tiny or hub or exact_items)) or scheduled or sddmm and tiny or dense_nn_parity or mlp_parity and tiny or host_entry" \
+  python -m pytest tests/test_gpu_gcn.py tests/test_gpu_gat.py tests/test_gpu_layer.py tests/test_gpu_mlp.py tests/test_gpu_backward.py \
+  tests/test_gpu_sampler.py -m gpu -q -x -p no:cacheprovider \
+  -k "(unscheduled and (tiny or hub or exact_items)) or scheduled or sddmm and tiny or dense_nn_parity or mlp_parity and tiny or host_entry or (backward and (tiny or hub or bighub) and not timing) or transpose_bit_exact or (sampler_matches_oracle and (hub or tiny))" \
   > "gpurun_out/sanitize_${tool}.log" 2>&1
 echo "exit=$?" >> "gpurun_out/sanitize_${tool}.log"
 tail -15 "gpurun_out/sanitize_${tool}.log"
