@@ -181,6 +181,8 @@ def main():
             return 0
         import oracle as orc
 
+        orc.use_all_cores()  # rank 0 alone runs this arm: every host core, also under torchrun (OMP_NUM_THREADS=1 there)
+
         dev = torch.device("cuda:%d" % local_rank) if torch.cuda.is_available() else torch.device("cpu")
         # the same graph; a leading row block is what gets timed, so only that block is built when no GPU is around
         gen_rows, gen_edges = (n, m) if dev.type == "cuda" else (n, min(m, 4_000_000))
@@ -428,6 +430,7 @@ def main():
 
     import oracle as orc
 
+    orc.use_all_cores()
     if N > 1:  # the CPU port needs the replicated X of rank 0's block
         g_all = [torch.randn((n, fin), device=dev, generator=torch.Generator(device=dev).manual_seed(123 + r)) for r in range(N)]
         Xcpu = torch.cat(g_all)

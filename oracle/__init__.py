@@ -44,6 +44,16 @@ def num_threads():
     return lib().orc_num_threads()
 
 
+def use_all_cores():
+    """OpenMP threads = the cores this process may run on, whatever OMP_NUM_THREADS says (torchrun sets it to 1)"""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    lib().orc_set_num_threads(C.c_int(cores))
+    return num_threads()
+
+
 def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 

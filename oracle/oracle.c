@@ -26,6 +26,16 @@
 #include <omp.h>
 #endif
 
+/* torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU baseline is meant to use all host cores */
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void)
 {
 #ifdef _OPENMP
