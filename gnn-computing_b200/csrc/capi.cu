@@ -819,7 +819,7 @@ int gnnagg_gcn_layer(gnnagg_aggregator *a, const float *X, const float *W, float
     if (int rc = gcn_run_impl(a, X, ax, feat_in, scheduled, (cudaStream_t)stream, false)) return rc;
     if (a->n > 0) {
         if (int rc = dense_nn_launch(ax, W, H, a->n, feat_out, feat_in, stream)) return rc;
-        ++a->launches;
+        a->launches += 2;  // split_w_kernel + dense_tf32x3_ws_kernel
     }
     PROF_RECORD(a, 4, (cudaStream_t)stream);
     return GNNAGG_OK;
@@ -835,7 +835,7 @@ int gnnagg_mlp_run(gnnagg_aggregator *a, const float *X, const float *W, float *
     if (int rc = ensure(a->ax, a->ax_cap, (size_t)a->n * feat)) return rc;
     PROF_RECORD(a, 0, st);
     if (int rc = dense_nn_launch(X, W, a->ax, a->n, feat, feat, stream)) return rc;  // P = X W, once per call
-    ++a->launches;
+    a->launches += 2;  // split_w_kernel + dense_tf32x3_ws_kernel
     if (a->prof) {
         CUDA_TRY(cudaEventRecord(a->ev[1], st));
         CUDA_TRY(cudaEventRecord(a->ev[2], st));
@@ -1232,7 +1232,7 @@ static int gcn_host_pipeline(gnnagg_aggregator *a, const float *h_X, const float
         if (int rc = gcn_run_impl(a, a->st_in, agg_out, feat_in, scheduled, st, !layer)) return rc;
         if (layer && a->n > 0) {
             if (int rc = dense_nn_launch(a->ax, a->st_w, a->st_out, a->n, feat_out, feat_in, st)) return rc;
-            ++a->launches;
+            a->launches += 2;  // split_w_kernel + dense_tf32x3_ws_kernel
         }
         CUDA_TRY(cudaMemcpyAsync(h_out, a->st_out, cout * sizeof(float), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
@@ -1299,7 +1299,7 @@ static int gcn_host_pipeline(gnnagg_aggregator *a, const float *h_X, const float
             if (int rc = dense_nn_launch(a->ax + (size_t)r0 * feat_in, a->st_w, a->st_out + (size_t)r0 * fo, r1 - r0, feat_out,
                                          feat_in, st))
                 return rc;
-            ++a->launches;
+            a->launches += 2;  // split_w_kernel + dense_tf32x3_ws_kernel
         }
         CUDA_TRY(cudaEventRecord(a->chunk_done[c], st));
         CUDA_TRY(cudaStreamWaitEvent(a->copy_stream, a->chunk_done[c], 0));

@@ -12,7 +12,7 @@ TOL = 1e-5
 
 @pytest.mark.parametrize("M,K,N", [(128, 32, 32), (1, 128, 128), (300, 128, 128), (1000, 64, 256), (777, 256, 64),
                                    (513, 256, 256), (4096, 128, 32), (129, 96, 160), (4097, 256, 128), (300, 128, 256),
-                                   (70000, 256, 256), (1, 192, 224)])
+                                   (70000, 256, 256), (1, 192, 224), (100000, 128, 128), (60000, 32, 32), (50000, 64, 224)])
 def test_dense_nn_parity(gn, orc, cuda, M, K, N):
     rng = np.random.default_rng(M + K + N)
     A = rng.standard_normal((M, K)).astype(np.float32)

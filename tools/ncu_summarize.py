@@ -27,9 +27,9 @@ CAPTURES = {
     "agg": ("aggregation kernel, reddit-shaped R-MAT, F=128 (headline workload)", "reddit_gcn_layer_128"),
     "agg_uniform": ("same kernel, uniformly random sources (cache-hostile context run)", "reddit_gcn_layer_128_uniform"),
     "fixup": ("carry fix-up kernels of the headline workload", None),
-    "dense": ("resident-W tcgen05 3xTF32 combination, 232,965 x 128 x 128", None),
+    "dense": ("warp-specialised tcgen05 3xTF32 combination (W resident), 232,965 x 128 x 128", None),
     "agg_products": ("aggregation kernel, products-shaped R-MAT, F=256", "products_gcn_layer_256"),
-    "dense_stream": ("streamed-W tcgen05 3xTF32 combination, 2,449,029 x 256 x 256", None),
+    "dense_stream": ("warp-specialised tcgen05 3xTF32 combination (W streamed), 2,449,029 x 256 x 256", None),
     "agg_proteins": ("aggregation kernel, proteins-shaped R-MAT, F=64", "proteins_gcn_layer_64"),
     "agg_arxiv": ("aggregation kernel, arxiv-shaped R-MAT, F=32", "arxiv_gcn_layer_32"),
     "gat": ("fused GAT aggregation, proteins-shaped R-MAT, F=64", None),
