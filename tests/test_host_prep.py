@@ -161,3 +161,40 @@ if given is not None:
         assert sorted(got[3].tolist()) == val.tolist()
         sizes = np.diff(got[0])
         assert sizes.size == 0 or (sizes.min() >= 1 and sizes.max() <= ng)
+
+
+def test_loader_text_variants_and_parallel_parse(gn, orc, tmp_path):
+    """what fscanf("%d") accepts: any whitespace, everything on one line, tokens after the last needed one; a file big
+    enough for the multi-threaded parser (> 1 MiB) against the oracle's fscanf loader; garbage and short files fail"""
+    d = str(tmp_path) + "/"
+
+    def put(name, cfg, graph):
+        (tmp_path / (name + ".config")).write_text(cfg)
+        (tmp_path / (name + ".graph")).write_text(graph)
+
+    put("a", "3 4", "  0\t1\r\n3 4\n\n2 0 1 2 ")
+    put("b", "3 4", "0 1 3 4 2 0 1 2 9 9")
+    for name in ("a", "b"):
+        ptr, idx, _, _ = gn.load_graph(name, d)
+        assert ptr.tolist() == [0, 1, 3, 4] and idx.tolist() == [2, 0, 1, 2]
+    put("c", "3 4", "0 1 3 4\n2 0 x 2")
+    put("e", "3 4", "0 1 3 4\n2 0 1")
+    for name in ("c", "e"):
+        with pytest.raises(gn.GnnaggError):
+            gn.load_graph(name, d)
+        assert not (tmp_path / (name + ".graph.edgedump")).exists()  # nothing cached from a bad file
+    from gnnagg import synth
+
+    ptr, idx = synth.small_random_csr(40000, 12.0, 2)
+    ptr, idx = ptr.astype(np.int32), idx.astype(np.int32)
+    gn.write_graph("big", ptr, idx, d)
+    assert (tmp_path / "big.graph").stat().st_size > (1 << 20)
+    p1, i1, _, _ = gn.load_graph("big", d)                 # text, written by the fast formatter
+    assert np.array_equal(p1, ptr) and np.array_equal(i1, idx)
+    (tmp_path / "big.graph.ptrdump").unlink()               # pointer line from the text again, edges from the dump
+    p2, i2, _, _ = gn.load_graph("big", d)
+    assert np.array_equal(p2, ptr) and np.array_equal(i2, idx)
+    (tmp_path / "big.graph.ptrdump").unlink()
+    (tmp_path / "big.graph.edgedump").unlink()
+    o_ptr, o_idx = orc.load_graph(d, "big")[:2]             # the oracle's fscanf restatement reads the same file
+    assert np.array_equal(o_ptr, ptr) and np.array_equal(o_idx, idx)
