@@ -272,26 +272,43 @@ extern "C" int gnnagg_lsh_reorder(const int *ptr, const int *idx, int num_v, int
     auto makenum = [numv](int a, int b) -> uint64_t {
         return a <= b ? (uint64_t)a * (uint64_t)numv + (uint64_t)b : (uint64_t)b * (uint64_t)numv + (uint64_t)a;
     };
-    std::vector<Pair> scored(keys.size());
+    // Initial pairs carry their index into `keys` in p1 and p2 = -1 until they are popped (their endpoints are lo/hi).
+    const size_t npairs = keys.size();
+    if (npairs > (size_t)INT32_MAX) return set_error(GNNAGG_ERR_ARG, "gnnagg_lsh_reorder: more than 2^31 candidate pairs");
+    std::vector<Pair> scored(npairs);
 #pragma omp parallel for schedule(dynamic, 1024)
-    for (int64_t k = 0; k < (int64_t)keys.size(); ++k) {
+    for (int64_t k = 0; k < (int64_t)npairs; ++k) {
         const int a = (int)(keys[k] >> 32), b = (int)(keys[k] & 0xFFFFFFFFu);
-        scored[k] = Pair{R.jaccard(a, b), a, b, a, b};
+        scored[k] = Pair{R.jaccard(a, b), a, b, (int)k, -1};
     }
-    KeySet sset(keys.size());
-    for (uint64_t k : keys) sset.insert(makenum((int)(k >> 32), (int)(k & 0xFFFFFFFFu)));
-    std::vector<uint64_t>().swap(keys);
-    // The queue of cluster2.py is one max-heap.  Its initial content is known up front, so it is sorted once (in
-    // parallel, best pair first) and consumed front to back; only the pairs re-queued during clustering live in a real
-    // heap.  Taking the larger of "next sorted pair" and "heap top" pops exactly the order one big heap would (the
-    // order is total: similarity, then ids), without 14 M cache-missing sift-downs through a 340 MB array.
+    // The queue of cluster2.py is one max-heap plus a set of the pairs currently queued (:70,96,126).  The initial content
+    // is known up front, so it is sorted once (in parallel, best pair first) and consumed front to back; only the pairs
+    // re-queued during clustering live in a real heap.  Taking the larger of "next sorted pair" and "heap top" pops
+    // exactly the order one big heap would (the order is total: similarity, then ids), without 14 M cache-missing
+    // sift-downs through a 340 MB array.  "Is this pair queued?" needs no 14 M-entry hash set either: an initial pair
+    // is queued iff its rank in the sorted run has not been consumed yet (rank_of, found through the sorted, per-vertex
+    // indexed key array), and only re-queued pairs go through a small dynamic set.
     const PairOrder before;
     __gnu_parallel::sort(scored.begin(), scored.end(), [&](const Pair &a, const Pair &b) { return before(b, a); });
+    std::vector<int> rank_of(npairs);
+#pragma omp parallel for schedule(static)
+    for (int64_t r = 0; r < (int64_t)npairs; ++r) rank_of[(size_t)scored[r].p1] = (int)r;
+    std::vector<int64_t> koff((size_t)numv + 1, 0);  // keys of first endpoint a: [koff[a], koff[a+1])
+    for (uint64_t k : keys) ++koff[(size_t)(k >> 32) + 1];
+    for (int i = 0; i < numv; ++i) koff[(size_t)i + 1] += koff[i];
     size_t next_sorted = 0;
+    auto queued_initial = [&](int x, int y) -> bool {
+        const int a = std::min(x, y), b = std::max(x, y);
+        const uint64_t key = ((uint64_t)a << 32) | (uint32_t)b;
+        const uint64_t *lo = keys.data() + koff[a], *hi = keys.data() + koff[(size_t)a + 1];
+        const uint64_t *it = std::lower_bound(lo, hi, key);
+        return it != hi && *it == key && (size_t)rank_of[(size_t)(it - keys.data())] >= next_sorted;
+    };
+    KeySet requeued(1024);
     std::priority_queue<Pair, std::vector<Pair>, PairOrder> heap;  // re-queued root pairs only
     auto put = [&](int p1, int p2) {
         heap.push(Pair{R.jaccard(p1, p2), std::min(p1, p2), std::max(p1, p2), p1, p2});
-        sset.insert(makenum(p1, p2));
+        requeued.insert(makenum(p1, p2));
     };
     lap("jaccard + pair sort");
     if (trace) fprintf(stderr, "[lsh_reorder] scored pairs: %zu\n", scored.size());
@@ -311,12 +328,13 @@ extern "C" int gnnagg_lsh_reorder(const int *ptr, const int *idx, int num_v, int
         Pair top;
         if (heap.empty() || (next_sorted < scored.size() && !before(scored[next_sorted], heap.top()))) {
             top = scored[next_sorted++];  // the sorted run holds the larger (or the only) candidate
+            top.p1 = top.lo, top.p2 = top.hi;
         } else {
             top = heap.top();
             heap.pop();
+            requeued.erase(makenum(top.p1, top.p2));
         }
         int p1 = top.p1, p2 = top.p2;
-        sset.erase(makenum(p1, p2));
         if (p1 == cluster_id[p1] && p2 == cluster_id[p2]) {
             if (deleted[p1] || deleted[p2]) continue;
             // the smaller cluster joins the larger one; on a tie p2 joins p1
@@ -332,7 +350,7 @@ extern "C" int gnnagg_lsh_reorder(const int *ptr, const int *idx, int num_v, int
             p1 = root(p1);
             p2 = root(p2);
             if (deleted[p1] || deleted[p2]) continue;
-            if (p1 != p2 && !sset.contains(makenum(p1, p2))) put(p1, p2);
+            if (p1 != p2 && !requeued.contains(makenum(p1, p2)) && !queued_initial(p1, p2)) put(p1, p2);
         }
     }
 
