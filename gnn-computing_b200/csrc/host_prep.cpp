@@ -8,6 +8,7 @@
 // rescans all m edges per slice).
 #include <sys/stat.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -33,22 +34,55 @@ static inline int slice_of(int src, int w, int par_num, int total)
     return p < par_num ? p : par_num - 1;
 }
 
+// contiguous row blocks with about the same number of edges, one per thread (bounds[0..blocks])
+static int row_blocks(const int *ptr, int num_v, std::vector<int> &bounds)
+{
+    int blocks = 1;
+#ifdef _OPENMP
+    blocks = omp_get_max_threads();
+#endif
+    if (num_v < 4096) blocks = 1;
+    bounds.assign((size_t)blocks + 1, num_v);
+    bounds[0] = 0;
+    const int64_t m = ptr[num_v];
+    for (int t = 1; t < blocks; ++t) {
+        const int64_t target = m * t / blocks;
+        bounds[t] = (int)(std::lower_bound(ptr + bounds[t - 1], ptr + num_v, target) - ptr);
+    }
+    return blocks;
+}
+
 static int build_neighbor_grouping(const int *ptr, const int *idx, int num_v, int num_e, int ng, gnnagg_schedule *s)
 {
-    // groups of row i: ceil(deg/ng)   (graph_schedule.h:100-120)
-    int64_t total = 0;
-    for (int i = 0; i < num_v; ++i) total += ((int64_t)ptr[i + 1] - ptr[i] + ng - 1) / ng;
+    // groups of row i: ceil(deg/ng)   (graph_schedule.h:100-120).  Rows are cut into one block per thread: count the
+    // groups of every block, prefix the counts, fill every block at its offset -- same output as the sequential walk.
+    std::vector<int> bounds;
+    const int blocks = row_blocks(ptr, num_v, bounds);
+    std::vector<int64_t> first((size_t)blocks + 1, 0);
+#pragma omp parallel for schedule(static, 1)
+    for (int t = 0; t < blocks; ++t) {
+        int64_t groups = 0;
+        for (int i = bounds[t]; i < bounds[t + 1]; ++i) groups += ((int64_t)ptr[i + 1] - ptr[i] + ng - 1) / ng;
+        first[(size_t)t + 1] = groups;
+    }
+    for (int t = 0; t < blocks; ++t) first[(size_t)t + 1] += first[t];
+    const int64_t total = first[blocks];
     s->ptr.resize((size_t)total + 1);
     s->target.resize((size_t)total);
-    s->idx.assign(idx, idx + num_e);  // verbatim copy (:123-124)
-    int64_t g = 0;
+    s->idx.resize((size_t)num_e);  // verbatim copy (:123-124)
     s->ptr[0] = 0;
-    for (int i = 0; i < num_v; ++i) {
-        const int end = ptr[i + 1];
-        for (int b = ptr[i]; b < end; b += ng) {
-            s->ptr[g + 1] = (b + ng < end) ? b + ng : end;
-            s->target[g] = i;
-            ++g;
+#pragma omp parallel for schedule(static, 1)
+    for (int t = 0; t < blocks; ++t) {
+        int64_t g = first[t];
+        const int e0 = ptr[bounds[t]], e1 = ptr[bounds[t + 1]];
+        if (e1 > e0) memcpy(s->idx.data() + e0, idx + e0, (size_t)(e1 - e0) * sizeof(int));
+        for (int i = bounds[t]; i < bounds[t + 1]; ++i) {
+            const int end = ptr[i + 1];
+            for (int b = ptr[i]; b < end; b += ng) {
+                s->ptr[g + 1] = (b + ng < end) ? b + ng : end;
+                s->target[g] = i;
+                ++g;
+            }
         }
     }
     return GNNAGG_OK;
@@ -58,30 +92,39 @@ static int build_locality(const int *ptr, const int *idx, const float *val, int 
                           int total_num_v, gnnagg_schedule *s)
 {
     const int w = total_num_v / par_num;
-    // pass 1: edges and groups per slice
-    std::vector<int64_t> slice_edges(par_num, 0), slice_groups(par_num, 0);
-    std::vector<int> cnt(par_num);
-    for (int i = 0; i < num_v; ++i) {
-        std::fill(cnt.begin(), cnt.end(), 0);
-        for (int j = ptr[i]; j < ptr[i + 1]; ++j) {
-            const int p = slice_of(idx[j], w, par_num, total_num_v);
-            if (p >= 0) ++cnt[p];
-        }
-        for (int p = 0; p < par_num; ++p) {
-            slice_edges[p] += cnt[p];
-            // one group per (slice,row) with a hit (:54-57); with neighbour grouping a group closes
-            // every ng hits and the remainder is flushed (:182-190, :202-209)
-            slice_groups[p] += (ng > 0) ? (cnt[p] + ng - 1) / ng : (cnt[p] > 0);
+    std::vector<int> bounds;
+    const int blocks = row_blocks(ptr, num_v, bounds);
+    // pass 1: edges and groups per (row block, slice).  Inside a slice the reference walks the rows in order
+    // (graph_schedule.h:24-63), so block t of slice p starts where blocks 0..t-1 of that slice end.
+    std::vector<int64_t> blk_edges((size_t)blocks * par_num, 0), blk_groups((size_t)blocks * par_num, 0);
+#pragma omp parallel for schedule(static, 1)
+    for (int t = 0; t < blocks; ++t) {
+        std::vector<int> cnt(par_num);
+        int64_t *be = blk_edges.data() + (size_t)t * par_num, *bg = blk_groups.data() + (size_t)t * par_num;
+        for (int i = bounds[t]; i < bounds[t + 1]; ++i) {
+            std::fill(cnt.begin(), cnt.end(), 0);
+            for (int j = ptr[i]; j < ptr[i + 1]; ++j) {
+                const int p = slice_of(idx[j], w, par_num, total_num_v);
+                if (p >= 0) ++cnt[p];
+            }
+            for (int p = 0; p < par_num; ++p) {
+                be[p] += cnt[p];
+                // one group per (slice,row) with a hit (:54-57); with neighbour grouping a group closes
+                // every ng hits and the remainder is flushed (:182-190, :202-209)
+                bg[p] += (ng > 0) ? (cnt[p] + ng - 1) / ng : (cnt[p] > 0);
+            }
         }
     }
-    std::vector<int64_t> edge_cur(par_num), group_cur(par_num);
+    // offsets: slices in order, inside a slice the row blocks in order
+    std::vector<int64_t> edge_at((size_t)blocks * par_num), group_at((size_t)blocks * par_num);
     int64_t te = 0, tg = 0;
-    for (int p = 0; p < par_num; ++p) {
-        edge_cur[p] = te;
-        group_cur[p] = tg;
-        te += slice_edges[p];
-        tg += slice_groups[p];
-    }
+    for (int p = 0; p < par_num; ++p)
+        for (int t = 0; t < blocks; ++t) {
+            edge_at[(size_t)t * par_num + p] = te;
+            group_at[(size_t)t * par_num + p] = tg;
+            te += blk_edges[(size_t)t * par_num + p];
+            tg += blk_groups[(size_t)t * par_num + p];
+        }
     s->ptr.resize((size_t)tg + 1);
     s->target.resize((size_t)tg);
     s->idx.resize((size_t)te);
@@ -89,24 +132,29 @@ static int build_locality(const int *ptr, const int *idx, const float *val, int 
     s->has_val = val != nullptr;
     s->ptr[0] = 0;
     // pass 2: scatter edges to their slice (stable), then close this row's groups in every slice
-    std::vector<int64_t> row_begin(par_num);
-    for (int i = 0; i < num_v; ++i) {
-        for (int p = 0; p < par_num; ++p) row_begin[p] = edge_cur[p];
-        for (int j = ptr[i]; j < ptr[i + 1]; ++j) {
-            const int p = slice_of(idx[j], w, par_num, total_num_v);
-            if (p < 0) continue;
-            s->idx[edge_cur[p]] = idx[j];
-            if (val) s->val[edge_cur[p]] = val[j];
-            ++edge_cur[p];
-        }
-        for (int p = 0; p < par_num; ++p) {
-            const int64_t b = row_begin[p], e = edge_cur[p];
-            if (b == e) continue;
-            const int64_t step = (ng > 0) ? ng : (e - b);
-            for (int64_t q = b; q < e; q += step) {
-                const int64_t g = group_cur[p]++;
-                s->ptr[g + 1] = (int)((q + step < e) ? q + step : e);
-                s->target[g] = i;
+#pragma omp parallel for schedule(static, 1)
+    for (int t = 0; t < blocks; ++t) {
+        std::vector<int64_t> edge_cur(edge_at.begin() + (size_t)t * par_num, edge_at.begin() + (size_t)(t + 1) * par_num);
+        std::vector<int64_t> group_cur(group_at.begin() + (size_t)t * par_num, group_at.begin() + (size_t)(t + 1) * par_num);
+        std::vector<int64_t> row_begin(par_num);
+        for (int i = bounds[t]; i < bounds[t + 1]; ++i) {
+            for (int p = 0; p < par_num; ++p) row_begin[p] = edge_cur[p];
+            for (int j = ptr[i]; j < ptr[i + 1]; ++j) {
+                const int p = slice_of(idx[j], w, par_num, total_num_v);
+                if (p < 0) continue;
+                s->idx[edge_cur[p]] = idx[j];
+                if (val) s->val[edge_cur[p]] = val[j];
+                ++edge_cur[p];
+            }
+            for (int p = 0; p < par_num; ++p) {
+                const int64_t b = row_begin[p], e = edge_cur[p];
+                if (b == e) continue;
+                const int64_t step = (ng > 0) ? ng : (e - b);
+                for (int64_t q = b; q < e; q += step) {
+                    const int64_t g = group_cur[p]++;
+                    s->ptr[g + 1] = (int)((q + step < e) ? q + step : e);
+                    s->target[g] = i;
+                }
             }
         }
     }

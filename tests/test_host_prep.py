@@ -198,3 +198,23 @@ def test_loader_text_variants_and_parallel_parse(gn, orc, tmp_path):
     (tmp_path / "big.graph.edgedump").unlink()
     o_ptr, o_idx = orc.load_graph(d, "big")[:2]             # the oracle's fscanf restatement reads the same file
     assert np.array_equal(o_ptr, ptr) and np.array_equal(o_idx, idx)
+
+
+@pytest.mark.parametrize("kind,kw", [(1, dict(neighbor_num=16)), (0, dict(par_num=5)), (2, dict(par_num=3, neighbor_num=8))])
+def test_schedules_multi_block_builders(gn, orc, kind, kw):
+    """above 4096 rows the host builders cut the rows into one block per thread (count, prefix, fill): same bytes as
+    the oracle's sequential walk, with empty rows, a hub and out-of-range sources in the mix"""
+    from gnnagg import synth
+
+    n = 9000
+    ptr, idx = synth.small_random_csr(n, 9.0, 17, empty_frac=0.25, hub=20000)
+    ptr, idx = ptr.astype(np.int32), idx.astype(np.int32)
+    val = np.random.default_rng(3).standard_normal(len(idx)).astype(np.float32)
+    total = n - 500  # sources >= total belong to no slice and are dropped (graph_schedule.h:37)
+    got = gn.schedule_build(kind, ptr, idx, None if kind == 1 else val, total_num_v=total, **kw)
+    if kind == 1:
+        want = orc.neighbor_grouping(ptr, idx, kw["neighbor_num"]) + (None,)
+    else:
+        want = orc.locality(ptr, idx, kw["par_num"], total, val, neighbor_num=kw.get("neighbor_num", 0))
+    for g, w in zip(got, want):
+        assert (g is None and w is None) or np.array_equal(g, w)
