@@ -1,21 +1,26 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the neighbour-aggregation hot path (BASELINE.json).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME] ...
 
 N = 1 (default): BASELINE.json configs[1] -- the fused GCN layer H = (A X) W, feat 128 -> 128, on the
 synthetic reddit-shaped power-law graph (232,965 vertices / 114,615,891 edges), one B200.
 N > 1 (launched by torch.distributed.run, one rank per GPU): the same layer on a graph that is
 1-D row-partitioned by destination: every rank owns a reddit-shaped row block (232,965 rows,
-114,615,891 edges whose sources span all N*232,965 vertices) and the matching X shard; a step is
-the NCCL all-gather of the source-feature halo over NVLink followed by the local layer (weak scaling).
+114,615,891 edges whose sources span all N*232,965 vertices) and the matching X shard (weak scaling).
+A step = the source-feature halo, pulled from the owners' shards over NVLink peer memory by the library's
+own kernels and overlapped stage by stage with the aggregation (gnnagg_dist_*, csrc/dist.cu), + the local layer.
 
-A "step" = one pass of the layer over the whole graph.  Reported metric: algorithmic GB/s of the
-layer (gather model of SURVEY.md 8(d): 4(n+1) + 8m + 4mF_in + 4nF_out + 4F_inF_out bytes per rank).
-`value`: inputs resident in HBM; `e2e`: the same step through the host-buffer entry point
-(gnnagg_gcn_layer_host at N=1) with pinned HOST X/W/H and the copies inside the timed region.
-`--impl reference`: the reference has no CPU implementation of this path; the arm times
-the scalar CPU port (oracle/) on all host threads on a bounded sample of the same workload.
+Besides the headline, every run also measures BASELINE.json configs[4] -- GCN aggregation feat 64 on the
+R-MAT scale-26 graph (2^26 vertices / 2^30 edges), the whole graph partitioned over the N ranks (strong
+scaling; N = 1 gives the single-GPU base) -- and prints it as the `c5` key; at N > 1 a row sample of both
+results is checked on rank 0 against the fp64 CPU oracle (`parity` keys).
+
+A "step" = one pass of the layer over the whole graph.  Reported metric: algorithmic GB/s of the layer
+(gather model of SURVEY.md 8(d): 4(n+1) + 8m + 4mF_in + 4nF_out + 4F_inF_out bytes per rank).
+`value`: inputs resident in HBM; `e2e`: the same step with pinned HOST X/W/H and the copies inside the timed
+region (gnnagg_gcn_layer_host at N = 1).  `--impl reference`: the reference has no CPU implementation of this
+path; the arm times the scalar CPU port (oracle/) on all host threads on a bounded sample.
 """
 import argparse
 import json
@@ -35,11 +40,13 @@ WORKLOADS = {
     "proteins_gcn_layer_64": ("proteins", 64, 64),
     "products_gcn_layer_256": ("products", 256, 256),
     # BASELINE.json configs[4]: GCN aggregation only on the RMAT scale-26 graph (2^26 vertices / 2^30 edges), the
-    # whole graph 1-D row-partitioned over the N ranks (strong scaling); a step = halo all-gather + aggregation
+    # whole graph 1-D row-partitioned over the N ranks (strong scaling); a step = halo exchange + aggregation
     "rmat26_gcn_agg_64": ("rmat26", 64, None),
     "rmat22_gcn_agg_64": ("rmat22", 64, None),   # down-scaled variant of the same workload
 }
 RMAT_SCALES = {"rmat26": (1 << 26, 1 << 30), "rmat22": (1 << 22, 1 << 26)}
+C5_WORKLOAD = "rmat26_gcn_agg_64"
+NVLINK_PEAK_GBS = 770.0  # measured peer-copy bandwidth per direction per GPU (B200_PROFILING.md); nominal 900
 
 
 def layer_bytes(n, m, fin, fout):
@@ -52,6 +59,11 @@ def layer_bytes(n, m, fin, fout):
 
 def spmm_bytes(n, m, F):
     return 4 * (n + 1) + 8 * m + 4 * m * F + 4 * n * F
+
+
+def compulsory_bytes(n, m, F, n_src=None):
+    """every array once, perfect reuse (SURVEY 8(d) model A)"""
+    return 4 * (n + 1) + 8 * m + 4 * (n if n_src is None else n_src) * F + 4 * n * F
 
 
 class ClockSampler(threading.Thread):
@@ -126,6 +138,389 @@ def cpu_sample(orc, ptr, idx, val, X, W, fin, fout, budget_s):
     return layer_bytes(rows, e, fin, fout) / t / 1e9, t, rows, e
 
 
+def auto_stages(shape, N):
+    """groups of owners the remote part of the halo is pulled and accumulated in (gnnagg_dist_set_graph).  More groups
+    = finer overlap of the pulls with the aggregation but one more read-modify-write pass over the output per group;
+    chosen from the sweeps in profiles/r2_sweep_*.jsonl."""
+    if N <= 1:
+        return 0
+    if shape in RMAT_SCALES:            # 16 edges per output row: the passes over Y are expensive
+        return 1 if N <= 2 else 2
+    return min(N - 1, 3)                # 490 edges per output row: Y passes are cheap, overlap pays
+
+
+class Workload:
+    """one named workload on this rank: graph block, inputs, the step functions"""
+
+    def __init__(self, args, name, N, rank, dev, dist, stages=None, halo=None):
+        import torch
+
+        import gnnagg
+        from gnnagg import synth
+
+        self.args, self.name, self.N, self.rank, self.dev, self.dist = args, name, N, rank, dev, dist
+        shape, fin, fout = WORKLOADS[name]
+        self.shape, self.fin, self.fout = shape, fin, fout
+        self.strong = shape in RMAT_SCALES
+        self.agg_only = fout is None
+        if self.strong:  # one fixed graph, partitioned: per-rank block = total / N
+            n_tot, m_tot = RMAT_SCALES[shape]
+            n, m = n_tot // N, m_tot // N
+            what = "GCN aggregation (CSR SpMM) feat %d on the R-MAT %s graph (%d vertices / %d edges in total), %d rows / %d " \
+                   "edges per GPU" % (fin, shape, n_tot, m_tot, n, m)
+        else:
+            n, m = synth.shape_of(shape)
+            what = "fused GCN layer (CSR SpMM aggregation + dense combination) feat %d->%d on synthetic %s-shaped R-MAT graph, " \
+                   "%d vertices / %d edges per GPU" % (fin, fout, shape, n, m)
+        self.n, self.m, self.src_n = n, m, n * N
+        self.config = {"workload": "%s: %s" % (name, what),
+                       "graph": "rmat(a=.57,b=.19,c=.19,d=.05) seed=123, val=1/sqrt((deg_u+1)(deg_v+1)), X~N(0,1), W~N(0,1)/sqrt(F)",
+                       "partition": "1d-row-by-destination" if N > 1 else "single-gpu",
+                       "scheduled": bool(args.scheduled), "sources": args.sources,
+                       "l2": "flushed between timed steps (256 MiB write) and inputs (idx+val %.0f MB, X %.0f MB) exceed the 126 MB L2"
+                             % (8 * m / 1e6, 4 * n * fin / 1e6)}
+        t0 = time.time()
+        # graph: rank r owns rows [r*n, (r+1)*n) of an (N*n)-vertex R-MAT graph, sources are global ids
+        ptr, idx = synth.rmat_csr(n, m, seed=123, device=dev, src_num_v=self.src_n if N > 1 else None,
+                                  dst_prefix=rank if N > 1 else None)
+        if args.sources == "uniform":
+            idx = torch.randint(0, self.src_n, (m,), device=dev, dtype=torch.int32,
+                                generator=torch.Generator(device=dev).manual_seed(99 + rank))
+        deg = (ptr[1:] - ptr[:-1]).to(torch.float32)
+        if N > 1:
+            deg_all = torch.empty(self.src_n, device=dev)
+            dist.all_gather_into_tensor(deg_all, deg)
+            val = synth.gcn_norm_val(ptr, idx, src_deg=deg_all)
+            del deg_all
+        else:
+            val = synth.gcn_norm_val(ptr, idx)
+        self.ptr, self.idx, self.val = ptr, idx, val
+        g = torch.Generator(device=dev).manual_seed(123 + rank)
+        self.Xs = torch.randn((n, fin), device=dev, generator=g)          # this rank's X shard
+        self.W = torch.randn((fin, fout or fin), device=dev, generator=torch.Generator(device=dev).manual_seed(7)) / fin ** 0.5
+        self.H = torch.empty((n, fout or fin), device=dev)
+        self.ph = self.agg = self.nccl = self.Xfull = None
+        self.halo = "none"
+        if N > 1:
+            self._setup_multi(stages, halo or args.halo)
+        else:
+            self.agg = gnnagg.Aggregator(ptr, idx, val)
+            if args.scheduled:
+                self.agg.schedule(gnnagg.SCHED_NEIGHBOR_GROUPING, [32])
+        torch.cuda.synchronize()
+        self.setup_s = time.time() - t0
+        self.hX = self.hW = self.hH = None
+
+    # -------------------------------------------------------------- multi-GPU set-up
+    def _setup_multi(self, stages, halo):
+        import torch
+
+        import gnnagg
+        from gnnagg.partition import PeerHalo, PrunedHalo
+
+        N, rank, dev, dist = self.N, self.rank, self.dev, self.dist
+        n, fin = self.n, self.fin
+        self.stages = stages if stages else (self.args.stages or auto_stages(self.shape, N))
+        err = ""
+        if halo in ("auto", "peer"):
+            try:
+                self.ph = PeerHalo(self.ptr, self.idx, self.val, [r * n for r in range(N + 1)], rank, N, fin, remote_stages=self.stages)
+                ok = 1
+            except Exception as e:  # e.g. cudaIpcOpenMemHandle not permitted in this container
+                ok, err = 0, "%s: %s" % (type(e).__name__, e)
+            t = torch.tensor([ok], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            if int(t.item()) == 1:
+                self.halo = "peer"
+                self.ph.x(0, fin).copy_(self.Xs)
+                self.config["halo"] = (
+                    "peer memory: each rank pulls the %.1f%% of X its block references (rank 0: %d distinct remote rows) straight "
+                    "from the owners' shards with 128-bit loads over NVLink (cudaIpc mappings, no NCCL in the step); %d remote "
+                    "stage(s) accumulated as their owners land, stage 0 = local sources" % (
+                        100.0 * (self.ph.num_recv + 0.0) / self.src_n, self.ph.num_recv, self.ph.num_stages - 1))
+                return
+            if self.ph is not None:
+                self.ph = None
+            if halo == "peer":
+                raise RuntimeError("peer-memory halo unavailable on some rank (%s)" % (err or "another rank failed"))
+        # NCCL paths (round-1 code, kept as the fallback when peer mappings are not available)
+        if halo == "auto":
+            frac = torch.tensor([torch.unique(self.idx).numel() / float(self.src_n)], device=dev)
+            dist.broadcast(frac, src=0)
+            halo = "pruned" if float(frac.item()) < 0.7 else "allgather"
+        if halo == "pruned":
+            self.nccl = PrunedHalo(self.ptr, self.idx, self.val, n, N, rank, fin)
+            self.agg = self.nccl.agg
+            self.halo = "nccl-pruned"
+            self.config["halo"] = "NCCL fallback%s: pack kernel + all_to_all_single of the referenced rows (%.1f%% of X on rank 0)" % (
+                (" (%s)" % err) if err else "", 100 * self.nccl.referenced_fraction)
+        else:
+            self.agg = gnnagg.Aggregator(self.ptr, self.idx, self.val)
+            self.Xfull = torch.empty((self.src_n, fin), device=dev)
+            self.halo = "nccl-allgather"
+            self.config["halo"] = "NCCL fallback%s: one all-gather of X, then the layer" % ((" (%s)" % err) if err else "")
+
+    # -------------------------------------------------------------- steps
+    def step(self, exchange=True):
+        sched = bool(self.args.scheduled)
+        if self.ph is not None:
+            if self.agg_only:
+                self.ph.gcn_run(self.H, 0, self.fin, exchange=exchange)
+            else:
+                self.ph.gcn_layer(self.W, self.H, 0, exchange=exchange)
+            return
+        x = self.Xs
+        if self.nccl is not None:
+            x = self.nccl.exchange(self.Xs) if exchange else self.nccl.recv_buf
+        elif self.Xfull is not None:
+            if exchange:
+                self.dist.all_gather_into_tensor(self.Xfull, self.Xs)
+            x = self.Xfull
+        if self.agg_only:
+            self.agg.gcn_run(x, self.H, scheduled=sched)
+        else:
+            self.agg.gcn_layer(x, self.W, self.H, None, scheduled=sched)
+
+    def host_buffers(self):
+        import torch
+
+        if self.hX is None:
+            self.hX = torch.empty((self.n, self.fin), pin_memory=True).copy_(self.Xs)
+            self.hW = torch.empty((self.fin, self.fout or self.fin), pin_memory=True).copy_(self.W)
+            self.hH = torch.empty((self.n, self.fout or self.fin), pin_memory=True)
+
+    def step_e2e(self):
+        import torch
+
+        sched = bool(self.args.scheduled)
+        if self.N == 1 and self.agg_only:
+            self.agg.gcn_run_host(self.hX, self.hH, scheduled=sched)
+        elif self.N == 1:
+            self.agg.gcn_layer_host(self.hX, self.hW, self.hH, scheduled=sched)  # H2D + layer + D2H + sync inside
+        else:
+            dst = self.ph.x(0, self.fin) if self.ph is not None else self.Xs
+            dst.copy_(self.hX, non_blocking=True)
+            self.step()
+            self.hH.copy_(self.H, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    def copies_only(self):
+        """the two host copies of step_e2e alone (what PCIe / the host memory system allows on this box at this N)"""
+        import torch
+
+        dst = self.ph.x(0, self.fin) if self.ph is not None else self.Xs
+        dst.copy_(self.hX, non_blocking=True)
+        self.hH.copy_(self.H, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def launch_count(self):
+        if self.ph is not None:
+            return self.ph.launches
+        return self.agg.launches
+
+    def close(self):
+        if self.ph is not None:
+            self.ph.close()
+        self.ph = self.agg = self.nccl = self.Xfull = None
+
+
+def make_timer(dev, dist, sampler, flush):
+    import torch
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, after_step=None):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        if sampler is not None:
+            sampler.active = True
+        for a, b in evs:
+            flush.fill_(1)  # L2 flush, outside the timed events
+            a.record()
+            fn()
+            b.record()
+            if after_step is not None:
+                after_step()
+        barrier()
+        if sampler is not None:
+            sampler.active = False
+        total_ms = sum(a.elapsed_time(b) for a, b in evs)
+        if dist is not None:
+            t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t.item())
+        return total_ms / steps
+
+    return timed, barrier
+
+
+def max_over_ranks(x, dev, dist):
+    import torch
+
+    if dist is None:
+        return float(x)
+    t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def measure(wl, timed, steps, warmup, e2e=True):
+    """times one workload: step, kernels-only step, exchange span, (optionally) end-to-end.  Collective: every rank
+    calls it."""
+    import numpy as np
+
+    out = {}
+    prof = []
+    l0 = wl.launch_count()
+    if wl.ph is not None:
+        wl.ph.profile(True)
+        ms = timed(wl.step, steps, warmup, after_step=lambda: prof.append(wl.ph.profile_read()))
+        wl.ph.profile(False)
+    elif wl.N == 1:
+        wl.agg.profile(True)
+        ms = timed(wl.step, steps, warmup, after_step=lambda: prof.append(wl.agg.profile_read()))
+        wl.agg.profile(False)
+    else:
+        ms = timed(wl.step, steps, warmup)
+    out["launches_per_step"] = (wl.launch_count() - l0) / float(steps + warmup)
+    out["ms"] = ms
+    out["prof"] = {k: float(np.mean([p[k] for p in prof])) for k in prof[0]} if prof else {}
+    if wl.N > 1:
+        out["compute_ms"] = timed(lambda: wl.step(exchange=False), max(3, steps // 2), 2)
+        if wl.ph is not None:
+            out["exchange_ms"] = max_over_ranks(out["prof"]["exchange"], wl.dev, wl.dist)
+            wl.ph.check()
+    if e2e:
+        wl.host_buffers()
+        out["ms_e2e"] = timed(wl.step_e2e, max(3, steps // 2), 3)
+        if wl.N > 1:
+            out["ms_copies"] = timed(wl.copies_only, 3, 1)
+    return out
+
+
+def parity_check(wl, max_rows=1024, max_edges=3_000_000):
+    """rank 0 checks a sample of its output rows against the fp64 CPU oracle.  The source rows the sample needs are
+    fetched from their owners with plain NCCL send/recv (independent of the library's halo path).  Collective."""
+    import numpy as np
+    import torch
+
+    dev, dist, N, rank, n, fin = wl.dev, wl.dist, wl.N, wl.rank, wl.n, wl.fin
+    wl.step()  # a fresh result from the path under test
+    torch.cuda.synchronize()
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    if rank == 0:
+        ptr, idx, val = wl.ptr, wl.idx, wl.val
+        deg_all = (ptr[1:] - ptr[:-1]).long()
+        hub = int(torch.argmax(deg_all).item())
+        rows = torch.unique(torch.cat([torch.linspace(0, n - 1, max_rows, device=dev).long(), torch.tensor([hub], device=dev)]))
+        deg = deg_all[rows]
+        keep = torch.cumsum(deg, 0) <= max_edges
+        keep[0] = True
+        rows, deg = rows[keep], deg[keep]
+        sub_ptr = torch.zeros(rows.numel() + 1, dtype=torch.int64, device=dev)
+        sub_ptr[1:] = torch.cumsum(deg, 0)
+        e_tot = int(sub_ptr[-1].item())
+        eid = torch.arange(e_tot, device=dev) - torch.repeat_interleave(sub_ptr[:-1], deg) + torch.repeat_interleave(ptr[rows].long(), deg)
+        g_src = idx[eid].long()
+        U = torch.unique(g_src)
+        sub_idx = torch.searchsorted(U, g_src).to(torch.int32)
+        sub_val = val[eid]
+        count[0] = U.numel()
+    if dist is not None:
+        dist.broadcast(count, src=0)
+        Ub = U if rank == 0 else torch.empty(int(count.item()), dtype=torch.int64, device=dev)
+        dist.broadcast(Ub, src=0)
+        owner = torch.div(Ub, n, rounding_mode="floor")
+        mine = Ub[owner == rank] - rank * n
+        send = wl.Xs[mine].contiguous()
+        if rank == 0:
+            Xsub = torch.empty((Ub.numel(), fin), device=dev)
+            counts = torch.bincount(owner, minlength=N).tolist()
+            off = 0
+            for r in range(N):
+                if r == 0:
+                    Xsub[off:off + counts[0]] = send
+                elif counts[r]:
+                    dist.recv(Xsub[off:off + counts[r]], src=r)
+                off += counts[r]
+        elif send.numel():
+            dist.send(send, dst=0)
+    else:
+        Xsub = wl.Xs[U]
+    res = None
+    if rank == 0:
+        import oracle as orc
+
+        orc.use_all_cores()
+        hp, hi, hv = sub_ptr.to(torch.int32).cpu().numpy(), sub_idx.cpu().numpy(), sub_val.cpu().numpy()
+        got = wl.H[rows].cpu().numpy().astype(np.float64)
+        if wl.agg_only:
+            y64, scale = orc.spmm_f64(hp, hi, hv, Xsub.cpu().numpy())
+        else:
+            _, y64, scale = orc.gcn_layer_f64(hp, hi, hv, Xsub.cpu().numpy(), wl.W.cpu().numpy())
+        err = np.abs(got - y64.astype(np.float64)) / (1e-5 * scale.astype(np.float64) + 1e-30)
+        res = {"rows": int(rows.numel()), "edges": e_tot, "includes_max_degree_row": True,
+               "worst_err_over_bound": round(float(err.max()), 4), "tolerance": "|y - y_fp64| <= 1e-5 * sum|terms|",
+               "ok": bool(err.max() <= 1.0),
+               "checked": "rank 0's output rows against oracle/oracle.c (fp64) with source rows fetched from their owners by NCCL send/recv"}
+    if dist is not None:
+        dist.barrier()
+    return res
+
+
+def c5_block(args, N, rank, dev, dist, timed, steps, warmup):
+    """BASELINE.json configs[4] on the same ranks, after the headline.  Collective."""
+    import torch
+
+    stage_list = [int(s) for s in args.c5_sweep.split(",")] if args.c5_sweep else [0]
+    best = None
+    for st in stage_list:
+        wl = Workload(args, C5_WORKLOAD, N, rank, dev, dist, stages=st or None)
+        r = measure(wl, timed, steps, warmup, e2e=False)
+        par = parity_check(wl) if N > 1 else None
+        nbytes = N * spmm_bytes(wl.n, wl.m, wl.fin)
+        d = {"workload": wl.config["workload"], "scaling": "strong", "ms_per_step": round(r["ms"], 4),
+             "value": round(nbytes / (r["ms"] * 1e-3) / 1e9, 1), "unit": "GB/s", "steps": steps, "warmup": warmup,
+             "edges_feat_per_s": round(N * wl.m * wl.fin / (r["ms"] * 1e-3), 1), "setup_s": round(wl.setup_s, 2),
+             "gpu_launches_per_step": round(r["launches_per_step"], 1)}
+        if N > 1:
+            d["halo"] = wl.config.get("halo")
+            d["compute_only_ms"] = round(r["compute_ms"], 4)
+            d["exposed_exchange_ms"] = round(r["ms"] - r["compute_ms"], 4)
+            if wl.ph is not None:
+                ex_bytes = wl.ph.num_recv * wl.fin * 4
+                d["remote_stages"] = wl.ph.num_stages - 1
+                d["bytes_exchanged_per_rank"] = ex_bytes
+                d["exchange_ms"] = round(r["exchange_ms"], 4)
+                d["nvlink_GBps_per_rank"] = round(ex_bytes / (r["exchange_ms"] * 1e-3) / 1e9, 1) if r["exchange_ms"] > 0 else None
+                d["nvlink_frac_of_770"] = round(d["nvlink_GBps_per_rank"] / NVLINK_PEAK_GBS, 3) if d["nvlink_GBps_per_rank"] else None
+            d["parity"] = par
+            base = None
+            try:
+                base = json.load(open(os.path.join(ROOT, "profiles", "c5_base_1gpu.json")))["ms_per_step"]
+            except Exception:
+                pass
+            d["base_1gpu_ms"] = base
+            d["speedup_vs_1gpu"] = round(base / r["ms"], 3) if base else None
+            d["base_source"] = "profiles/c5_base_1gpu.json (the N=1 `c5` value of this bench on the same pool)" if base else None
+        else:
+            d["kernel_ms"] = round(r["prof"].get("agg", 0.0), 4)
+            d["note"] = "single-GPU base of the strong-scaling series"
+        if len(stage_list) > 1 and rank == 0:
+            print(json.dumps({"c5_sweep": d}), flush=True)
+        if best is None or d["ms_per_step"] < best["ms_per_step"]:
+            best = d
+        wl.close()
+        del wl
+        torch.cuda.empty_cache()
+    return best
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -138,11 +533,15 @@ def main():
     ap.add_argument("--sources", default="rmat", choices=["rmat", "uniform"],
                     help="rmat: the R-MAT source distribution of the workload definition (default, headline); uniform: same "
                          "degree sequence but uniformly random sources -- the cache-hostile extreme, reported as context")
-    ap.add_argument("--halo", default="auto", choices=["auto", "allgather", "pruned"],
-                    help="N>1: all-gather the whole X, or exchange only the referenced source rows (all-to-all). "
-                         "auto = pruned for the partitioned R-MAT graph, all-gather otherwise")
-    ap.add_argument("--pipeline", type=int, default=0,
-                    help="N>1: number of row chunks of the pipelined halo all-gather (0 = one all-gather, then the layer)")
+    ap.add_argument("--halo", default="auto", choices=["auto", "peer", "pruned", "allgather"],
+                    help="N>1: peer = the library's own NVLink peer-memory exchange (default); pruned / allgather = the NCCL "
+                         "paths of round 1 (also the automatic fallback when peer mappings cannot be opened)")
+    ap.add_argument("--stages", type=int, default=0, help="N>1, peer halo: remote stages (0 = automatic)")
+    ap.add_argument("--sweep", default="", help="N>1: comma-separated remote-stage counts to time on the headline workload")
+    ap.add_argument("--c5", type=int, default=-1, help="1/0: also measure the RMAT-26 strong-scaling config (default: only "
+                                                        "with the default workload)")
+    ap.add_argument("--c5-sweep", default="", help="comma-separated remote-stage counts for the c5 block")
+    ap.add_argument("--ref-kernels", type=int, default=1, help="N=1: time the reference's own kernels (oracle/_ref) after the headline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -155,25 +554,11 @@ def main():
     if world != args.gpus and world > 1:
         args.gpus = world
     shape, fin, fout = WORKLOADS[args.workload]
+    do_c5 = (args.workload == "reddit_gcn_layer_128" and not args.scheduled and args.sources == "rmat") if args.c5 < 0 else bool(args.c5)
 
     from gnnagg import synth
 
     strong = shape in RMAT_SCALES
-    if strong:  # one fixed graph, partitioned: per-rank block = total / N
-        n_tot, m_tot = RMAT_SCALES[shape]
-        n, m = n_tot // args.gpus, m_tot // args.gpus
-        what = "GCN aggregation (CSR SpMM) feat %d on the R-MAT %s graph (%d vertices / %d edges in total), %d rows / %d edges per GPU" % (
-            fin, shape, n_tot, m_tot, n, m)
-    else:
-        n, m = synth.shape_of(shape)
-        what = "fused GCN layer (CSR SpMM aggregation + dense combination) feat %d->%d on synthetic %s-shaped R-MAT graph, " \
-               "%d vertices / %d edges per GPU" % (fin, fout, shape, n, m)
-    config = {"workload": "%s: %s" % (args.workload, what),
-              "graph": "rmat(a=.57,b=.19,c=.19,d=.05) seed=123, val=1/sqrt((deg_u+1)(deg_v+1)), X~N(0,1), W~N(0,1)/sqrt(F)",
-              "partition": "1d-row-by-destination" if args.gpus > 1 else "single-gpu",
-              "scheduled": bool(args.scheduled), "sources": args.sources,
-              "l2": "flushed between timed steps (256 MiB write) and inputs (idx+val %.0f MB, X %.0f MB) exceed the 126 MB L2"
-                    % (8 * m / 1e6, 4 * n * fin / 1e6)}
 
     # ------------------------------------------------------------------ reference arm (CPU port)
     if args.impl == "reference":
@@ -182,13 +567,19 @@ def main():
         import oracle as orc
 
         orc.use_all_cores()  # rank 0 alone runs this arm: every host core, also under torchrun (OMP_NUM_THREADS=1 there)
-
+        if strong:
+            n_tot, m_tot = RMAT_SCALES[shape]
+            n, m = n_tot // args.gpus, m_tot // args.gpus
+        else:
+            n, m = synth.shape_of(shape)
+        config = {"workload": "%s (rank 0's block of the same synthetic graph)" % args.workload, "partition":
+                  "1d-row-by-destination" if args.gpus > 1 else "single-gpu", "scheduled": bool(args.scheduled), "sources": args.sources}
         dev = torch.device("cuda:%d" % local_rank) if torch.cuda.is_available() else torch.device("cpu")
         # the same graph; a leading row block is what gets timed, so only that block is built when no GPU is around
         gen_rows, gen_edges = (n, m) if dev.type == "cuda" else (n, min(m, 4_000_000))
-        src_total = n * args.gpus if strong else n  # the reference arm always times rank 0's block
-        ptr, idx = synth.rmat_csr(gen_rows, gen_edges, seed=123, device=dev, src_num_v=src_total if strong and args.gpus > 1 else None,
-                                  dst_prefix=0 if strong and args.gpus > 1 else None)
+        src_total = n * args.gpus
+        ptr, idx = synth.rmat_csr(gen_rows, gen_edges, seed=123, device=dev, src_num_v=src_total if args.gpus > 1 else None,
+                                  dst_prefix=0 if args.gpus > 1 else None)
         val = synth.gcn_norm_val(ptr, idx) if src_total == n else torch.rand(idx.numel(), device=dev) + 0.5
         g = torch.Generator(device=dev).manual_seed(123)
         X = torch.randn((src_total, fin), device=dev, generator=g)
@@ -210,10 +601,11 @@ def main():
         gbs = layer_bytes(rows, e, fin, fout) / t_mean / 1e9
         sample = "rows [0,%d) of the workload graph = %d edges (%.2f%% of m), scalar fp32 CSR port + fp32 GEMM, OpenMP" % (
             rows, e, 100.0 * e / m)
-        line = {"impl": "reference", "metric": "gcn_layer_algorithmic_GBps", "value": round(gbs, 3), "unit": "GB/s",
+        line = {"impl": "reference", "metric": "gcn_aggregation_algorithmic_GBps" if fout is None else "gcn_layer_algorithmic_GBps",
+                "value": round(gbs, 3), "unit": "GB/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t_mean * 1e3, 3),
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": config,
+                "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": round(gbs, 3), "unit": "GB/s", "cores": orc.num_threads(), "kind": "port",
                                  "sample": sample},
                 "e2e": {"value": round(gbs, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -224,7 +616,7 @@ def main():
 
     # ------------------------------------------------------------------ our arm
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU port"
-    import gnnagg
+    import gnnagg  # noqa: F401  (fails loudly when libgnnagg.so is missing)
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda:%d" % local_rank)
@@ -234,234 +626,224 @@ def main():
 
         dist.init_process_group("nccl", device_id=dev)
     N = args.gpus
-    src_n = n * N
-
-    # graph: rank r owns rows [r*n, (r+1)*n) of an (N*n)-vertex R-MAT graph, sources are global ids
-    t0 = time.time()
-    ptr, idx = synth.rmat_csr(n, m, seed=123, device=dev, src_num_v=src_n if N > 1 else None,
-                              dst_prefix=rank if N > 1 else None)
-    if args.sources == "uniform":
-        idx = torch.randint(0, src_n, (m,), device=dev, dtype=torch.int32,
-                            generator=torch.Generator(device=dev).manual_seed(99 + rank))
-    deg = (ptr[1:] - ptr[:-1]).to(torch.float32)
-    if N > 1:
-        deg_all = torch.empty(src_n, device=dev)
-        dist.all_gather_into_tensor(deg_all, deg)
-        val = synth.gcn_norm_val(ptr, idx, src_deg=deg_all)
-        del deg_all
-    else:
-        val = synth.gcn_norm_val(ptr, idx)
-    g = torch.Generator(device=dev).manual_seed(123 + rank)
-    Xs = torch.randn((n, fin), device=dev, generator=g)          # this rank's X shard
-    agg_only = fout is None
-    W = torch.randn((fin, fout or fin), device=dev, generator=torch.Generator(device=dev).manual_seed(7)) / fin ** 0.5
-    halo = args.halo
-    if halo == "auto" and args.gpus > 1:
-        # exchange only the referenced source rows when that is clearly less than X (decided from the data, identically
-        # on every rank: the fraction of rank 0 is broadcast)
-        import torch.distributed as dist0
-
-        frac = torch.tensor([torch.unique(idx).numel() / float(src_n)], device=dev)
-        dist0.broadcast(frac, src=0)
-        halo = "pruned" if float(frac.item()) < 0.7 else "allgather"
-    elif halo == "auto":
-        halo = "allgather"
-    pruned = N > 1 and halo == "pruned" and not args.scheduled
-    pipelined = N > 1 and args.pipeline > 0 and not args.scheduled and not pruned
-    Xfull = torch.empty((src_n, fin), device=dev) if (N > 1 and not pipelined and not pruned) else Xs
-    H = torch.empty((n, fout or fin), device=dev)
-    ph = None
-    if pruned:
-        from gnnagg.partition import PrunedHalo
-
-        if args.pipeline > 0:
-            from gnnagg.partition import PipelinedPrunedHalo
-
-            ph = PipelinedPrunedHalo(ptr, idx, val, n, N, rank, fin, chunks=args.pipeline)
-            agg = ph.aggs[0]
-            config["halo"] = "pruned + pipelined: %d row chunks, chunk c fetches only the referenced source rows no earlier chunk " \
-                             "fetched (all-to-all per chunk, %.1f%% of X on rank 0, stage shares %s) while chunk c-1 is aggregated" % (
-                                 args.pipeline, 100 * ph.referenced_fraction, [round(f, 2) for f in ph.stage_fraction])
-        else:
-            ph = PrunedHalo(ptr, idx, val, n, N, rank, fin)
-            agg = ph.agg
-            config["halo"] = "pruned: only referenced source rows travel (all-to-all, %.1f%% of X on rank 0), CSR re-indexed " \
-                             "into the compact receive buffer" % (100 * ph.referenced_fraction)
-    else:
-        agg = gnnagg.Aggregator(ptr, idx, val)
-    if args.scheduled:
-        agg.schedule(gnnagg.SCHED_NEIGHBOR_GROUPING, [32])
-    pipe = AX = None
-    AXp = torch.empty((n, fin), device=dev) if (pruned and args.pipeline > 0 and not agg_only) else None
-    if pipelined:
-        from gnnagg.partition import HaloPipeline
-
-        pipe = HaloPipeline(ptr, idx, val, n, N, rank, fin, chunks=args.pipeline)
-        AX = torch.empty((n, fin), device=dev)
-        config["halo"] = "all-gather cut into %d row chunks, sub-CSR of chunk c accumulated while chunk c+1 is in flight; " \
-                         "edges with local sources first" % args.pipeline
-    elif N > 1 and not pruned:
-        config["halo"] = "one NCCL all-gather of X, then the layer"
-    torch.cuda.synchronize()
-    t_setup = time.time() - t0
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-
-    def layer(x_full):
-        if pipelined:
-            pipe.aggregate(Xs, H if agg_only else AX)  # chunked all-gather overlapped with aggregation
-            if not agg_only:
-                gnnagg.dense_nn(AX, W, H)
-        else:
-            if pruned and args.pipeline > 0:
-                ph.aggregate(Xs, H if agg_only else AXp)   # pack, per-chunk all-to-all overlapped with aggregation
-                if not agg_only:
-                    gnnagg.dense_nn(AXp, W, H)
-                return
-            if pruned:
-                x_full = ph.exchange(Xs)                  # pack + all-to-all of the referenced rows
-            elif N > 1:
-                dist.all_gather_into_tensor(Xfull, Xs)   # source-feature halo over NVLink
-            if agg_only:
-                agg.gcn_run(x_full, H, scheduled=bool(args.scheduled))
-            else:
-                agg.gcn_layer(x_full, W, H, None, scheduled=bool(args.scheduled))
-
-    def step():
-        layer(Xfull)
-
-    # host buffers for the end-to-end number
-    hX = torch.empty((n, fin), pin_memory=True).copy_(Xs)
-    hW = torch.empty((fin, fout or fin), pin_memory=True).copy_(W)
-    hH = torch.empty((n, fout or fin), pin_memory=True)
-
-    def step_e2e():
-        if N == 1 and agg_only:
-            agg.gcn_run_host(hX, hH, scheduled=bool(args.scheduled))
-        elif N == 1:
-            agg.gcn_layer_host(hX, hW, hH, scheduled=bool(args.scheduled))  # H2D + layer + D2H + sync inside
-        else:
-            Xs.copy_(hX, non_blocking=True)
-            layer(Xfull)
-            hH.copy_(H, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, warmup, profile=False):
-        for _ in range(warmup):
-            fn()
-        barrier()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        prof = []
-        aggs = pipe.aggs if pipelined else (ph.aggs if (pruned and args.pipeline > 0) else [agg])
-        count = lambda: sum(a.launches for a in aggs)
-        l0 = count()
-        sampler.active = True
-        for a, b in evs:
-            flush.fill_(1)  # L2 flush, outside the timed events
-            a.record()
-            fn()
-            b.record()
-            if profile:
-                reads = [a.profile_read() for a in aggs]
-                prof.append({k: sum(r[k] for r in reads) for k in reads[0]})
-        barrier()
-        sampler.active = False
-        total_ms = sum(a.elapsed_time(b) for a, b in evs)
-        if dist is not None:
-            t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            total_ms = float(t.item())
-        return total_ms / steps, count() - l0 + (steps if (pipelined and not agg_only) else 0), prof  # + the dense launch
-
     sampler = ClockSampler(local_rank)
     sampler.start()
-    prof_aggs = pipe.aggs if pipelined else (ph.aggs if (pruned and args.pipeline > 0) else [agg])
-    for a_ in prof_aggs:
-        a_.profile(True)
-    ms, launches, prof = timed(step, args.steps, args.warmup, profile=True)
-    for a_ in prof_aggs:
-        a_.profile(False)
-    ms_e2e, _, _ = timed(step_e2e, max(3, args.steps // 2), 3)
+    timed, barrier = make_timer(dev, dist, sampler, flush)
+
+    wl = Workload(args, args.workload, N, rank, dev, dist)
+    n, m = wl.n, wl.m
+    agg_only = wl.agg_only
+
+    # optional: remote-stage sweep on the headline workload (builder's tuning runs; one JSON line per setting)
+    if args.sweep and N > 1 and wl.ph is not None:
+        for st in [int(s) for s in args.sweep.split(",")]:
+            w2 = wl if st == wl.ph.num_stages - 1 else Workload(args, args.workload, N, rank, dev, dist, stages=st)
+            r = measure(w2, timed, max(5, args.steps // 2), 3, e2e=False)
+            if rank == 0:
+                print(json.dumps({"sweep": {"workload": args.workload, "n_gpus": N, "remote_stages": st, "ms_per_step": round(r["ms"], 4),
+                                            "compute_only_ms": round(r["compute_ms"], 4), "exchange_ms": round(r["exchange_ms"], 4),
+                                            "nvlink_GBps_per_rank": round(w2.ph.num_recv * fin * 4 / (r["exchange_ms"] * 1e-3) / 1e9, 1),
+                                            "stage_edges": w2.ph.stage_edges}}), flush=True)
+            if w2 is not wl:
+                w2.close()
+                del w2
+                torch.cuda.empty_cache()
+
+    r = measure(wl, timed, args.steps, args.warmup, e2e=True)
     clocks = sampler.result()
+    timed, barrier = make_timer(dev, dist, None, flush)  # the clock sampler covers the headline region only
+    ms, ms_e2e = r["ms"], r["ms_e2e"]
+    parity = parity_check(wl) if N > 1 else None
 
     bytes_rank = layer_bytes(n, m, fin, fout)
     value = N * bytes_rank / (ms * 1e-3) / 1e9
     e2e_value = N * bytes_rank / (ms_e2e * 1e-3) / 1e9
 
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return 0
+    line = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        prof = r["prof"]
+        lpr, nv = (8, 1) if fin <= 32 else (16, 1) if fin <= 64 else (32, 1) if fin <= 128 else (32, 2)
+        if N == 1:
+            agg_ms, total_ms, dense_ms = prof["agg"], prof["total"], prof["dense"]
+            breakdown = {k: round(prof[k], 4) for k in ("agg", "agg_rest", "dense", "total")}
+        else:
+            total_ms = r["compute_ms"]
+            dense_ms = prof.get("dense", 0.0)
+            agg_ms = max(total_ms - dense_ms, 1e-6)  # all stages' aggregation kernels + their fix-ups
+            breakdown = {"aggregation_all_stages": round(agg_ms, 4), "dense": round(dense_ms, 4), "compute_total": round(total_ms, 4),
+                         "stage0_local_sources": round(prof.get("stage0", 0.0), 4)}
+        achieved = spmm_bytes(n, m, fin) / (agg_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "agg_kernel<%d,%d,GCN,%s,%d> (CSR SpMM aggregation)%s" % (
+                        lpr, nv, "sched" if args.scheduled else "csr", 128 if m < 4000000 else 512,
+                        "" if N == 1 else ", %d stage launches per step" % (wl.ph.num_stages if wl.ph is not None else 1)),
+                    "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                    "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": spmm_bytes(n, m, fin), "kernel_ms": round(agg_ms, 4),
+                    "step_breakdown_ms": breakdown,
+                    "note": "gather model (SURVEY 8(d)): one F-float source row per edge, so L1/L2 hits count as bytes: `frac` is an "
+                            "effective-bandwidth figure and exceeds 1 where X (%.0f MB) is cache resident; `frac_dram` is the HBM "
+                            "fraction proper" % (4 * n * fin / 1e6)}
+        if N == 1:
+            try:  # counters of the dominant kernel from the committed `ncu --set full` capture of this very command
+                summ = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
+                key = args.workload + ("_sched" if args.scheduled else "") + ("_uniform" if args.sources == "uniform" else "")
+                s = summ.get(key, {})
+                if s.get("dram_bytes_per_launch"):
+                    roofline["traffic"] = s["dram_bytes_per_launch"]
+                    comp = compulsory_bytes(n, m, fin)
+                    roofline["compulsory_bytes"] = comp
+                    roofline["traffic_over_compulsory"] = round(s["dram_bytes_per_launch"] / comp, 3)
+                    roofline["frac_dram"] = round(s["dram_bytes_per_launch"] / (agg_ms * 1e-3) / 1e9 / peak, 4)
+                units = {k: s[k] for k in ("l1tex_throughput_pct", "lts_throughput_pct", "dram_throughput_pct") if k in s}
+                if units:
+                    top = max(units, key=units.get)
+                    roofline["binding_unit"] = {"unit": top.split("_")[0], "pct_of_peak": units[top]}
+                roofline["ncu"] = {k: s[k] for k in ("l1tex_throughput_pct", "lts_throughput_pct", "dram_GBps", "l2_hit_pct",
+                                                     "l1_hit_pct", "duration_ms", "source") if k in s}
+            except Exception:
+                pass
+        else:
+            roofline["note"] += "; ncu counters are captured at N = 1 only and are not repeated here"
 
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    agg_ms = float(np.mean([p["agg"] for p in prof]))
-    traffic, ncu_units = None, {}
-    try:  # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this workload
-        summ = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
-        key = args.workload + ("_sched" if args.scheduled else "") + ("_uniform" if args.sources == "uniform" else "")
-        traffic = summ.get(key, {}).get("dram_bytes_per_launch")
-        ncu_units = {k: summ[key][k] for k in ("l1tex_throughput_pct", "lts_throughput_pct", "dram_GBps", "l2_hit_pct",
-                                               "l1_hit_pct", "duration_ms", "source") if k in summ.get(key, {})}
-    except Exception:
-        pass
-    achieved = spmm_bytes(n, m, fin) / (agg_ms * 1e-3) / 1e9
-    lpr, nv = (8, 1) if fin <= 32 else (16, 1) if fin <= 64 else (32, 1) if fin <= 128 else (32, 2)
-    roofline = {"bound": "hbm", "kernel": "agg_kernel<%d,%d,GCN,%s,%d> (CSR SpMM aggregation)" % (
-                    lpr, nv, "sched" if args.scheduled else "csr", 128 if m < 4000000 else 512),
-                "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": traffic, "peak_source": peak_src,
-                # which unit binds, from the committed `ncu --set full` capture of this kernel on this workload (percent of
-                # the unit's peak throughput; DRAM in GB/s): the gathers run out of L1/L2, so HBM is not the binding unit here
-                "ncu": ncu_units,
-                "algorithmic_bytes_per_launch": spmm_bytes(n, m, fin), "kernel_ms": round(agg_ms, 4),
-                "step_breakdown_ms": {k: round(float(np.mean([p[k] for p in prof])), 4) for k in ("agg", "agg_rest", "dense", "total")},
-                "note": "gather model: one F-float source row per edge; X (%.0f MB) is L2-resident to a large degree, so this is an "
-                        "effective-bandwidth figure and may exceed the HBM copy peak" % (4 * n * fin / 1e6)}
+        import oracle as orc
 
-    import oracle as orc
+        orc.use_all_cores()
+        # the CPU port on a leading block of rank 0's rows; at N > 1 the sample's sources are re-indexed onto their
+        # own X rows, regenerated from the per-rank seeds (same generator, same device type)
+        if N > 1:
+            hp_full = wl.ptr.cpu()
+            rows_c = int(torch.searchsorted(hp_full, min(int(hp_full[-1]), 40_000_000)).item())
+            e_c = int(hp_full[rows_c])
+            U = torch.unique(wl.idx[:e_c].long())
+            idx_c = torch.searchsorted(U, wl.idx[:e_c].long()).to(torch.int32)
+            Xc = torch.empty((U.numel(), fin), device=dev)
+            for rr in range(N):
+                sel = (U >= rr * n) & (U < (rr + 1) * n)
+                if bool(sel.any()):
+                    shard = torch.randn((n, fin), device=dev, generator=torch.Generator(device=dev).manual_seed(123 + rr))
+                    Xc[sel] = shard[U[sel] - rr * n]
+                    del shard
+            gbs, t_cpu, rows, e = cpu_sample(orc, wl.ptr[: rows_c + 1].contiguous(), idx_c, wl.val[:e_c], Xc, wl.W, fin, fout,
+                                             args.cpu_seconds)
+        else:
+            gbs, t_cpu, rows, e = cpu_sample(orc, wl.ptr, wl.idx, wl.val, wl.Xs, wl.W, fin, fout, args.cpu_seconds)
+        cpu_baseline = {"value": round(gbs, 3), "unit": "GB/s", "cores": orc.num_threads(), "kind": "port",
+                        "sample": "rows [0,%d) = %d edges (%.2f%% of m) of rank 0's graph, %.1f s; scalar fp32 CSR port + fp32 GEMM "
+                                  "(oracle/oracle.c, OpenMP dynamic,64)" % (rows, e, 100.0 * e / m, t_cpu)}
 
-    orc.use_all_cores()
-    if N > 1:  # the CPU port needs the replicated X of rank 0's block
-        g_all = [torch.randn((n, fin), device=dev, generator=torch.Generator(device=dev).manual_seed(123 + r)) for r in range(N)]
-        Xcpu = torch.cat(g_all)
-    else:
-        Xcpu = Xs
-    gbs, t_cpu, rows, e = cpu_sample(orc, ptr, idx, val, Xcpu, W, fin, fout, args.cpu_seconds)
-    cpu_baseline = {"value": round(gbs, 3), "unit": "GB/s", "cores": orc.num_threads(), "kind": "port",
-                    "sample": "rows [0,%d) = %d edges (%.2f%% of m) of rank 0's graph, %.1f s; scalar fp32 CSR port + fp32 GEMM "
-                              "(oracle/oracle.c, OpenMP dynamic,64)" % (rows, e, 100.0 * e / m, t_cpu)}
+        line = {"metric": "gcn_aggregation_algorithmic_GBps" if agg_only else "gcn_layer_algorithmic_GBps", "value": round(value, 1),
+                "unit": "GB/s", "n_gpus": N,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True,
+                "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wl.config,
+                "edges_feat_per_s": round(N * m * fin / (ms * 1e-3), 1),
+                "clocks": clocks,
+                "e2e": {"value": round(e2e_value, 1), "unit": "GB/s", "ms_per_step": round(ms_e2e, 4),
+                        "h2d_bytes_per_step": 4 * n * fin + (4 * fin * fout if (N == 1 and not agg_only) else 0),
+                        "d2h_bytes_per_step": 4 * n * (fout or fin),
+                        "api": ("gnnagg_gcn_run_host (pinned host X -> Y)" if agg_only else "gnnagg_gcn_layer_host (pinned host X, W -> H)") if N == 1 else
+                               "pinned H2D of the X shard into the peer-visible buffer + the step (halo pulls + aggregation + combination) + D2H of the H shard"},
+                "gpu_launches": int(round(r["launches_per_step"] * args.steps)),
+                "compute_only": {"ms_per_step": round(total_ms, 4),
+                                 "value": round(N * bytes_rank / (total_ms * 1e-3) / 1e9, 1), "unit": "GB/s",
+                                 "note": "kernels only (X already resident, no halo exchange)" + (
+                                     ", the library's own CUDA events" if N == 1 else ", timed like the step with the exchange switched off, max over ranks")},
+                "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "setup_s": round(wl.setup_s, 2)}
+        if N > 1:
+            line["e2e"]["copies_only_ms"] = round(r["ms_copies"], 4)
+            line["e2e"]["note"] = "copies_only_ms = the H2D + D2H of the same buffers alone, all ranks at once: what the host side of this box allows at this N"
+            hal = {"kind": wl.halo, "exposed_ms": round(ms - r["compute_ms"], 4)}
+            if wl.ph is not None:
+                ex_bytes = wl.ph.num_recv * fin * 4
+                hal.update({"remote_stages": wl.ph.num_stages - 1, "stage_edges": wl.ph.stage_edges,
+                            "bytes_per_rank": ex_bytes, "exchange_ms": round(r["exchange_ms"], 4),
+                            "nvlink_GBps_per_rank": round(ex_bytes / (r["exchange_ms"] * 1e-3) / 1e9, 1),
+                            "nvlink_frac_of_770": round(ex_bytes / (r["exchange_ms"] * 1e-3) / 1e9 / NVLINK_PEAK_GBS, 3),
+                            "note": "exchange_ms = first pull issued .. last row landed on the comm stream (max over ranks), "
+                                    "running concurrently with the aggregation; exposed_ms = step - kernels-only step"})
+            line["halo"] = hal
+            line["parity"] = parity
 
-    line = {"metric": "gcn_aggregation_algorithmic_GBps" if agg_only else "gcn_layer_algorithmic_GBps", "value": round(value, 1),
-            "unit": "GB/s", "n_gpus": N,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True,
-            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-            "edges_feat_per_s": round(N * m * fin / (ms * 1e-3), 1),
-            "clocks": clocks,
-            "e2e": {"value": round(e2e_value, 1), "unit": "GB/s", "ms_per_step": round(ms_e2e, 4),
-                    "h2d_bytes_per_step": 4 * n * fin + (4 * fin * fout if (N == 1 and not agg_only) else 0),
-                    "d2h_bytes_per_step": 4 * n * (fout or fin),
-                    "api": ("gnnagg_gcn_run_host (pinned host X -> Y)" if agg_only else "gnnagg_gcn_layer_host (pinned host X, W -> H)") if N == 1 else
-                           "pinned H2D of the X shard + NCCL halo all-gather + aggregation + combination + D2H of the H shard"},
-            "gpu_launches": int(launches) + (args.steps if pruned else 0),  # + the row-packing kernel
-            "compute_only": {"ms_per_step": round(float(np.mean([p["total"] for p in prof])), 4),
-                             "value": round(N * bytes_rank / (float(np.mean([p["total"] for p in prof])) * 1e-3) / 1e9, 1), "unit": "GB/s",
-                             "note": "rank 0's kernels only (X already resident, no halo exchange), from the library's own CUDA events"},
-            "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "setup_s": round(t_setup, 2)}
-    print(json.dumps(line))
+    # ---- the kernel to beat: the reference's own kernels recompiled for sm_100 (oracle/_ref), after the headline
+    if rank == 0 and N == 1 and args.ref_kernels and not args.scheduled:
+        try:
+            line["ref_kernels_sm100"] = ref_kernels(wl, flush)
+        except Exception as e:
+            line["ref_kernels_sm100"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+
+    wl.close()
+    del wl
+    torch.cuda.empty_cache()
+
+    if do_c5:
+        try:
+            c5 = c5_block(args, N, rank, dev, dist, timed, 5, 3)
+        except Exception as e:  # never lose the headline line to the extra block
+            c5 = {"error": "%s: %s" % (type(e).__name__, e)}
+        if rank == 0:
+            line["c5"] = c5
+    if rank == 0:
+        print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+def ref_kernels(wl, flush):
+    """ours vs the reference's aggr_gcn (un-scheduled) and aggr_gcn_target (NG 32) on the headline graph, same inputs.
+    oracle/_ref/libref.so = the reference's sources compiled for sm_100 by oracle/Makefile; used as the measured
+    'kernel to beat' beside the headline, never on the product path."""
+    import ctypes as C
+
+    import numpy as np
+    import torch
+
+    import oracle as orc
+
+    if not orc.ref_available():
+        return {"unavailable": "oracle/_ref/libref.so not built (needs /root/reference at build time)"}
+    ref = orc.ref()
+    n, m, F = wl.n, wl.m, wl.fin
+    P = lambda t: C.c_void_p(t.data_ptr())
+    Y, Yr = torch.empty((n, F), device=wl.dev), torch.zeros((n, F), device=wl.dev)
+
+    def timeit(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+
+    ref.ref_set_globals(n, m)
+    h = C.c_void_p(ref.ref_gcn_create(P(wl.ptr), P(wl.idx), P(wl.val), n, m, F, F))
+    out = {"graph": wl.name, "F": F}
+    out["ours_gcn_ms"] = round(timeit(lambda: wl.agg.gcn_run(wl.Xs, Y), 5), 4)
+    out["ref_aggr_gcn_ms"] = round(timeit(lambda: ref.ref_gcn_run(h, P(wl.Xs), P(Yr), max(128, F), 0, F), 3), 4)
+    wl.agg.schedule(1, [32])
+    ref.ref_gcn_schedule(h, 1, 32, 0)
+    out["ours_gcn_ng32_ms"] = round(timeit(lambda: wl.agg.gcn_run(wl.Xs, Y, scheduled=True), 5), 4)
+    out["ref_aggr_gcn_target_ng32_ms"] = round(timeit(lambda: ref.ref_gcn_run(h, P(wl.Xs), P(Yr), max(128, F), 1, F), 3), 4)
+    out["speedup_vs_aggr_gcn"] = round(out["ref_aggr_gcn_ms"] / out["ours_gcn_ms"], 2)
+    out["speedup_vs_aggr_gcn_target"] = round(out["ref_aggr_gcn_target_ng32_ms"] / min(out["ours_gcn_ms"], out["ours_gcn_ng32_ms"]), 2)
+    diff = (Y - Yr).abs().max().item() / max(1e-30, Yr.abs().max().item())
+    out["max_abs_diff_over_max_abs"] = float("%.3g" % diff)
+    out["source"] = "include/aggr_gcn.h:5-36 (aggr_gcn), :78-114 (aggr_gcn_target) compiled from /root/reference for sm_100 (-O2 --use_fast_math)"
+    return out
 
 
 if __name__ == "__main__":

@@ -157,6 +157,18 @@ static int build_item_rows(gnnagg_aggregator *a, const int *d_ptr, int rows, int
     return GNNAGG_OK;
 }
 
+int build_item_rows_device(const int *d_ptr, int rows, int edges, int **out, int *items, cudaStream_t st)
+{
+    *items = (int)cdiv(edges, kFineItem);
+    *out = nullptr;
+    CUDA_TRY(cudaMalloc((void **)out, (size_t)(*items ? *items : 1) * sizeof(int)));
+    if (*items > 0) {
+        item_row_kernel<<<(unsigned)cdiv(*items, 256), 256, 0, st>>>(d_ptr, rows, edges, *out, *items);
+        CUDA_TRY(cudaPeekAtLastError());
+    }
+    return GNNAGG_OK;
+}
+
 static void free_schedule(gnnagg_aggregator *a)
 {
     cudaFree(a->s_ptr);
@@ -177,6 +189,13 @@ __global__ void gather_val_kernel(const float *__restrict__ val, const int *__re
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) out[i] = __ldg(val + __ldg(perm + i));
+}
+
+// out[perm[i]] = in[i]: scheduled edge order back to CSR order
+__global__ void scatter_val_kernel(const float *__restrict__ in, const int *__restrict__ perm, float *__restrict__ out, int count)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[__ldg(perm + i)] = __ldg(in + i);
 }
 
 static int check_feat(int F)
@@ -620,6 +639,16 @@ int gnnagg_device_info(int *sm_count, int *cc_major, int *cc_minor, char *name, 
 int gnnagg_create(const int *d_ptr, const int *d_idx, const int *h_ptr, const int *h_idx, int num_v, int num_e,
                   gnnagg_aggregator **out)
 {
+    // legacy-stream variant (what the reference's constructors do): returns with the set-up kernel complete, so a run
+    // issued on ANY stream right afterwards is ordered behind it
+    const int rc = gnnagg_create_on(d_ptr, d_idx, h_ptr, h_idx, num_v, num_e, out, nullptr);
+    if (rc == GNNAGG_OK) CUDA_TRY(cudaStreamSynchronize(0));
+    return rc;
+}
+
+int gnnagg_create_on(const int *d_ptr, const int *d_idx, const int *h_ptr, const int *h_idx, int num_v, int num_e,
+                     gnnagg_aggregator **out, void *stream)
+{
     if (!out || !d_ptr || (num_e > 0 && !d_idx) || num_v < 0 || num_e < 0)
         return set_error(GNNAGG_ERR_ARG, "gnnagg_create: bad argument");
     gnnagg_aggregator *a = new gnnagg_aggregator();
@@ -629,7 +658,7 @@ int gnnagg_create(const int *d_ptr, const int *d_idx, const int *h_ptr, const in
     a->h_idx_user = h_idx;
     a->n = num_v;
     a->m = num_e;
-    const int rc = build_item_rows(a, d_ptr, num_v, num_e, &a->d_item_row, &a->num_items, 0);
+    const int rc = build_item_rows(a, d_ptr, num_v, num_e, &a->d_item_row, &a->num_items, (cudaStream_t)stream);
     if (rc != GNNAGG_OK) {
         delete a;
         return rc;
@@ -674,6 +703,13 @@ int gnnagg_destroy(gnnagg_aggregator *a)
 
 int gnnagg_set_val(gnnagg_aggregator *a, const float *d_val)
 {
+    const int rc = gnnagg_set_val_on(a, d_val, nullptr);
+    if (rc == GNNAGG_OK && a->s_perm) CUDA_TRY(cudaStreamSynchronize(0));  // the permuted copy is complete on return
+    return rc;
+}
+
+int gnnagg_set_val_on(gnnagg_aggregator *a, const float *d_val, void *stream)
+{
     if (!a) return set_error(GNNAGG_ERR_ARG, "gnnagg_set_val: NULL aggregator");
     a->d_val = d_val;
     a->t_val_of = nullptr;  // same pointer, possibly new contents (aggr_gcn.h:540-544): re-mirror on the next backward
@@ -682,7 +718,8 @@ int gnnagg_set_val(gnnagg_aggregator *a, const float *d_val)
     if (a->s_perm) {  // locality kinds keep a permuted copy (aggr_gcn.h:522-537)
         if (!a->s_val) CUDA_TRY(cudaMalloc((void **)&a->s_val, (size_t)(a->sched_edges ? a->sched_edges : 1) * sizeof(float)));
         if (d_val && a->sched_edges > 0) {
-            gather_val_kernel<<<(unsigned)cdiv(a->sched_edges, 256), 256>>>(d_val, a->s_perm, a->s_val, a->sched_edges);
+            gather_val_kernel<<<(unsigned)cdiv(a->sched_edges, 256), 256, 0, (cudaStream_t)stream>>>(d_val, a->s_perm, a->s_val,
+                                                                                                  a->sched_edges);
             LAUNCH_CHECK(a);
         }
     } else {
@@ -734,6 +771,25 @@ int gnnagg_schedule_apply(gnnagg_aggregator *a, int kind, const int *params, int
     return GNNAGG_OK;
 }
 
+int gnnagg_schedule_kind(const gnnagg_aggregator *a) { return a ? a->sched_kind : GNNAGG_SCHED_NOP; }
+
+int gnnagg_sched_to_csr_order(gnnagg_aggregator *a, const float *in_sched, float *out_csr, void *stream)
+{
+    if (!a || (a->m > 0 && (!in_sched || !out_csr))) return set_error(GNNAGG_ERR_ARG, "gnnagg_sched_to_csr_order: NULL argument");
+    if (a->m == 0) return GNNAGG_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!a->s_perm) {  // no schedule, or neighbour grouping: the scheduled order IS the CSR order
+        if (in_sched != out_csr) CUDA_TRY(cudaMemcpyAsync(out_csr, in_sched, (size_t)a->m * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        return GNNAGG_OK;
+    }
+    if (in_sched == out_csr) return set_error(GNNAGG_ERR_ARG, "gnnagg_sched_to_csr_order: in place is not possible after a locality schedule");
+    if (a->sched_edges != a->m)
+        return set_error(GNNAGG_ERR_STATE, "gnnagg_sched_to_csr_order: the schedule dropped edges (sources outside the slice range)");
+    scatter_val_kernel<<<(unsigned)cdiv(a->m, 256), 256, 0, st>>>(in_sched, a->s_perm, out_csr, a->m);
+    LAUNCH_CHECK(a);
+    return GNNAGG_OK;
+}
+
 int gnnagg_num_target(const gnnagg_aggregator *a) { return a ? a->num_target : 0; }
 const int *gnnagg_sched_dev_ptr(const gnnagg_aggregator *a) { return a ? a->s_ptr : nullptr; }
 const int *gnnagg_sched_dev_idx(const gnnagg_aggregator *a) { return a ? a->s_idx : nullptr; }
@@ -782,6 +838,25 @@ int gnnagg_memcpy_d2h(void *h_dst, const void *d_src, uint64_t bytes)
     if (!h_dst || !d_src) return set_error(GNNAGG_ERR_ARG, "gnnagg_memcpy_d2h: NULL argument");
     CUDA_TRY(cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost));
     return GNNAGG_OK;
+}
+
+int gnnagg_prepare(gnnagg_aggregator *a, int feat, void *stream)
+{
+    if (!a) return set_error(GNNAGG_ERR_ARG, "gnnagg_prepare: NULL aggregator");
+    if (int rc = check_feat(feat)) return rc;
+    if (a->m == 0 || a->n == 0) return GNNAGG_OK;
+    const int EB = item_edges_for(a, feat, a->m);
+    if (int rc = ensure(a->carry, a->carry_cap, (size_t)cdiv(a->m, EB) * feat)) return rc;
+    AggParams p{};
+    p.ptr = a->d_ptr;
+    p.item_row = a->d_item_row;
+    p.num_rows = a->n;
+    p.num_edges = a->m;
+    p.num_fine_items = a->num_items;
+    const int *list = nullptr;
+    const int2 *records = nullptr;
+    int num_long = 0;
+    return long_rows_of(a, p, EB, (cudaStream_t)stream, &list, &num_long, &records);
 }
 
 int gnnagg_gcn_run(gnnagg_aggregator *a, const float *X, float *Y, int feat, int scheduled, void *stream)

@@ -336,6 +336,21 @@ static cudaMemPool_t split_pool(int dev)
     return pools[dev];
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) property of the function: remember what
+// has been configured for EACH device, so that a process driving several GPUs (gnnagg_dist_create) opts in on all
+template <class Kernel>
+static cudaError_t ensure_dynamic_smem(Kernel kernel, int slot, int dev, size_t bytes)
+{
+    static std::mutex lock;
+    static size_t configured[2][64] = {};
+    if (dev < 0 || dev >= 64) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    std::lock_guard<std::mutex> guard(lock);
+    if (bytes <= configured[slot][dev]) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) configured[slot][dev] = bytes;
+    return e;
+}
+
 int dense_nn_launch(const float *A, const float *B, float *C, int64_t M, int N, int K, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
@@ -362,19 +377,11 @@ int dense_nn_launch(const float *A, const float *B, float *C, int64_t M, int N, 
     cudaError_t e = cudaSuccess;
     if (N * K > kMaxNK) {  // W does not fit in shared memory next to the A ring: stream it stage by stage
         const size_t smem_s = 2 * ((size_t)2 * kStageBytes + (size_t)2 * N * 128);
-        static size_t configured_s = 0;
-        if (smem_s > configured_s) {
-            e = cudaFuncSetAttribute(dense_tf32x3_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);
-            if (e == cudaSuccess) configured_s = smem_s;
-        }
+        e = ensure_dynamic_smem(dense_tf32x3_ws_kernel<false>, 0, dev, smem_s);
         if (e == cudaSuccess) dense_tf32x3_ws_kernel<false><<<grid, kWsThreads, smem_s, st>>>(A, whi, wlo, C, M, N, K, acc_cols);
     } else {
         const size_t smem = (size_t)2 * N * K * 4 + (size_t)3 * 2 * kStageBytes;  // W hi/lo resident + 3 ring stages
-        static size_t configured = 0;
-        if (smem > configured) {
-            e = cudaFuncSetAttribute(dense_tf32x3_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e == cudaSuccess) configured = smem;
-        }
+        e = ensure_dynamic_smem(dense_tf32x3_ws_kernel<true>, 1, dev, smem);
         if (e == cudaSuccess) dense_tf32x3_ws_kernel<true><<<grid, kWsThreads, smem, st>>>(A, whi, wlo, C, M, N, K, acc_cols);
     }
     if (e == cudaSuccess) e = cudaPeekAtLastError();

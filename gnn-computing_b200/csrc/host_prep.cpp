@@ -230,47 +230,46 @@ static inline bool is_space(char c) { return c == ' ' || c == '\n' || c == '\t' 
 template <class Sink>
 static long long parse_ints_parallel(const char *p, const char *end, Sink sink)
 {
+    // The text is cut into a FIXED number of byte chunks and the chunks are distributed with `parallel for`: nothing
+    // depends on how many threads the runtime actually delivers (num_threads() is only a request -- under
+    // OMP_THREAD_LIMIT, cgroup limits or a nested region fewer arrive, and per-thread byte ranges would go unparsed).
     const size_t bytes = (size_t)(end - p);
-    int threads = 1;
+    int chunks = 1;
 #ifdef _OPENMP
-    threads = omp_get_max_threads();
+    chunks = omp_get_max_threads() * 4;
 #endif
-    if (bytes < (1u << 20)) threads = 1;
-    std::vector<long long> first((size_t)threads + 1, 0);
-    bool bad = false;
-#pragma omp parallel num_threads(threads)
-    {
-        int t = 0;
-#ifdef _OPENMP
-        t = omp_get_thread_num();
-#endif
-        const size_t lo = bytes * (size_t)t / (size_t)threads, hi = bytes * ((size_t)t + 1) / (size_t)threads;
+    if (bytes < (1u << 20) || chunks < 1) chunks = 1;
+    std::vector<long long> first((size_t)chunks + 1, 0);
+    auto lo_of = [&](int c) { return bytes * (size_t)c / (size_t)chunks; };
+    // pass 1: tokens that START in every chunk
+#pragma omp parallel for schedule(static)
+    for (int c = 0; c < chunks; ++c) {
+        const size_t lo = lo_of(c), hi = lo_of(c + 1);
         long long count = 0;
         for (size_t i = lo; i < hi; ++i)
             if (!is_space(p[i]) && (i == 0 || is_space(p[i - 1]))) ++count;
-        first[(size_t)t + 1] = count;
-#pragma omp barrier
-#pragma omp single
-        for (int k = 0; k < threads; ++k) first[(size_t)k + 1] += first[(size_t)k];
-        long long k = first[(size_t)t];
-        bool local_bad = false;
+        first[(size_t)c + 1] = count;
+    }
+    for (int c = 0; c < chunks; ++c) first[(size_t)c + 1] += first[(size_t)c];
+    // pass 2: parse them at their final index
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (int c = 0; c < chunks; ++c) {
+        const size_t lo = lo_of(c), hi = lo_of(c + 1);
+        long long k = first[(size_t)c];
         for (size_t i = lo; i < hi; ++i) {
             if (is_space(p[i]) || !(i == 0 || is_space(p[i - 1]))) continue;
             const char *q = p + i;
             bool neg = false;
             if (*q == '-' || *q == '+') neg = (*q++ == '-');
-            if (q >= end || *q < '0' || *q > '9') local_bad = true;
+            if (q >= end || *q < '0' || *q > '9') bad |= 1;
             long long v = 0;
             while (q < end && *q >= '0' && *q <= '9') v = v * 10 + (*q++ - '0');
-            if (q < end && !is_space(*q)) local_bad = true;
+            if (q < end && !is_space(*q)) bad |= 1;
             sink(k++, (int)(neg ? -v : v));
         }
-        if (local_bad) {
-#pragma omp critical
-            bad = true;
-        }
     }
-    return bad ? -1 : first[(size_t)threads];
+    return bad ? -1 : first[(size_t)chunks];
 }
 
 static bool read_raw(const std::string &path, int *dst, size_t count)
@@ -327,13 +326,22 @@ int gnnagg_reorder_csr(const int *ptr, const int *idx, const int *map, const int
     // new row i is old row map[i]; its neighbours keep their old order and are relabelled through
     // reverse_map (src/data.cu:15-27).  Row lengths first, then an offset scan, then the copy.
     newptr[0] = 0;
-    for (int i = 0; i < num_v; ++i) newptr[i + 1] = newptr[i] + (ptr[map[i] + 1] - ptr[map[i]]);
+    for (int i = 0; i < num_v; ++i) {
+        const int old = map[i];
+        if (old < 0 || old >= num_v) return set_error(GNNAGG_ERR_ARG, "gnnagg_reorder_csr: map entry outside [0, num_v)");
+        const long long next = (long long)newptr[i] + (ptr[old + 1] - ptr[old]);
+        if (next > num_e) return set_error(GNNAGG_ERR_ARG, "gnnagg_reorder_csr: map is not a permutation");
+        newptr[i + 1] = (int)next;
+    }
     if (newptr[num_v] != num_e) return set_error(GNNAGG_ERR_ARG, "gnnagg_reorder_csr: map is not a permutation");
     for (int i = 0; i < num_v; ++i) {
         const int *src = idx + ptr[map[i]];
         int *dst = newidx + newptr[i];
         const int len = newptr[i + 1] - newptr[i];
-        for (int j = 0; j < len; ++j) dst[j] = reverse_map[src[j]];
+        for (int j = 0; j < len; ++j) {
+            if (src[j] < 0 || src[j] >= num_v) return set_error(GNNAGG_ERR_ARG, "gnnagg_reorder_csr: source id outside [0, num_v)");
+            dst[j] = reverse_map[src[j]];
+        }
     }
     return GNNAGG_OK;
 }

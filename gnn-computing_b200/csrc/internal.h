@@ -33,7 +33,10 @@ int transpose_build_device(const int *d_ptr, const int *d_idx, const int *d_item
 // the CSR split by source-id ranges into num_slices sub-CSRs over the same rows (sched_device.cu)
 int source_slices_build_device(const int *d_ptr, const int *d_idx, const int *d_item_row, int num_items, int n, int m,
                                int num_slices, int width, int **sl_ptr, int **sl_idx, int **sl_perm, int *edge_off,
-                               int *edge_cnt, cudaStream_t st);
+                               int *edge_cnt, cudaStream_t st, const int *d_edge_keys = nullptr);
+
+// item_row table of a CSR (row containing edge k*128), cudaMalloc'ed into *out (capi.cu)
+int build_item_rows_device(const int *d_ptr, int rows, int edges, int **out, int *items, cudaStream_t st);
 
 // sub-graph samplers of include/sample.h (sample_device.cu); outputs are cudaMalloc'ed
 int sample_subgraph_device(const int *d_ptr, const int *d_idx, const int *d_item_row, int num_items, int n, int m,

@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(256) slice_key_kernel(const int *__restrict__ 
 
 int source_slices_build_device(const int *d_ptr, const int *d_idx, const int *d_item_row, int num_items, int n, int m,
                                int num_slices, int width, int **sl_ptr, int **sl_idx, int **sl_perm, int *edge_off,
-                               int *edge_cnt, cudaStream_t st)
+                               int *edge_cnt, cudaStream_t st, const int *d_edge_keys)
 {
     *sl_ptr = *sl_idx = *sl_perm = nullptr;
     int *keys = nullptr, *keys_sorted = nullptr, *edge_id = nullptr, *perm = nullptr, *rows_sorted = nullptr, *bounds_d = nullptr;
@@ -341,17 +341,22 @@ int source_slices_build_device(const int *d_ptr, const int *d_idx, const int *d_
     SD_TRY(cudaMalloc((void **)sl_idx, padded * sizeof(int)));
     SD_TRY(cudaMalloc((void **)sl_perm, padded * sizeof(int)));
     SD_TRY(cudaMemsetAsync(*sl_perm, 0, padded * sizeof(int), st));
-    SD_TRY(cudaMalloc((void **)&keys, me * sizeof(int)));
+    if (!d_edge_keys) SD_TRY(cudaMalloc((void **)&keys, me * sizeof(int)));
     SD_TRY(cudaMalloc((void **)&keys_sorted, me * sizeof(int)));
     SD_TRY(cudaMalloc((void **)&edge_id, me * sizeof(int)));
     SD_TRY(cudaMalloc((void **)&perm, me * sizeof(int)));
     SD_TRY(cudaMalloc((void **)&rows_sorted, me * sizeof(int)));
     SD_TRY(cudaMalloc((void **)&bounds_d, ((size_t)num_slices + 1) * sizeof(int)));
     if (m > 0) {
-        slice_key_kernel<<<blocks(m), 256, 0, st>>>(d_idx, m, num_slices, width, keys, edge_id);
-        SD_TRY(cub::DeviceRadixSort::SortPairs(nullptr, need, keys, keys_sorted, edge_id, perm, m, 0, end_bit, st));
+        // slice of every edge: source id / width, or handed in by the caller (dist.cu: stage of the source's owner)
+        const int *sort_keys = d_edge_keys ? d_edge_keys : keys;
+        if (d_edge_keys)
+            iota_kernel<<<blocks(m), 256, 0, st>>>(edge_id, m);
+        else
+            slice_key_kernel<<<blocks(m), 256, 0, st>>>(d_idx, m, num_slices, width, keys, edge_id);
+        SD_TRY(cub::DeviceRadixSort::SortPairs(nullptr, need, sort_keys, keys_sorted, edge_id, perm, m, 0, end_bit, st));
         SD_TRY(cudaMalloc(&tmp, need ? need : 1));
-        SD_TRY(cub::DeviceRadixSort::SortPairs(tmp, need, keys, keys_sorted, edge_id, perm, m, 0, end_bit, st));  // stable
+        SD_TRY(cub::DeviceRadixSort::SortPairs(tmp, need, sort_keys, keys_sorted, edge_id, perm, m, 0, end_bit, st));  // stable
         ptr_from_sorted_kernel<<<blocks((int64_t)m + 1), 256, 0, st>>>(keys_sorted, m, num_slices, bounds_d);
         edge_rows_kernel<<<blocks(m), 256, 0, st>>>(d_ptr, d_item_row, num_items, n, perm, m, rows_sorted);
         SD_TRY(cudaMemcpyAsync(bounds, bounds_d, ((size_t)num_slices + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));

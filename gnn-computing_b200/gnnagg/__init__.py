@@ -55,14 +55,19 @@ _SIGS = {
                                      C.c_uint64, C.c_void_p]),
     "gnnagg_reorder_write": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int]),
     "gnnagg_create": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "gnnagg_create_on": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p]),
+    "gnnagg_set_val_on": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "gnnagg_destroy": (C.c_int, [C.c_void_p]),
     "gnnagg_set_val": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gnnagg_schedule_apply": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int]),
     "gnnagg_num_target": (C.c_int, [C.c_void_p]),
+    "gnnagg_schedule_kind": (C.c_int, [C.c_void_p]),
+    "gnnagg_sched_to_csr_order": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gnnagg_sched_dev_ptr": (C.c_void_p, [C.c_void_p]),
     "gnnagg_sched_dev_idx": (C.c_void_p, [C.c_void_p]),
     "gnnagg_sched_dev_target": (C.c_void_p, [C.c_void_p]),
     "gnnagg_sched_dev_val": (C.c_void_p, [C.c_void_p]),
+    "gnnagg_prepare": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "gnnagg_gcn_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "gnnagg_gcn_run_acc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "gnnagg_gcn_run_edgewise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
@@ -98,7 +103,27 @@ _SIGS = {
     "gnnagg_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "gnnagg_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "gnnagg_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    # multi-GPU over NVLink peer memory (dist.cu)
+    "gnnagg_dist_create": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_void_p)]),
+    "gnnagg_dist_create_rank": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_void_p)]),
+    "gnnagg_dist_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gnnagg_dist_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gnnagg_dist_destroy": (C.c_int, [C.c_void_p]),
+    "gnnagg_dist_set_graph": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "gnnagg_dist_x": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "gnnagg_dist_gcn_run": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "gnnagg_dist_gcn_layer": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "gnnagg_dist_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int),
+                                   C.POINTER(C.c_int64)]),
+    "gnnagg_dist_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "gnnagg_dist_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "gnnagg_dist_check": (C.c_int, [C.c_void_p]),
+    "gnnagg_dist_launch_count": (C.c_int64, [C.c_void_p]),
 }
+
+DIST_BLOB_BYTES = 256
+DIST_MAX_WORLD = 16
+DIST_NO_EXCHANGE = 1
 
 
 def lib():
@@ -219,6 +244,28 @@ def _dp(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def _f32(t, name, cuda=True):
+    """device (or host) float32 operand of a C-ABI call: the library only sees a raw pointer, so a float64 tensor,
+    a column-sliced view or a tensor on the wrong side would silently compute garbage -- reject them here"""
+    import torch
+
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        if cuda:
+            raise GnnaggError("%s: expected a CUDA tensor, got a numpy array" % name)
+        if t.dtype != np.float32 or not t.flags["C_CONTIGUOUS"]:
+            raise GnnaggError("%s: numpy operand must be C-contiguous float32" % name)
+        return C.c_void_p(t.ctypes.data)
+    if t.dtype != torch.float32:
+        raise GnnaggError("%s: expected float32, got %s" % (name, t.dtype))
+    if not t.is_contiguous():
+        raise GnnaggError("%s: expected a contiguous row-major tensor (got strides %s)" % (name, tuple(t.stride())))
+    if bool(t.is_cuda) != bool(cuda):
+        raise GnnaggError("%s: expected a %s tensor" % (name, "CUDA" if cuda else "host"))
+    return C.c_void_p(t.data_ptr())
+
+
 def device_info():
     sm, ma, mi = C.c_int(), C.c_int(), C.c_int()
     name = C.create_string_buffer(256)
@@ -241,8 +288,9 @@ class Aggregator:
         self._h_idx = None if h_idx is None else np.ascontiguousarray(h_idx, np.int32)
         self.n, self.m = ptr.numel() - 1, idx.numel()
         h = C.c_void_p()
-        check(lib().gnnagg_create(_dp(self.ptr), _dp(self.idx), _np(self._h_ptr), _np(self._h_idx), self.n, self.m,
-                                  C.byref(h)))
+        # set-up kernels go on torch's current stream: ptr/idx may still be in flight there, and the runs follow on it
+        check(lib().gnnagg_create_on(_dp(self.ptr), _dp(self.idx), _np(self._h_ptr), _np(self._h_idx), self.n, self.m,
+                                     C.byref(h), _stream()))
         self.h = h
         if val is not None:
             self.set_val(val)
@@ -259,10 +307,17 @@ class Aggregator:
             pass
 
     def set_val(self, val):
+        import torch
+
+        if val.dtype != torch.float32 or not val.is_cuda or val.numel() != self.m:
+            raise GnnaggError("set_val: expected a float32 CUDA tensor with one value per edge")
         self.val = val.contiguous()
-        check(lib().gnnagg_set_val(self.h, _dp(self.val)))
+        check(lib().gnnagg_set_val_on(self.h, _dp(self.val), _stream()))
 
     def schedule(self, kind, params, total_num_v=None):
+        import torch
+
+        torch.cuda.current_stream().synchronize()  # the schedule is built on the legacy stream from ptr/idx/val
         arr = (C.c_int * len(params))(*params)
         check(lib().gnnagg_schedule_apply(self.h, kind, arr, len(params), self.n if total_num_v is None else total_num_v))
         return self.num_target
@@ -311,11 +366,11 @@ class Aggregator:
 
     # --- GCN
     def gcn_run(self, X, Y, scheduled=False):
-        check(lib().gnnagg_gcn_run(self.h, _dp(X), _dp(Y), X.shape[1], int(scheduled), _stream()))
+        check(lib().gnnagg_gcn_run(self.h, _f32(X, "X"), _f32(Y, "Y"), X.shape[1], int(scheduled), _stream()))
         return Y
 
     def gcn_run_acc(self, X, Y, accumulate=True):
-        check(lib().gnnagg_gcn_run_acc(self.h, _dp(X), _dp(Y), X.shape[1], int(accumulate), _stream()))
+        check(lib().gnnagg_gcn_run_acc(self.h, _f32(X, "X"), _f32(Y, "Y"), X.shape[1], int(accumulate), _stream()))
         return Y
 
     def gcn_run_edgewise(self, X, Y):
@@ -327,13 +382,13 @@ class Aggregator:
         return out
 
     def gcn_layer(self, X, W, H, AX=None, scheduled=False):
-        check(lib().gnnagg_gcn_layer(self.h, _dp(X), _dp(W), _dp(H), _dp(AX), W.shape[0], W.shape[1], int(scheduled),
+        check(lib().gnnagg_gcn_layer(self.h, _f32(X, "X"), _f32(W, "W"), _f32(H, "H"), _f32(AX, "AX"), W.shape[0], W.shape[1], int(scheduled),
                                      _stream()))
         return H
 
     # --- GAT
     def gat_run(self, X, att, Y, slope=0.2, scheduled=False):
-        check(lib().gnnagg_gat_run(self.h, _dp(X), _dp(att), _dp(Y), X.shape[1], slope, int(scheduled), _stream()))
+        check(lib().gnnagg_gat_run(self.h, _f32(X, "X"), _f32(att, "att"), _f32(Y, "Y"), X.shape[1], slope, int(scheduled), _stream()))
         return Y
 
     def gat_edge_weights_ptr(self):
@@ -357,12 +412,12 @@ class Aggregator:
 
     # --- per-edge MLP aggregator (aggr_nn.h)
     def mlp_run(self, X, W, Y, scheduled=False):
-        check(lib().gnnagg_mlp_run(self.h, _dp(X), _dp(W), _dp(Y), X.shape[1], int(scheduled), _stream()))
+        check(lib().gnnagg_mlp_run(self.h, _f32(X, "X"), _f32(W, "W"), _f32(Y, "Y"), X.shape[1], int(scheduled), _stream()))
         return Y
 
     # --- SDDMM
     def sddmm(self, X1, X2, out_val, scheduled=False):
-        check(lib().gnnagg_sddmm(self.h, _dp(X1), _dp(X2), _dp(out_val), X1.shape[1], int(scheduled), _stream()))
+        check(lib().gnnagg_sddmm(self.h, _f32(X1, "X1"), _f32(X2, "X2"), _f32(out_val, "out_val"), X1.shape[1], int(scheduled), _stream()))
         return out_val
 
     # --- backward (transposed CSR built once on the GPU, then gather-side aggregation over it)
@@ -385,11 +440,11 @@ class Aggregator:
         return back(tp, ns.value + 1), back(ti, self.m), back(tq, self.m)
 
     def gcn_backward(self, dY, dX):
-        check(lib().gnnagg_gcn_backward(self.h, _dp(dY), _dp(dX), dY.shape[1], _stream()))
+        check(lib().gnnagg_gcn_backward(self.h, _f32(dY, "dY"), _f32(dX, "dX"), dY.shape[1], _stream()))
         return dX
 
     def gat_backward(self, X, att, Y, dY, dX, datt, slope=0.2, w=None, den=None):
-        check(lib().gnnagg_gat_backward(self.h, _dp(X), _dp(att), _dp(w), _dp(den), _dp(Y), _dp(dY), _dp(dX), _dp(datt),
+        check(lib().gnnagg_gat_backward(self.h, _f32(X, "X"), _f32(att, "att"), _f32(w, "w"), _f32(den, "den"), _f32(Y, "Y"), _f32(dY, "dY"), _f32(dX, "dX"), _f32(datt, "datt"),
                                         X.shape[1], slope, _stream()))
         return dX, datt
 
@@ -417,22 +472,22 @@ class Aggregator:
 
     # --- host-buffer entry points (pinned CPU tensors or numpy arrays)
     def gcn_run_host(self, hX, hY, scheduled=False):
-        check(lib().gnnagg_gcn_run_host(self.h, _dp(hX), _dp(hY), hX.shape[1], int(scheduled), _stream()))
+        check(lib().gnnagg_gcn_run_host(self.h, _f32(hX, "hX", cuda=False), _f32(hY, "hY", cuda=False), hX.shape[1], int(scheduled), _stream()))
         return hY
 
     def gcn_layer_host(self, hX, hW, hH, scheduled=False):
-        check(lib().gnnagg_gcn_layer_host(self.h, _dp(hX), _dp(hW), _dp(hH), hW.shape[0], hW.shape[1], int(scheduled),
+        check(lib().gnnagg_gcn_layer_host(self.h, _f32(hX, "hX", cuda=False), _f32(hW, "hW", cuda=False), _f32(hH, "hH", cuda=False), hW.shape[0], hW.shape[1], int(scheduled),
                                           _stream()))
         return hH
 
     def gat_run_host(self, hX, hatt, hY, slope=0.2, scheduled=False):
-        check(lib().gnnagg_gat_run_host(self.h, _dp(hX), _dp(hatt), _dp(hY), hX.shape[1], slope, int(scheduled),
+        check(lib().gnnagg_gat_run_host(self.h, _f32(hX, "hX", cuda=False), _f32(hatt, "hatt", cuda=False), _f32(hY, "hY", cuda=False), hX.shape[1], slope, int(scheduled),
                                         _stream()))
         return hY
 
 
 def dense_nn(A, B, Cout):
-    check(lib().gnnagg_dense_nn(_dp(A), _dp(B), _dp(Cout), A.shape[0], B.shape[1], A.shape[1], _stream()))
+    check(lib().gnnagg_dense_nn(_f32(A, "A"), _f32(B, "B"), _f32(Cout, "C"), A.shape[0], B.shape[1], A.shape[1], _stream()))
     return Cout
 
 

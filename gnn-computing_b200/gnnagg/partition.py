@@ -300,3 +300,202 @@ class PipelinedPrunedHalo:
     @property
     def launches(self):
         return sum(a.launches for a in self.aggs)
+
+
+# ------------------------------------------------------------------------------------------------
+# peer-memory halo: binding over gnnagg_dist_* (csrc/dist.cu).  The exchange is not a collective: every
+# rank pulls the distinct remote source rows its block references straight out of the owners' X shards
+# with 128-bit loads over NVLink, owner group by owner group, while the edges whose sources have already
+# landed are being aggregated.  torch.distributed is only used once, to all-gather the 256-byte
+# connection blobs (cudaIpc handles) at set-up.
+# ------------------------------------------------------------------------------------------------
+class _DeviceMemory:
+    """a library-owned device buffer exposed through __cuda_array_interface__ (zero-copy torch view)"""
+
+    def __init__(self, ptr, shape, owner):
+        self.owner = owner
+        self.__cuda_array_interface__ = {"shape": tuple(int(s) for s in shape), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def _bounds_array(bounds):
+    import ctypes as C
+
+    return (C.c_int64 * len(bounds))(*[int(b) for b in bounds])
+
+
+class PeerHalo:
+    """one rank of the peer-memory multi-GPU aggregation.  `handle` may be passed in by LocalDist (single process
+    driving several ranks); otherwise the rank is created on the current device and connected to its peers through
+    torch.distributed (any backend: the blobs are plain bytes)."""
+
+    def __init__(self, ptr, idx, val, bounds, rank, world, feat_cap, remote_stages=1, group=None, handle=None):
+        import ctypes as C
+
+        import torch
+
+        from . import DIST_BLOB_BYTES, _dp, _stream, check, lib
+
+        L = lib()
+        self.rank, self.world, self.feat_cap, self.group = rank, world, feat_cap, group
+        self.bounds = [int(b) for b in bounds]
+        self.rows = self.bounds[rank + 1] - self.bounds[rank]
+        self.device = ptr.device
+        self._owns = handle is None
+        if handle is None:
+            h = C.c_void_p()
+            check(L.gnnagg_dist_create_rank(rank, world, _bounds_array(self.bounds), feat_cap, C.byref(h)))
+            self.h = h
+            if world > 1:
+                import torch.distributed as dist
+
+                blob = C.create_string_buffer(DIST_BLOB_BYTES)
+                check(L.gnnagg_dist_export(self.h, blob))
+                on_gpu = dist.get_backend(group) == "nccl"
+                mine = torch.frombuffer(bytearray(blob.raw), dtype=torch.uint8)
+                mine = mine.to(self.device) if on_gpu else mine
+                every = torch.empty(world * DIST_BLOB_BYTES, dtype=torch.uint8, device=mine.device)
+                dist.all_gather_into_tensor(every, mine, group=group)
+                raw = every.cpu().numpy().tobytes()
+                check(L.gnnagg_dist_connect(self.h, raw))
+        else:
+            self.h = handle
+        assert ptr.dtype == torch.int32 and idx.dtype == torch.int32 and val.dtype == torch.float32
+        assert ptr.numel() - 1 == self.rows, "the row block must match the rank's shard of X"
+        check(L.gnnagg_dist_set_graph(self.h, _dp(ptr.contiguous()), _dp(idx.contiguous()), _dp(val.contiguous()), idx.numel(),
+                                      int(remote_stages), _stream()))
+        nrecv, counts, nst = C.c_int64(), (C.c_int64 * world)(), C.c_int()
+        edges = (C.c_int64 * 16)()
+        check(L.gnnagg_dist_info(self.h, C.byref(nrecv), counts, C.byref(nst), edges))
+        self.num_recv, self.recv_counts, self.num_stages = int(nrecv.value), [int(c) for c in counts], int(nst.value)
+        self.stage_edges = [int(edges[s]) for s in range(self.num_stages)]
+        self.referenced_fraction = (self.num_recv + 0.0) / max(1, self.bounds[-1])
+
+    def x(self, buf=0, feat=None):
+        """torch view [rows, feat] of peer-visible shard buffer `buf` (write X here, or let a layer write H here)"""
+        import torch
+
+        from . import lib
+
+        feat = self.feat_cap if feat is None else feat
+        p = lib().gnnagg_dist_x(self.h, int(buf))
+        if self.rows == 0:
+            return torch.empty((0, feat), device=self.device)
+        return torch.as_tensor(_DeviceMemory(p, (self.rows, feat), self), device=self.device)
+
+    def gcn_run(self, Y, buf=0, feat=None, exchange=True):
+        from . import DIST_NO_EXCHANGE, _f32, _stream, check, lib
+
+        feat = Y.shape[1] if feat is None else feat
+        check(lib().gnnagg_dist_gcn_run(self.h, int(buf), _f32(Y, "Y"), int(feat), 0 if exchange else DIST_NO_EXCHANGE, _stream()))
+        return Y
+
+    def gcn_layer(self, W, H, buf=0, exchange=True):
+        from . import DIST_NO_EXCHANGE, _f32, _stream, check, lib
+
+        check(lib().gnnagg_dist_gcn_layer(self.h, int(buf), _f32(W, "W"), _f32(H, "H"), W.shape[0], W.shape[1],
+                                          0 if exchange else DIST_NO_EXCHANGE, _stream()))
+        return H
+
+    def profile(self, on=True):
+        from . import check, lib
+
+        check(lib().gnnagg_dist_profile_enable(self.h, int(on)))
+
+    def profile_read(self):
+        """ms of the last run: dict(exchange, step, stage0, dense)"""
+        import ctypes as C
+
+        from . import check, lib
+
+        ms = (C.c_float * 4)()
+        check(lib().gnnagg_dist_profile_read(self.h, ms))
+        return {"exchange": ms[0], "step": ms[1], "stage0": ms[2], "dense": ms[3]}
+
+    def check(self):
+        from . import check, lib
+
+        check(lib().gnnagg_dist_check(self.h))
+
+    @property
+    def launches(self):
+        from . import lib
+
+        return lib().gnnagg_dist_launch_count(self.h)
+
+    def close(self):
+        """collective when world > 1 and the rank was created here: peers must have stopped reading this shard"""
+        from . import lib
+
+        if getattr(self, "h", None) and self._owns:
+            if self.world > 1:
+                import torch
+                import torch.distributed as dist
+
+                torch.cuda.synchronize()
+                dist.barrier(group=self.group)
+            lib().gnnagg_dist_destroy(self.h)
+        self.h = None
+
+
+class LocalDist:
+    """gnnagg_dist_create: ONE process drives `world` ranks (devices[r], default r; the same device may be given
+    several times, which is how the single-GPU tests exercise the whole protocol)"""
+
+    def __init__(self, bounds, feat_cap, devices=None):
+        import ctypes as C
+
+        from . import check, lib
+
+        world = len(bounds) - 1
+        self.world, self.bounds, self.feat_cap = world, [int(b) for b in bounds], feat_cap
+        self.devices = list(range(world)) if devices is None else [int(d) for d in devices]
+        hs = (C.c_void_p * world)()
+        check(lib().gnnagg_dist_create(world, (C.c_int * world)(*self.devices), _bounds_array(self.bounds), feat_cap, hs))
+        self.handles = [C.c_void_p(hs[r]) for r in range(world)]
+        self.ranks = [None] * world
+
+    def set_graph(self, rank, ptr, idx, val, remote_stages=1):
+        self.ranks[rank] = PeerHalo(ptr, idx, val, self.bounds, rank, self.world, self.feat_cap, remote_stages,
+                                    handle=self.handles[rank])
+        return self.ranks[rank]
+
+    def close(self):
+        import torch
+
+        from . import lib
+
+        torch.cuda.synchronize()
+        for h in self.handles:
+            lib().gnnagg_dist_destroy(h)
+        self.handles = []
+
+
+def peer_plan(idx, bounds, rank, remote_stages):
+    """numpy restatement of the index bookkeeping of gnnagg_dist_set_graph (csrc/dist.cu), for tests and for
+    reasoning about traffic without a GPU.  Returns a dict:
+      recv_rows   global ids of the distinct REMOTE sources of this block, ascending (= receive-buffer order)
+      recv_off    [world+1] slot range of every owner inside recv_rows
+      recv_local  recv_rows as local row numbers inside their owner's shard (what the pull kernel reads)
+      stage_of    [world] stage of every owner: 0 = this rank, 1..R = groups of the owners taken in the order
+                  rank+1, rank+2, ... (mod world)
+      pull_order  the world-1 remote owners in that order
+      idx_new     per edge: local row of the own shard (stage 0) or receive-buffer slot (stages >= 1)
+      stage       per edge: its stage"""
+    bounds = np.asarray(bounds, np.int64)
+    W = len(bounds) - 1
+    g = np.asarray(idx, np.int64)
+    own_lo, own_hi = int(bounds[rank]), int(bounds[rank + 1])
+    remote = (g < own_lo) | (g >= own_hi)
+    U = np.unique(g[remote])
+    owner_u = np.searchsorted(bounds, U, side="right") - 1
+    R = 0 if W == 1 else max(1, min(int(remote_stages), W - 1))
+    order = [(rank + 1 + k) % W for k in range(W - 1)]
+    stage_of = np.zeros(W, np.int64)
+    for k, p in enumerate(order):
+        stage_of[p] = 1 + (k * R) // (W - 1)
+    owner_e = np.clip(np.searchsorted(bounds, g, side="right") - 1, 0, W - 1)
+    return {"recv_rows": U, "recv_off": np.searchsorted(U, bounds, side="left"), "recv_local": U - bounds[owner_u],
+            "stage_of": stage_of, "pull_order": order, "num_stages": 1 + R,
+            "idx_new": np.where(remote, np.searchsorted(U, g), g - own_lo).astype(np.int32),
+            "stage": np.where(remote, stage_of[owner_e], 0).astype(np.int32)}

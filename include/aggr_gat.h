@@ -53,10 +53,24 @@ public:
             checkGnnagg(gnnagg_transpose_build(handle, vertex_count(), NULL));
             transposed = true;
         }
-        checkGnnagg(gnnagg_gat_backward(handle, infeat, NULL, newval, div, output, doutput, d_feat, d_a_b, feat_in, relu_l, NULL));
+        // newval arrives in SCHEDULED edge order (aggr_gat_fine wrote it that way); the backward indexes weights in CSR
+        // order.  The two coincide for nop / neighbor_grouping; after a locality schedule the weights are mapped back.
+        const int kind = gnnagg_schedule_kind(handle);
+        float *w_csr = newval;
+        if (kind == GNNAGG_SCHED_LOCALITY || kind == GNNAGG_SCHED_LOCALITY_NEIGHBOR_GROUPING) {
+            if (!bwd_w) checkCudaErrors(cudaMalloc((void **)&bwd_w, sizeof(float) * (size_t)(edge_count() > 0 ? edge_count() : 1)));
+            checkGnnagg(gnnagg_sched_to_csr_order(handle, newval, bwd_w, NULL));
+            w_csr = bwd_w;
+        }
+        checkGnnagg(gnnagg_gat_backward(handle, infeat, NULL, w_csr, div, output, doutput, d_feat, d_a_b, feat_in, relu_l, NULL));
+    }
+    ~Aggregator_GAT()
+    {
+        if (bwd_w) cudaFree(bwd_w);
     }
 
 private:
     bool transposed = false;
+    float *bwd_w = NULL;  // newval in CSR order (run_bwd after a locality schedule)
 };
 #endif

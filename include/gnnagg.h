@@ -113,11 +113,19 @@ int gnnagg_reorder_write(const char *path, const int *rows, int num_v); /* clust
  * device when a host schedule needs them (aggregator.h:30-39). */
 int gnnagg_create(const int *d_ptr, const int *d_idx, const int *h_ptr, const int *h_idx, int num_v, int num_e,
                   gnnagg_aggregator **out);
+/* same, with the set-up kernel (a row lookup table) issued on `stream` instead of the legacy stream: use it when
+ * d_ptr / d_idx are still being produced on that stream, or when runs follow on a non-blocking stream.
+ * gnnagg_create itself returns with the set-up complete. */
+int gnnagg_create_on(const int *d_ptr, const int *d_idx, const int *h_ptr, const int *h_idx, int num_v, int num_e,
+                     gnnagg_aggregator **out, void *stream);
 int gnnagg_destroy(gnnagg_aggregator *a);
 
 /* edge values of the GCN aggregator: ctor argument of Aggregator_GCN (aggr_gcn.h:365-374) and
  * Aggregator_GCN::updateval (aggr_gcn.h:540-544) / GCN_update_val_impl.  Borrowed. */
 int gnnagg_set_val(gnnagg_aggregator *a, const float *d_val);
+/* same on `stream` (after a locality schedule the values are permuted by a kernel: gnnagg_set_val waits for it,
+ * this variant orders it on the caller's stream) */
+int gnnagg_set_val_on(gnnagg_aggregator *a, const float *d_val, void *stream);
 
 /* replaces Aggregator::schedule / Aggregator_GCN::schedule (aggregator.h:67-99,
  * aggr_gcn.h:501-538) / GCN_schedule_impl, GAT_schedule_impl.  params[0] = par_num or
@@ -126,12 +134,23 @@ int gnnagg_set_val(gnnagg_aggregator *a, const float *d_val);
  * permuted alongside as in aggr_gcn.h:522-537. */
 int gnnagg_schedule_apply(gnnagg_aggregator *a, int kind, const int *params, int nparams, int total_num_v);
 int gnnagg_num_target(const gnnagg_aggregator *a); /* public field Aggregator::num_target */
+int gnnagg_schedule_kind(const gnnagg_aggregator *a); /* GNNAGG_SCHED_* of the schedule in force (NOP before any) */
+/* per-edge data from SCHEDULED edge order (what the scheduled GAT run leaves in gnnagg_gat_edge_weights, like
+ * aggr_gat_fine's newval, aggr_gat.h:192) back to CSR order, the order gnnagg_gat_backward indexes `w` in.  The two
+ * orders coincide for `nop` and `neighbor_grouping` (then this is a copy); after a locality schedule they do not. */
+int gnnagg_sched_to_csr_order(gnnagg_aggregator *a, const float *in_sched, float *out_csr, void *stream);
 /* device views of the uploaded schedule (d_ptr_scheduled, d_idx_scheduled, d_target_scheduled,
  * d_val_scheduled of aggregator.h:132-134 / aggr_gcn.h:549); NULL before a schedule */
 const int *gnnagg_sched_dev_ptr(const gnnagg_aggregator *a);
 const int *gnnagg_sched_dev_idx(const gnnagg_aggregator *a);
 const int *gnnagg_sched_dev_target(const gnnagg_aggregator *a);
 const float *gnnagg_sched_dev_val(const gnnagg_aggregator *a);
+
+/* Optional: builds, now, the per-graph tables the FIRST un-scheduled run for this feature width would otherwise build
+ * (which rows cross item boundaries; one host synchronisation).  After it, runs of that width never synchronise the
+ * host: required before CUDA-graph capture, and used by the multi-GPU path, where a host wait in the middle of a step
+ * could deadlock a process that drives several ranks. */
+int gnnagg_prepare(gnnagg_aggregator *a, int feat, void *stream);
 
 /* GCN aggregation Y = A*X.  replaces Aggregator_GCN::run / run_with_feat (aggr_gcn.h:379-444)
  * / GCN_run_impl and the kernels aggr_gcn (:5-36) [scheduled=0] and aggr_gcn_target (:78-114)
@@ -255,6 +274,58 @@ int gnnagg_spmm_naive(int num_v, const int *d_ptr, const int *d_idx, const float
 int gnnagg_validate(const float *d_ref, const float *d_ans, int64_t num, int *diffnum, void *stream);
 int gnnagg_validate_reordered(const float *d_ref, const float *d_ans, const int *d_map, int num_v, int feat,
                               int *diffnum, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU: 1-D row partition by destination, source-feature halo over NVLink peer memory.
+ * The reference is single-GPU: every driver asserts GPUNUM == 1 (Figure9/main.cu:19); what it
+ * sketched and never built are the per-GPU globals GPUNUM / gptrs / gidxs (include/util.h:39-57),
+ * syncAll (include/util.h:135-142) and the prepare*Multi prototypes (include/data.h:48-58).
+ * These entry points are that missing piece.  Rank r owns the destination rows
+ * [shard_bounds[r], shard_bounds[r+1]) and the matching rows of X; its CSR block keeps GLOBAL
+ * source ids.  A gnnagg_dist handle is ONE rank (one GPU).  Two ways to get connected ranks:
+ *   single process : gnnagg_dist_create(world, devices, ...) -> world handles with peer access on
+ *                    (the shape SURVEY 8(b) names; per-rank calls may be issued from one thread,
+ *                    none of them blocks the host);
+ *   process per GPU: gnnagg_dist_create_rank on the current device, gnnagg_dist_export a
+ *                    GNNAGG_DIST_BLOB_BYTES blob, all-gather the blobs with whatever the caller has
+ *                    (MPI, torch.distributed, a file), gnnagg_dist_connect (cudaIpc mapping).
+ * The X shard lives in library-owned, peer-visible memory (two buffers, gnnagg_dist_x(d, 0|1), so a layer can
+ * write the next layer's input while peers may still read this one's): fill it on `stream`, then run.
+ * A run = stage 0 (edges with local sources) while the remote rows are pulled from the owners' shards by plain
+ * 128-bit loads over NVLink into a compact receive buffer, then one accumulating stage per group of owners as
+ * it lands (`remote_stages` groups; more groups = finer overlap, more passes over Y).  Deterministic: no atomics,
+ * a fixed summation order per (world, remote_stages).  No NCCL, no pack kernel, no send buffer.
+ * ------------------------------------------------------------------------------------------ */
+#define GNNAGG_DIST_MAX_WORLD 16
+#define GNNAGG_DIST_BLOB_BYTES 256
+#define GNNAGG_DIST_NO_EXCHANGE 1 /* run flag: re-use the receive buffer of the previous run (kernels-only timing) */
+typedef struct gnnagg_dist gnnagg_dist;
+int gnnagg_dist_create(int world, const int *devices /* NULL: 0..world-1 */, const int64_t *shard_bounds /* world+1 */,
+                       int feat_cap, gnnagg_dist **out /* [world] */);
+int gnnagg_dist_create_rank(int rank, int world, const int64_t *shard_bounds, int feat_cap, gnnagg_dist **out);
+int gnnagg_dist_export(gnnagg_dist *d, void *blob /* GNNAGG_DIST_BLOB_BYTES */);
+int gnnagg_dist_connect(gnnagg_dist *d, const void *blobs /* world * GNNAGG_DIST_BLOB_BYTES, indexed by rank */);
+int gnnagg_dist_destroy(gnnagg_dist *d);
+/* the rank's row block (borrowed only during the call: the library keeps its own re-indexed per-stage CSRs);
+ * synchronises `stream`.  remote_stages in [1, world-1]. */
+int gnnagg_dist_set_graph(gnnagg_dist *d, const int *d_ptr, const int *d_idx, const float *d_val, int64_t num_e,
+                          int remote_stages, void *stream);
+float *gnnagg_dist_x(gnnagg_dist *d, int buf); /* [rows of the shard, feat] row-major, feat <= feat_cap */
+/* Y = A_block * X  /  H = (A_block * X) * W, with X = buffer `buf` of every rank (all ranks must call with the same
+ * buf and feat).  Asynchronous on `stream`; Y/H may be the other shard buffer. */
+int gnnagg_dist_gcn_run(gnnagg_dist *d, int buf, float *Y, int feat, int flags, void *stream);
+int gnnagg_dist_gcn_layer(gnnagg_dist *d, int buf, const float *W, float *H, int feat_in, int feat_out, int flags,
+                          void *stream);
+/* distinct remote source rows this rank receives per step (in total / per owner), stages and their edge counts */
+int gnnagg_dist_info(const gnnagg_dist *d, int64_t *num_recv, int64_t *recv_counts /* [world] */, int *num_stages,
+                     int64_t *stage_edges /* [num_stages] */);
+/* device timing of the last run: ms[0] halo exchange (first pull issued .. last row landed, comm stream),
+ * ms[1] whole step, ms[2] stage 0, ms[3] dense combination */
+int gnnagg_dist_profile_enable(gnnagg_dist *d, int on);
+int gnnagg_dist_profile_read(gnnagg_dist *d, float *ms /* [4] */);
+/* GNNAGG_ERR_STATE if a kernel of this rank gave up waiting for a peer (bounded spin, 20 s); synchronous */
+int gnnagg_dist_check(gnnagg_dist *d);
+int64_t gnnagg_dist_launch_count(const gnnagg_dist *d);
 
 /* ------------------------------------------------------------------------------------------
  * Host-buffer entry points (what a caller holding HOST arrays uses; bench.py's e2e number).

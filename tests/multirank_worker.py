@@ -1,0 +1,96 @@
+"""torchrun worker of tests/test_gpu_dist.py::test_multi_process_equals_single_gpu (also runnable by hand:
+`torchrun --nproc-per-node N tests/multirank_worker.py`).  Every rank builds the SAME down-scaled R-MAT graph
+(scale 22 by default: 4.2 M vertices / 67 M edges, F = 64), keeps its row block, and runs the peer-memory
+aggregation; rank 0 also runs the whole graph on its one GPU and the results are compared block by block:
+  * against the single-GPU result within the parity gate (summation order differs stage by stage), and
+  * a row sample against the fp64 CPU oracle,
+for several remote-stage settings, plus run-to-run bit equality.  Prints one JSON line per setting on rank 0."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "gnn-computing_b200"))
+
+
+def main():
+    import gnnagg
+    from gnnagg import synth
+    from gnnagg.partition import PeerHalo
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda:%d" % local)
+    dist.init_process_group("nccl", device_id=dev)
+    scale = int(os.environ.get("GNNAGG_MR_SCALE", "22"))
+    n, m, F = 1 << scale, 1 << (scale + 4), 64
+    ptr, idx = synth.rmat_csr(n, m, seed=123, device=dev)          # identical on every rank
+    val = synth.gcn_norm_val(ptr, idx)
+    X = torch.randn((n, F), device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+    # edge-balanced ragged row blocks (split on ptr), as SURVEY 8(e) prescribes
+    hp = ptr.cpu().numpy()
+    from gnnagg import partition
+
+    bounds = [int(b) for b in partition.split_rows(hp, world, "edges")]
+    r0, r1 = bounds[rank], bounds[rank + 1]
+    e0, e1 = int(hp[r0]), int(hp[r1])
+    lptr = (ptr[r0:r1 + 1] - e0).contiguous()
+    lidx, lval = idx[e0:e1].contiguous(), val[e0:e1].contiguous()
+    if rank == 0:
+        single = gnnagg.Aggregator(ptr, idx, val)
+        Y1 = single.gcn_run(X, torch.empty((n, F), device=dev))
+        torch.cuda.synchronize()
+    for stages in sorted({1, 2, world - 1}):
+        if stages < 1:
+            continue
+        ph = PeerHalo(lptr, lidx, lval, bounds, rank, world, F, remote_stages=stages)
+        ph.x(0, F).copy_(X[r0:r1])
+        Y = torch.empty((r1 - r0, F), device=dev)
+        ph.gcn_run(Y, 0, F)
+        Y2 = torch.empty_like(Y)
+        ph.gcn_run(Y2, 0, F)
+        torch.cuda.synchronize()
+        ph.check()
+        same = bool(torch.equal(Y, Y2))
+        # collect the blocks on rank 0
+        if rank == 0:
+            full = torch.empty((n, F), device=dev)
+            full[r0:r1] = Y
+            for r in range(1, world):
+                if bounds[r + 1] > bounds[r]:
+                    dist.recv(full[bounds[r]:bounds[r + 1]], src=r)
+        elif r1 > r0:
+            dist.send(Y, dst=0)
+        flags = torch.tensor([int(same)], device=dev)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            import oracle as orc
+
+            orc.use_all_cores()
+            rows = min(n, 3000)
+            e = int(hp[rows])
+            y64, sc = orc.spmm_f64(np.ascontiguousarray(hp[:rows + 1]), idx[:e].cpu().numpy(), val[:e].cpu().numpy(), X.cpu().numpy())
+            err = np.abs(full[:rows].cpu().numpy().astype(np.float64) - y64) / (1e-5 * sc.astype(np.float64) + 1e-30)
+            # vs the single-GPU result: both are within the gate of the fp64 value, so within twice the bound of each other;
+            # the bound needs sum|terms| of every row: one more GPU pass with |val| and |X|
+            absagg = gnnagg.Aggregator(ptr, idx, val.abs())
+            S = absagg.gcn_run(X.abs(), torch.empty((n, F), device=dev))
+            d = ((full - Y1).abs() / (2e-5 * S + 1e-30)).max().item()
+            line = {"test": "multirank_equals_single_gpu", "world": world, "remote_stages": stages, "graph": "rmat%d" % scale,
+                    "n": n, "m": m, "F": F, "bounds": bounds, "worst_err_over_bound_vs_fp64_oracle": round(float(err.max()), 4),
+                    "worst_diff_over_2x_bound_vs_single_gpu": round(float(d), 4), "bit_reproducible": bool(flags.item()),
+                    "recv_rows_rank0": ph.num_recv, "stage_edges_rank0": ph.stage_edges}
+            line["ok"] = bool(err.max() <= 1.0 and d <= 1.0 and flags.item() == 1)
+            print(json.dumps(line), flush=True)
+        ph.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

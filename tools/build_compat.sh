@@ -18,6 +18,7 @@ build() { # src out
   fi
 }
 build "$ROOT/tests/cpp/dropin_check.cu" "$OUT/dropin_check.out"
+build "$ROOT/tests/cpp/dist_check.cu" "$OUT/dist_check.out"
 REF="${REF:-/root/reference}"
 if [ -d "$REF/Figure9" ]; then
   build "$REF/Figure9/main.cu"    "$OUT/Figure9_main.out"
