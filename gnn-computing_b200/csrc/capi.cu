@@ -237,6 +237,29 @@ static void launch_agg_we(const AggParams &p, cudaStream_t st)
         agg_kernel<32, 2, MODE, SCHED, WE><<<grid, kCtaThreads, 0, st>>>(p);
 }
 
+// CUDA loads a kernel lazily at its first launch, and that load can wait for the device to go idle.  A process that
+// drives several ranks must therefore never launch a kernel for the FIRST time while another rank's kernels spin on a
+// flag this rank has yet to set (dist.cu).  cudaFuncGetAttributes forces the load.
+template <class K>
+static void preload(K kernel)
+{
+    cudaFuncAttributes attr;
+    if (cudaFuncGetAttributes(&attr, kernel) != cudaSuccess) cudaGetLastError();
+}
+
+template <int WE>
+static void preload_gcn_we(int F)
+{
+    if (F <= 32)
+        preload(agg_kernel<8, 1, kModeGCN, false, WE>);
+    else if (F <= 64)
+        preload(agg_kernel<16, 1, kModeGCN, false, WE>);
+    else if (F <= 128)
+        preload(agg_kernel<32, 1, kModeGCN, false, WE>);
+    else
+        preload(agg_kernel<32, 2, kModeGCN, false, WE>);
+}
+
 // rows of a's CSR with more than kFixChunk carry items of EB edges, found once per item size (one host synchronisation)
 static int long_rows_of(gnnagg_aggregator *a, const AggParams &p, int EB, cudaStream_t st, const int **list, int *count,
                         const int2 **records)
@@ -847,6 +870,12 @@ int gnnagg_prepare(gnnagg_aggregator *a, int feat, void *stream)
     if (a->m == 0 || a->n == 0) return GNNAGG_OK;
     const int EB = item_edges_for(a, feat, a->m);
     if (int rc = ensure(a->carry, a->carry_cap, (size_t)cdiv(a->m, EB) * feat)) return rc;
+    if (warp_edges_for(a, a->m) == 128)
+        preload_gcn_we<128>(feat);
+    else
+        preload_gcn_we<kWarpEdges>(feat);
+    preload(agg_fixup_kernel<kModeGCN>);
+    preload(agg_fixup_long_kernel<kModeGCN>);
     AggParams p{};
     p.ptr = a->d_ptr;
     p.item_row = a->d_item_row;

@@ -351,6 +351,22 @@ static cudaError_t ensure_dynamic_smem(Kernel kernel, int slot, int dev, size_t 
     return e;
 }
 
+// forces the (lazy) load of the combination kernels and creates the W-split pool; see capi.cu: preload
+void dense_preload()
+{
+    cudaFuncAttributes attr;
+    if (cudaFuncGetAttributes(&attr, split_w_kernel) != cudaSuccess) cudaGetLastError();
+    if (cudaFuncGetAttributes(&attr, dense_tf32x3_ws_kernel<true>) != cudaSuccess) cudaGetLastError();
+    if (cudaFuncGetAttributes(&attr, dense_tf32x3_ws_kernel<false>) != cudaSuccess) cudaGetLastError();
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) {
+        split_pool(dev);
+        // opt in to the largest dynamic shared memory either variant can ask for, now rather than at the first launch
+        ensure_dynamic_smem(dense_tf32x3_ws_kernel<false>, 0, dev, 2 * ((size_t)2 * kStageBytes + (size_t)2 * 256 * 128));
+        ensure_dynamic_smem(dense_tf32x3_ws_kernel<true>, 1, dev, (size_t)2 * kMaxNK * 4 + (size_t)3 * 2 * kStageBytes);
+    }
+}
+
 int dense_nn_launch(const float *A, const float *B, float *C, int64_t M, int N, int K, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;

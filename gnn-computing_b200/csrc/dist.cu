@@ -339,6 +339,13 @@ int gnnagg_dist_create_rank(int rank, int world, const int64_t *shard_bounds, in
     cudaEventCreateWithFlags(&d->ev_sig, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&d->ev_done, cudaEventDisableTiming);
     for (int s = 0; s < kMaxStages; ++s) cudaEventCreateWithFlags(&d->ev_stage[s], cudaEventDisableTiming);
+    {  // load the step's kernels now: a first launch while a peer's kernels spin on this rank could wait forever
+        cudaFuncAttributes attr;
+        if (cudaFuncGetAttributes(&attr, halo_signal_kernel) != cudaSuccess) cudaGetLastError();
+        if (cudaFuncGetAttributes(&attr, halo_done_kernel) != cudaSuccess) cudaGetLastError();
+        if (cudaFuncGetAttributes(&attr, halo_pull_kernel<8>) != cudaSuccess) cudaGetLastError();
+        dense_preload();
+    }
     d->peer_base[rank] = d->base;
     d->peer_off_x[rank][0] = d->off_x[0];
     d->peer_off_x[rank][1] = d->off_x[1];
@@ -587,8 +594,28 @@ int gnnagg_dist_set_graph(gnnagg_dist *d, const int *d_ptr, const int *d_idx, co
     }
     d->num_e = num_e;
     d->launches += 6 + 3 * d->num_stages;
-    return GNNAGG_OK;
+    return gnnagg_dist_prepare(d, d->feat_cap, stream);
 #undef SG_TRY
+}
+
+int gnnagg_dist_prepare(gnnagg_dist *d, int feat, void *stream)
+{
+    if (!d || d->num_stages == 0) return set_error(GNNAGG_ERR_STATE, "gnnagg_dist_prepare: no graph (gnnagg_dist_set_graph)");
+    if (feat < 4 || (feat & 3) || feat > d->feat_cap) return set_error(GNNAGG_ERR_ARG, "gnnagg_dist_prepare: bad feat");
+    DeviceGuard guard(d->device);
+    for (int s = 0; s < d->num_stages; ++s)
+        if (int rc = gnnagg_prepare(d->stage[s], feat, stream)) return rc;
+    // A*X of the fused layer: allocated here rather than inside the first step for the same reason
+    const size_t need = (size_t)d->rows * feat;
+    if (need > d->ax_cap) {
+        cudaFree(d->ax);
+        d->ax = nullptr;
+        d->ax_cap = 0;
+        DT_TRY(cudaMalloc((void **)&d->ax, (need ? need : 1) * sizeof(float)));
+        d->ax_cap = need;
+    }
+    d->prepared_feat = feat;
+    return GNNAGG_OK;
 }
 
 int gnnagg_dist_info(const gnnagg_dist *d, int64_t *num_recv, int64_t *recv_counts, int *num_stages, int64_t *stage_edges)
@@ -656,7 +683,7 @@ int64_t gnnagg_dist_launch_count(const gnnagg_dist *d)
 static int dist_run(gnnagg_dist *d, int buf, float *Y, const float *W, float *H, int feat_in, int feat_out, int flags,
                     cudaStream_t st)
 {
-    if (!d || !Y || buf < 0 || buf > 1) return set_error(GNNAGG_ERR_ARG, "gnnagg_dist_gcn_run: bad argument");
+    if (!d || (!Y && d->rows > 0) || buf < 0 || buf > 1) return set_error(GNNAGG_ERR_ARG, "gnnagg_dist_gcn_run: bad argument");
     if (!d->connected) return set_error(GNNAGG_ERR_STATE, "gnnagg_dist_gcn_run: peers not connected (gnnagg_dist_connect)");
     if (d->num_stages == 0) return set_error(GNNAGG_ERR_STATE, "gnnagg_dist_gcn_run: no graph (gnnagg_dist_set_graph)");
     if (feat_in < 4 || (feat_in & 3) || feat_in > d->feat_cap)
@@ -664,14 +691,12 @@ static int dist_run(gnnagg_dist *d, int buf, float *Y, const float *W, float *H,
     DeviceGuard guard(d->device);
     const int Wd = d->world;
     const bool exchange = Wd > 1 && !(flags & GNNAGG_DIST_NO_EXCHANGE);
-    // per-stage fix-up tables for this feature width: built (with a host synchronisation) only the first time, and
-    // BEFORE anything of this step is enqueued -- a host wait behind a cross-rank dependency would deadlock a process
-    // that drives several ranks from one thread
-    if (d->prepared_feat != feat_in) {
-        for (int s = 0; s < d->num_stages; ++s)
-            if (int rc = gnnagg_prepare(d->stage[s], feat_in, st)) return rc;
-        d->prepared_feat = feat_in;
-    }
+    // per-stage fix-up tables for this feature width (set_graph builds them for feat_cap).  Building them waits for the
+    // device, which is harmless with one process per GPU; a process that drives SEVERAL ranks must call
+    // gnnagg_dist_prepare for every rank before the first step of a new width (a device-wide wait while another rank's
+    // kernels spin on this rank's signal would never return)
+    if (d->prepared_feat != feat_in)
+        if (int rc = gnnagg_dist_prepare(d, feat_in, st)) return rc;
     const float *xs = reinterpret_cast<const float *>(d->base + d->off_x[buf]);
     if (d->prof) DT_TRY(cudaEventRecord(d->t_m0, st));
     if (exchange) {
@@ -758,7 +783,7 @@ int gnnagg_dist_gcn_run(gnnagg_dist *d, int buf, float *Y, int feat, int flags, 
 
 int gnnagg_dist_gcn_layer(gnnagg_dist *d, int buf, const float *W, float *H, int feat_in, int feat_out, int flags, void *stream)
 {
-    if (!W || !H) return set_error(GNNAGG_ERR_ARG, "gnnagg_dist_gcn_layer: NULL argument");
+    if (!W || (!H && d && d->rows > 0)) return set_error(GNNAGG_ERR_ARG, "gnnagg_dist_gcn_layer: NULL argument");
     return dist_run(d, buf, H, W, H, feat_in, feat_out, flags, (cudaStream_t)stream);
 }
 

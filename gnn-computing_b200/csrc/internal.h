@@ -45,5 +45,7 @@ int sample_subgraph_device(const int *d_ptr, const int *d_idx, const int *d_item
 
 // dense combination on tcgen05 (dense_tc.cu); stream is a cudaStream_t
 int dense_nn_launch(const float *A, const float *B, float *C, int64_t M, int N, int K, void *stream);
+// loads the combination kernels and their per-device state ahead of the first launch (dense_tc.cu)
+void dense_preload();
 
 }  // namespace gnnagg

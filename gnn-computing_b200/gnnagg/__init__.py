@@ -110,6 +110,7 @@ _SIGS = {
     "gnnagg_dist_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gnnagg_dist_destroy": (C.c_int, [C.c_void_p]),
     "gnnagg_dist_set_graph": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "gnnagg_dist_prepare": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "gnnagg_dist_x": (C.c_void_p, [C.c_void_p, C.c_int]),
     "gnnagg_dist_gcn_run": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "gnnagg_dist_gcn_layer": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -310,6 +310,10 @@ int gnnagg_dist_destroy(gnnagg_dist *d);
  * synchronises `stream`.  remote_stages in [1, world-1]. */
 int gnnagg_dist_set_graph(gnnagg_dist *d, const int *d_ptr, const int *d_idx, const float *d_val, int64_t num_e,
                           int remote_stages, void *stream);
+/* builds the per-stage tables for a feature width other than feat_cap (set_graph prepares feat_cap).  Waits for the
+ * device: with one process per GPU the first run of a new width does it by itself; a process driving several ranks
+ * must call it for EVERY rank before the first step of that width. */
+int gnnagg_dist_prepare(gnnagg_dist *d, int feat, void *stream);
 float *gnnagg_dist_x(gnnagg_dist *d, int buf); /* [rows of the shard, feat] row-major, feat <= feat_cap */
 /* Y = A_block * X  /  H = (A_block * X) * W, with X = buffer `buf` of every rank (all ranks must call with the same
  * buf and feat).  Asynchronous on `stream`; Y/H may be the other shard buffer. */
