@@ -417,7 +417,9 @@ def parity_check(wl, max_rows=1024, max_edges=3_000_000):
         ptr, idx, val = wl.ptr, wl.idx, wl.val
         deg_all = (ptr[1:] - ptr[:-1]).long()
         hub = int(torch.argmax(deg_all).item())
-        rows = torch.unique(torch.cat([torch.linspace(0, n - 1, max_rows, device=dev).long(), torch.tensor([hub], device=dev)]))
+        k = min(max_rows, n)
+        spread = (torch.arange(k, device=dev, dtype=torch.int64) * (n - 1)) // max(k - 1, 1)   # integer arithmetic: n ~ 2^25
+        rows = torch.unique(torch.cat([spread, torch.tensor([hub], device=dev)]))
         deg = deg_all[rows]
         keep = torch.cumsum(deg, 0) <= max_edges
         keep[0] = True

@@ -198,11 +198,15 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
                     acc1 = make_float4(acc1.x * inv, acc1.y * inv, acc1.z * inv, acc1.w * inv);
                 }
                 if (MODE == kModeGCN && p.accumulate) {  // each row is stored by exactly one item: plain RMW is safe
-                    if (act0) acc0 = add4(acc0, *reinterpret_cast<const float4 *>(y));
-                    if (act1) acc1 = add4(acc1, *reinterpret_cast<const float4 *>(y + LPR * 4));
+                    // a lane whose partial sum is exactly zero has nothing to add: rows without edges in this sub-CSR
+                    // (most rows of a source slice of a low-degree graph) cost no traffic on Y
+                    const bool z0 = !act0 || is_zero4(acc0), z1 = !act1 || is_zero4(acc1);
+                    if (!z0) stg_f4(y, add4(acc0, *reinterpret_cast<const float4 *>(y)));
+                    if (!z1) stg_f4(y + LPR * 4, add4(acc1, *reinterpret_cast<const float4 *>(y + LPR * 4)));
+                } else {
+                    if (act0) stg_f4(y, acc0);
+                    if (act1) stg_f4(y + LPR * 4, acc1);
                 }
-                if (act0) stg_f4(y, acc0);
-                if (act1) stg_f4(y + LPR * 4, acc1);
             }
             if (!SCHED) {
                 acc0 = make_float4(0.f, 0.f, 0.f, 0.f);

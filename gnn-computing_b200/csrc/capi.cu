@@ -55,6 +55,14 @@ static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 using namespace gnnagg;
 
+constexpr int kMaxSlices = 16;
+// automatic locality slicing (gnnagg_set_locality_slices(a, 0)): X at least this many times the L2, slices of about
+// kLocalitySliceL2Multiples x L2, average degree at least kLocalityMinDegree
+constexpr double kLocalityMinL2Multiples = 8.0;
+constexpr double kLocalitySliceL2Multiples = 2.5;
+constexpr double kLocalityMinDegree = 20.0;
+constexpr int kLocalityMaxAuto = 8;
+
 struct gnnagg_aggregator {
     // borrowed graph
     const int *d_ptr = nullptr, *d_idx = nullptr;
@@ -111,11 +119,17 @@ struct gnnagg_aggregator {
     // the rows of X that slice c+1 gathers are still on their way from the host (source_slices_build_device)
     int host_slices = 0;  // 0 = automatic, > 0 forced slice count, < 0 row-chunk pipeline only (gnnagg_set_host_pipeline)
     int num_slices = 0, slice_width = 0;
-    gnnagg_aggregator *slice[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    gnnagg_aggregator *slice[kMaxSlices] = {nullptr};
     int *sl_ptr = nullptr, *sl_idx = nullptr, *sl_perm = nullptr;
     float *sl_val = nullptr;
     const float *sl_val_of = nullptr;
-    int sl_off[8] = {0}, sl_cnt[8] = {0};
+    int sl_off[kMaxSlices] = {0}, sl_cnt[kMaxSlices] = {0};
+    // locality slices of the device-resident path (gnnagg_set_locality_slices): when X is many times the L2, the
+    // un-scheduled aggregation runs source slice by source slice (sub-CSRs in accumulate mode, deterministic) so that
+    // the rows a slice gathers stay cache resident -- locality_schedule (graph_schedule.h:17-89) without its atomics.
+    // `loc` borrows this aggregator's CSR and owns the slices.
+    int loc_slices = 0;  // 0 = automatic, 1 = off, 2..kMaxSlices forced
+    gnnagg_aggregator *loc = nullptr;
     cudaStream_t in_stream = nullptr;
     cudaEvent_t in_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t in_free = nullptr;
@@ -529,6 +543,97 @@ static int mlp_run_core(gnnagg_aggregator *a, const float *P, float *Y, int F, i
     return launch_agg<kModeMLP, false>(a, p, st);
 }
 
+static void free_slices(gnnagg_aggregator *a);
+
+// builds the source slices on first use and (re)mirrors the edge values into slice order
+static int ensure_slices(gnnagg_aggregator *a, int want, cudaStream_t st)
+{
+    if (a->num_slices != want) {
+        free_slices(a);
+        const int width = (int)cdiv(a->n, want);
+        if (int rc = source_slices_build_device(a->d_ptr, a->d_idx, a->d_item_row, a->num_items, a->n, a->m, want, width,
+                                                &a->sl_ptr, &a->sl_idx, &a->sl_perm, a->sl_off, a->sl_cnt, st))
+            return rc;
+        const size_t padded = (size_t)a->m + 4 * (size_t)want;
+        if (cudaMalloc((void **)&a->sl_val, padded * sizeof(float)) != cudaSuccess) {
+            free_slices(a);
+            return set_error(GNNAGG_ERR_CUDA, "host pipeline: out of device memory for the source slices");
+        }
+        for (int c = 0; c < want; ++c) {
+            gnnagg_aggregator *s = new gnnagg_aggregator();
+            a->slice[c] = s;
+            s->d_ptr = a->sl_ptr + (size_t)c * ((size_t)a->n + 1);
+            s->d_idx = a->sl_idx + a->sl_off[c];
+            s->d_val = a->sl_val + a->sl_off[c];
+            s->n = a->n;
+            s->m = a->sl_cnt[c];
+            s->warp_edges = a->warp_edges ? a->warp_edges : (a->m < kSmallGraphEdges ? 128 : kWarpEdges);  // as the whole graph
+            if (int rc = build_item_rows(s, s->d_ptr, s->n, s->m, &s->d_item_row, &s->num_items, st)) {
+                free_slices(a);
+                return rc;
+            }
+        }
+        a->num_slices = want;
+        a->slice_width = width;
+        a->launches += 6 + 3 * want;
+    }
+    if (a->sl_val_of != a->d_val) {
+        for (int c = 0; c < want; ++c) {
+            if (a->sl_cnt[c] == 0) continue;
+            gather_val_kernel<<<(unsigned)cdiv(a->sl_cnt[c], 256), 256, 0, st>>>(a->d_val, a->sl_perm + a->sl_off[c],
+                                                                              a->sl_val + a->sl_off[c], a->sl_cnt[c]);
+            LAUNCH_CHECK(a);
+        }
+        a->sl_val_of = a->d_val;
+    }
+    return GNNAGG_OK;
+}
+
+
+// how many source slices the device-resident un-scheduled aggregation uses for this feature width (1 = none)
+static int locality_slices_for(const gnnagg_aggregator *a, int F)
+{
+    if (a->loc_slices >= 1) return a->loc_slices < kMaxSlices ? a->loc_slices : kMaxSlices;
+    // automatic: worth it when X is many times the L2 (the gathers of a slice then stay resident where those of the
+    // whole graph do not) and rows are long enough that the extra passes over Y stay small next to the gathers
+    int dev = 0, l2 = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev) != cudaSuccess || l2 <= 0)
+        return 1;
+    const double x_bytes = 4.0 * (double)a->n * F;
+    if (x_bytes < kLocalityMinL2Multiples * (double)l2 || a->m < kSmallGraphEdges) return 1;
+    if ((double)a->m < kLocalityMinDegree * (double)a->n) return 1;
+    int S = (int)(x_bytes / (kLocalitySliceL2Multiples * (double)l2) + 0.999);
+    return S < 2 ? 1 : (S > kLocalityMaxAuto ? kLocalityMaxAuto : S);
+}
+
+// Y (+)= A X slice by slice over the source ranges; same result as the un-sliced run up to fp32 summation order
+static int gcn_run_sliced(gnnagg_aggregator *a, const float *X, float *Y, int F, int S, cudaStream_t st, int accumulate)
+{
+    if (!a->loc) {
+        a->loc = new gnnagg_aggregator();
+        a->loc->d_ptr = a->d_ptr;
+        a->loc->d_idx = a->d_idx;
+        a->loc->n = a->n;
+        a->loc->m = a->m;
+        a->loc->d_item_row = a->d_item_row;  // borrowed
+        a->loc->num_items = a->num_items;
+    }
+    a->loc->warp_edges = a->warp_edges;
+    a->loc->d_val = a->d_val;
+    const int64_t before_build = a->loc->launches;
+    if (int rc = ensure_slices(a->loc, S, st)) return rc;
+    a->launches += a->loc->launches - before_build;
+    PROF_RECORD(a, 1, st);
+    for (int c = 0; c < S; ++c) {
+        gnnagg_aggregator *s = a->loc->slice[c];
+        const int64_t before = s->launches;
+        if (int rc = gcn_run_core(s, X, Y, F, 0, st, accumulate || c > 0)) return rc;
+        a->launches += s->launches - before;
+    }
+    PROF_RECORD(a, 2, st);
+    return GNNAGG_OK;
+}
+
 // timing brackets: ev[0] call entry, ev[3] end of the aggregation part, ev[4] end of the call
 static int gcn_run_impl(gnnagg_aggregator *a, const float *X, float *Y, int F, int scheduled, cudaStream_t st,
                         bool last = true, int accumulate = 0)
@@ -538,7 +643,14 @@ static int gcn_run_impl(gnnagg_aggregator *a, const float *X, float *Y, int F, i
         CUDA_TRY(cudaEventRecord(a->ev[1], st));
         CUDA_TRY(cudaEventRecord(a->ev[2], st));
     }
-    if (int rc = gcn_run_core(a, X, Y, F, scheduled, st, accumulate)) return rc;
+    int S = 1;
+    if (a && !scheduled && a->n > 0 && a->m > 0 && X && Y && check_feat(F) == GNNAGG_OK && a->d_val) S = locality_slices_for(a, F);
+    if (S > 1) {
+        if (!aligned16(X) || !aligned16(Y)) return set_error(GNNAGG_ERR_ARG, "X and Y must be 16-byte aligned");
+        if (int rc = gcn_run_sliced(a, X, Y, F, S, st, accumulate)) return rc;
+    } else if (int rc = gcn_run_core(a, X, Y, F, scheduled, st, accumulate)) {
+        return rc;
+    }
     PROF_RECORD(a, 3, st);
     if (last) PROF_RECORD(a, 4, st);
     return GNNAGG_OK;
@@ -595,7 +707,7 @@ static void free_long_rows(gnnagg_aggregator *a)
 
 static void free_slices(gnnagg_aggregator *a)
 {
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < kMaxSlices; ++c) {
         if (!a->slice[c]) continue;
         cudaFree(a->slice[c]->d_item_row);
         cudaFree(a->slice[c]->carry);
@@ -696,6 +808,11 @@ int gnnagg_destroy(gnnagg_aggregator *a)
     free_schedule(a);
     free_transpose(a);
     free_slices(a);
+    if (a->loc) {
+        free_slices(a->loc);  // its CSR and item table are this aggregator's
+        delete a->loc;
+        a->loc = nullptr;
+    }
     free_long_rows(a);
     for (int i = 0; i < 8; ++i)
         if (a->in_done[i]) cudaEventDestroy(a->in_done[i]);
@@ -737,6 +854,7 @@ int gnnagg_set_val_on(gnnagg_aggregator *a, const float *d_val, void *stream)
     a->d_val = d_val;
     a->t_val_of = nullptr;  // same pointer, possibly new contents (aggr_gcn.h:540-544): re-mirror on the next backward
     a->sl_val_of = nullptr;
+    if (a->loc) a->loc->sl_val_of = nullptr;
     if (a->sched_kind == GNNAGG_SCHED_NOP) return GNNAGG_OK;
     if (a->s_perm) {  // locality kinds keep a permuted copy (aggr_gcn.h:522-537)
         if (!a->s_val) CUDA_TRY(cudaMalloc((void **)&a->s_val, (size_t)(a->sched_edges ? a->sched_edges : 1) * sizeof(float)));
@@ -827,6 +945,13 @@ int gnnagg_set_warp_edges(gnnagg_aggregator *a, int warp_edges)
         return set_error(GNNAGG_ERR_ARG, "gnnagg_set_warp_edges: 0, 128 or 512");
     a->warp_edges = warp_edges;
     if (a->tr) a->tr->warp_edges = warp_edges;
+    return GNNAGG_OK;
+}
+
+int gnnagg_set_locality_slices(gnnagg_aggregator *a, int slices)
+{
+    if (!a || slices < 0 || slices > kMaxSlices) return set_error(GNNAGG_ERR_ARG, "gnnagg_set_locality_slices: 0 (automatic), 1 (off) .. 16");
+    a->loc_slices = slices;
     return GNNAGG_OK;
 }
 
@@ -1255,50 +1380,6 @@ int gnnagg_validate_reordered(const float *d_ref, const float *d_ans, const int 
 // ------------------------------------------------------------------ host-buffer entry points
 constexpr int kHostChunks = 4;
 constexpr int kHostSlices = 4;
-
-// builds the source slices on first use and (re)mirrors the edge values into slice order
-static int ensure_slices(gnnagg_aggregator *a, int want, cudaStream_t st)
-{
-    if (a->num_slices != want) {
-        free_slices(a);
-        const int width = (int)cdiv(a->n, want);
-        if (int rc = source_slices_build_device(a->d_ptr, a->d_idx, a->d_item_row, a->num_items, a->n, a->m, want, width,
-                                                &a->sl_ptr, &a->sl_idx, &a->sl_perm, a->sl_off, a->sl_cnt, st))
-            return rc;
-        const size_t padded = (size_t)a->m + 4 * (size_t)want;
-        if (cudaMalloc((void **)&a->sl_val, padded * sizeof(float)) != cudaSuccess) {
-            free_slices(a);
-            return set_error(GNNAGG_ERR_CUDA, "host pipeline: out of device memory for the source slices");
-        }
-        for (int c = 0; c < want; ++c) {
-            gnnagg_aggregator *s = new gnnagg_aggregator();
-            a->slice[c] = s;
-            s->d_ptr = a->sl_ptr + (size_t)c * ((size_t)a->n + 1);
-            s->d_idx = a->sl_idx + a->sl_off[c];
-            s->d_val = a->sl_val + a->sl_off[c];
-            s->n = a->n;
-            s->m = a->sl_cnt[c];
-            s->warp_edges = a->warp_edges ? a->warp_edges : (a->m < kSmallGraphEdges ? 128 : kWarpEdges);  // as the whole graph
-            if (int rc = build_item_rows(s, s->d_ptr, s->n, s->m, &s->d_item_row, &s->num_items, st)) {
-                free_slices(a);
-                return rc;
-            }
-        }
-        a->num_slices = want;
-        a->slice_width = width;
-        a->launches += 6 + 3 * want;
-    }
-    if (a->sl_val_of != a->d_val) {
-        for (int c = 0; c < want; ++c) {
-            if (a->sl_cnt[c] == 0) continue;
-            gather_val_kernel<<<(unsigned)cdiv(a->sl_cnt[c], 256), 256, 0, st>>>(a->d_val, a->sl_perm + a->sl_off[c],
-                                                                              a->sl_val + a->sl_off[c], a->sl_cnt[c]);
-            LAUNCH_CHECK(a);
-        }
-        a->sl_val_of = a->d_val;
-    }
-    return GNNAGG_OK;
-}
 
 static int ensure_in_stream(gnnagg_aggregator *a)
 {

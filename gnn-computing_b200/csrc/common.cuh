@@ -111,6 +111,7 @@ __device__ __forceinline__ float4 add4(const float4 &a, const float4 &b)
 {
     return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
 }
+__device__ __forceinline__ bool is_zero4(const float4 &a) { return a.x == 0.f && a.y == 0.f && a.z == 0.f && a.w == 0.f; }
 // 128-bit reduction into global memory (RED.E.ADD.F32x4 on sm_90+)
 __device__ __forceinline__ void red_add_f4(float *p, const float4 &v) { atomicAdd(reinterpret_cast<float4 *>(p), v); }
 

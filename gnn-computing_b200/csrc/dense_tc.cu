@@ -99,34 +99,41 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r)
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Warp-specialised version (the one dense_nn_launch uses).  The two kernels above funnel everything through one
-// __syncthreads per K chunk: thread 0 waits for W, issues the MMAs and only then converts its own share of the
-// next chunk, so the other seven warps spend a third of their time at the barrier (ncu: 34 % stall_barrier), and
-// nobody loads A while the epilogue drains TMEM (23 % of the samples sit on tcgen05.ld).  Here the roles never
-// meet at a CTA barrier inside the loop; they hand stages to each other through mbarriers:
-//   warps 4-7  producers : A chunk (128 rows x 32 floats) global -> registers (two chunks ahead) -> hi/lo -> ring stage;
-//                          arrive on full_a[stage]
-//   warp  8    MMA       : one lane waits full_a (and full_w), issues the 12 tcgen05.mma of the chunk into accumulator
+// Warp-specialised kernel.  Roles never meet at a CTA barrier inside the loop; they hand stages to each other
+// through mbarriers:
+//   warps 4-11 producers : A chunk (128 rows x 32 floats) global -> registers -> hi/lo -> ring stage; arrive on
+//                          full_a[stage].  Each thread keeps FOUR chunks of loads in flight (4 x 4 float4 registers
+//                          with fixed roles per unrolled step: the loads issued in step c are first read in step c+4),
+//                          64 KB per SM -- the round-1 kernel had 4 producer warps and 32 KB in flight and ran at the
+//                          speed that much latency hiding allows (2.3 TB/s)
+//   warp  12   MMA       : one lane waits full_a (and full_w), issues the 12 tcgen05.mma of the chunk into accumulator
 //                          buffer tile&1, tcgen05.commit -> empty[stage]; after the last chunk commit -> acc_full[buffer]
-//   warp  9    W loader  : streamed W: bulk copies of the two W chunks of a stage as soon as the stage is empty;
+//   warp  13   W loader  : streamed W: bulk copies of the two W chunks of a stage as soon as the stage is empty;
 //                          resident W: one set of bulk copies at the start
-//   warps 0-3  epilogue  : wait acc_full[buffer], tcgen05.ld their 32 TMEM lanes, store rows, arrive on acc_empty[buffer]
+//   warps 0-3  epilogue  : wait acc_full[buffer], tcgen05.ld their 32 TMEM lanes 32 columns at a time, TRANSPOSE the
+//                          32 x 32 block through a padded shared-memory tile and store 4 rows x 128 B per instruction
+//                          (the round-1 epilogue stored 16 B from 32 different rows per instruction: twice the L2 write
+//                          requests, half a sector each); arrive on acc_empty[buffer]
 // The accumulator is double-buffered in TMEM (2 x N columns <= 512), so the epilogue of tile t overlaps the main loop
 // of tile t+1 and A loads never stop.  W is split once per call into global memory (split_w_kernel: hi/lo in the
 // canonical chunk layout) instead of once per CTA.  RESIDENT (2*K*N*4 <= 128 KB): every CTA pulls all of it into
-// shared memory with bulk copies while the producers already fill the ring (3 stages); otherwise the two W chunks
-// of a stage arrive by bulk copy per stage (2 stages).
+// shared memory with bulk copies while the producers already fill the ring; otherwise the two W chunks of a stage
+// arrive by bulk copy per stage.  Ring depth S (2..4) = whatever fits beside W and the epilogue tiles.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kWsThreads = 320;
+constexpr int kWsThreads = 448;
+constexpr int kProducerThreads = 256;
+constexpr int kMaxStages = 4;
+constexpr int kEpiRowBytes = (32 + 4) * 4;                 // 32 floats + 16 B of padding: conflict-free both ways
+constexpr int kEpiBytes = 4 * 32 * kEpiRowBytes;           // one 32 x 32 tile per epilogue warp
 
 template <bool RESIDENT>
 __global__ void __launch_bounds__(kWsThreads, 1)
 dense_tf32x3_ws_kernel(const float *__restrict__ A, const float *__restrict__ Whi, const float *__restrict__ Wlo,
-                       float *__restrict__ C, int64_t M, int N, int K, int acc_cols)
+                       float *__restrict__ C, int64_t M, int N, int K, int acc_cols, int S)
 {
-    constexpr int S = RESIDENT ? 3 : 2;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t s_full_a[S], s_full_w[S], s_empty[S], s_acc_full[2], s_acc_empty[2], s_w_ready;
+    __shared__ __align__(8) uint64_t s_full_a[kMaxStages], s_full_w[kMaxStages], s_empty[kMaxStages], s_acc_full[2], s_acc_empty[2],
+        s_w_ready;
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -135,10 +142,11 @@ dense_tf32x3_ws_kernel(const float *__restrict__ A, const float *__restrict__ Wh
     const uint32_t w_bytes = RESIDENT ? 2u * (uint32_t)chunks * b_chunk : 0u;
     const uint32_t stage_bytes = RESIDENT ? 2u * kStageBytes : 2u * kStageBytes + 2u * b_chunk;  // [Ahi | Alo | (Bhi | Blo)]
     uint8_t *const ring = smem + w_bytes;
+    uint8_t *const epi = ring + (uint32_t)S * stage_bytes;
     const uint32_t sbo = (kChunkK / 4) * 128;  // 1024 B between 8-row core-matrix groups, both operands
     const int64_t tiles = (M + kTileM - 1) / kTileM;
 
-    if (warp == 8) {
+    if (warp == 12) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
                      "r"((uint32_t)(2 * acc_cols))
                      : "memory");
@@ -146,7 +154,7 @@ dense_tf32x3_ws_kernel(const float *__restrict__ A, const float *__restrict__ Wh
     }
     if (tid == 0) {
         for (int i = 0; i < S; ++i) {
-            mbar_init(smem_u32(&s_full_a[i]), 128);
+            mbar_init(smem_u32(&s_full_a[i]), kProducerThreads);
             mbar_init(smem_u32(&s_full_w[i]), 1);
             mbar_init(smem_u32(&s_empty[i]), 1);
         }
@@ -162,26 +170,26 @@ dense_tf32x3_ws_kernel(const float *__restrict__ A, const float *__restrict__ Wh
     tc_fence_after();
     const uint32_t tmem = s_tmem;
 
-    if (warp >= 4 && warp < 8) {
+    if (warp >= 4 && warp < 12) {
         // ---------------------------------------------------------------- producers
         const int t = tid - 128;
-        auto fetch = [&](int64_t tile, int kc, float4 (&v)[8]) {
+        // element u = p * 256 + t of a stage: row = (u >> 6) * 8 + (u & 7), 16-byte K piece kq = (u >> 3) & 7.
+        // Eight consecutive lanes cover the 8 rows of one core matrix (conflict-free 128-byte shared-memory phases);
+        // a warp-wide load touches 8 rows x 64 B, whole sectors.
+        auto fetch = [&](int64_t tile, int kc, float4 (&v)[4]) {
 #pragma unroll
-            for (int p = 0; p < 8; ++p) {
-                const int u = p * 128 + t;
+            for (int p = 0; p < 4; ++p) {
+                const int u = p * kProducerThreads + t;
                 const int r8 = u & 7, kq = (u >> 3) & 7, rb = u >> 6;
                 const int64_t row = tile * kTileM + rb * 8 + r8;
                 v[p] = (tile < tiles && row < M) ? ldg_f4(A + (size_t)row * K + kc * kChunkK + kq * 4)
                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
-        // Three register buffers with FIXED roles per unrolled step: the loads issued in step c are first read in step
-        // c+2, so two chunks (32 KB per SM) really are in flight.  (Rotating one queue with register moves at the end of
-        // every iteration made each step wait for the loads it had just issued -- one step of lookahead in name only.)
-        float4 b0[8], b1[8], b2[8];
+        float4 b0[4], b1[4], b2[4], b3[4];
         int64_t ftile = blockIdx.x;
         int fkc = 0;
-        auto fetch_next = [&](float4 (&v)[8]) {
+        auto fetch_next = [&](float4 (&v)[4]) {
             fetch(ftile, fkc, v);
             if (++fkc == chunks) {
                 fkc = 0;
@@ -190,17 +198,15 @@ dense_tf32x3_ws_kernel(const float *__restrict__ A, const float *__restrict__ Wh
         };
         const int64_t my_tiles = (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
         const uint32_t total = (uint32_t)(my_tiles * chunks);
-        uint32_t c = 0;
-        auto step = [&](const float4 (&use)[8], float4 (&fill)[8]) {
-            fetch_next(fill);
-            const uint32_t stage = c % S;
-            if (c >= (uint32_t)S) mbar_wait(smem_u32(&s_empty[stage]), ((c / S) - 1) & 1);  // MMAs of the previous use retired
+        uint32_t c = 0, stage = 0, round = 0;  // round = c / S
+        auto step = [&](float4 (&buf)[4]) {
+            if (round > 0) mbar_wait(smem_u32(&s_empty[stage]), (round - 1) & 1);  // MMAs of the previous use retired
             uint8_t *aHi = ring + stage * stage_bytes, *aLo = aHi + kStageBytes;
 #pragma unroll
-            for (int p = 0; p < 8; ++p) {
-                const int u = p * 128 + t;
+            for (int p = 0; p < 4; ++p) {
+                const int u = p * kProducerThreads + t;
                 const int r8 = u & 7, kq = (u >> 3) & 7, rb = u >> 6;
-                const float4 v = use[p];
+                const float4 v = buf[p];
                 const float4 h = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
                 const float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
                 const uint32_t off = (uint32_t)rb * sbo + (uint32_t)kq * 128u + (uint32_t)r8 * 16u;
@@ -209,31 +215,39 @@ dense_tf32x3_ws_kernel(const float *__restrict__ A, const float *__restrict__ Wh
             }
             fence_proxy_async();  // generic-proxy stores visible to the tensor core's async proxy
             mbar_arrive(smem_u32(&s_full_a[stage]));
+            fetch_next(buf);      // refill this buffer: first read four steps from now
             ++c;
+            if (++stage == (uint32_t)S) {
+                stage = 0;
+                ++round;
+            }
         };
         fetch_next(b0);
         fetch_next(b1);
+        fetch_next(b2);
+        fetch_next(b3);
         for (;;) {
             if (c >= total) break;
-            step(b0, b2);
+            step(b0);
             if (c >= total) break;
-            step(b1, b0);
+            step(b1);
             if (c >= total) break;
-            step(b2, b1);
+            step(b2);
+            if (c >= total) break;
+            step(b3);
         }
-    } else if (warp == 8) {
+    } else if (warp == 12) {
         // ---------------------------------------------------------------- MMA issue (one lane)
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
             if (RESIDENT) mbar_wait(smem_u32(&s_w_ready), 0);
-            uint32_t c = 0, t = 0;
+            uint32_t stage = 0, par = 0, t = 0;
             for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++t) {
                 const uint32_t buf = t & 1;
                 if (t >= 2) mbar_wait(smem_u32(&s_acc_empty[buf]), ((t >> 1) - 1) & 1);  // epilogue drained this buffer
                 tc_fence_after();
                 const uint32_t d_tmem = tmem + buf * (uint32_t)acc_cols;
-                for (int kc = 0; kc < chunks; ++kc, ++c) {
-                    const uint32_t stage = c % S, par = (c / S) & 1;
+                for (int kc = 0; kc < chunks; ++kc) {
                     mbar_wait(smem_u32(&s_full_a[stage]), par);
                     if (!RESIDENT) mbar_wait(smem_u32(&s_full_w[stage]), par);
                     tc_fence_after();
@@ -249,65 +263,79 @@ dense_tf32x3_ws_kernel(const float *__restrict__ A, const float *__restrict__ Wh
                         tc_mma_tf32(d_tmem, dah, dbh, idesc, 1u);
                     }
                     tc_commit(smem_u32(&s_empty[stage]));
+                    if (++stage == (uint32_t)S) {
+                        stage = 0;
+                        par ^= 1u;
+                    }
                 }
                 tc_commit(smem_u32(&s_acc_full[buf]));
             }
         }
-    } else {
-        // ---------------------------------------------------------------- warps 0-3 (epilogue) and 9 (W)
-        if (warp == 9) {
-            if (RESIDENT && lane == 0) {
-                // all of W (pre-split, chunk layout) into shared memory once: 2 * chunks bulk copies on one mbarrier
-                const uint32_t ready = smem_u32(&s_w_ready);
-                mbar_expect_tx(ready, w_bytes);
+    } else if (warp == 13) {
+        // ---------------------------------------------------------------- W loader
+        if (RESIDENT && lane == 0) {
+            // all of W (pre-split, chunk layout) into shared memory once: 2 * chunks bulk copies on one mbarrier
+            const uint32_t ready = smem_u32(&s_w_ready);
+            mbar_expect_tx(ready, w_bytes);
+            for (int kc = 0; kc < chunks; ++kc) {
+                bulk_g2s(smem_u32(smem) + (uint32_t)kc * b_chunk, Whi + (size_t)kc * N * 32, b_chunk, ready);
+                bulk_g2s(smem_u32(smem) + (uint32_t)(chunks + kc) * b_chunk, Wlo + (size_t)kc * N * 32, b_chunk, ready);
+            }
+        }
+        if (!RESIDENT && lane == 0) {
+            uint32_t stage = 0, round = 0;
+            for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
                 for (int kc = 0; kc < chunks; ++kc) {
-                    bulk_g2s(smem_u32(smem) + (uint32_t)kc * b_chunk, Whi + (size_t)kc * N * 32, b_chunk, ready);
-                    bulk_g2s(smem_u32(smem) + (uint32_t)(chunks + kc) * b_chunk, Wlo + (size_t)kc * N * 32, b_chunk, ready);
-                }
-            }
-            if (!RESIDENT && lane == 0) {
-                uint32_t c = 0;
-                for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-                    for (int kc = 0; kc < chunks; ++kc, ++c) {
-                        const uint32_t stage = c % S;
-                        if (c >= (uint32_t)S) mbar_wait(smem_u32(&s_empty[stage]), ((c / S) - 1) & 1);
-                        const uint32_t full = smem_u32(&s_full_w[stage]);
-                        const uint32_t dst = smem_u32(ring + stage * stage_bytes) + 2u * kStageBytes;
-                        mbar_expect_tx(full, 2u * b_chunk);
-                        bulk_g2s(dst, Whi + (size_t)kc * N * 32, b_chunk, full);
-                        bulk_g2s(dst + b_chunk, Wlo + (size_t)kc * N * 32, b_chunk, full);
+                    if (round > 0) mbar_wait(smem_u32(&s_empty[stage]), (round - 1) & 1);
+                    const uint32_t full = smem_u32(&s_full_w[stage]);
+                    const uint32_t dst = smem_u32(ring + stage * stage_bytes) + 2u * kStageBytes;
+                    mbar_expect_tx(full, 2u * b_chunk);
+                    bulk_g2s(dst, Whi + (size_t)kc * N * 32, b_chunk, full);
+                    bulk_g2s(dst + b_chunk, Wlo + (size_t)kc * N * 32, b_chunk, full);
+                    if (++stage == (uint32_t)S) {
+                        stage = 0;
+                        ++round;
                     }
                 }
             }
-        } else {
-            uint32_t t = 0;
-            for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++t) {
-                const uint32_t buf = t & 1;
-                mbar_wait(smem_u32(&s_acc_full[buf]), (t >> 1) & 1);
-                tc_fence_after();
-                const int64_t row = tile * kTileM + warp * 32 + lane;
-                const uint32_t taddr = tmem + buf * (uint32_t)acc_cols + ((uint32_t)(warp * 32) << 16);
-                for (int col = 0; col < N; col += 32) {  // N is a multiple of 32: two 16-column TMEM loads per wait
-                    uint32_t r[32];
-                    tmem_ld16(taddr + (uint32_t)col, r);
-                    tmem_ld16(taddr + (uint32_t)col + 16u, r + 16);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (row < M) {
-                        float *dst = C + (size_t)row * N + col;
+        }
+    } else {
+        // ---------------------------------------------------------------- warps 0-3: epilogue
+        uint8_t *const my_tile = epi + warp * (32 * kEpiRowBytes);
+        uint32_t t = 0;
+        for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++t) {
+            const uint32_t buf = t & 1;
+            mbar_wait(smem_u32(&s_acc_full[buf]), (t >> 1) & 1);
+            tc_fence_after();
+            const int64_t row0 = tile * kTileM + warp * 32;  // first of this warp's 32 rows
+            const uint32_t taddr = tmem + buf * (uint32_t)acc_cols + ((uint32_t)(warp * 32) << 16);
+            for (int col = 0; col < N; col += 32) {  // N is a multiple of 32: two 16-column TMEM loads per wait
+                uint32_t r[32];
+                tmem_ld16(taddr + (uint32_t)col, r);
+                tmem_ld16(taddr + (uint32_t)col + 16u, r + 16);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                // lane = row: write the row's 32 values, then read the block back 4 rows x 128 B at a time
+                float4 *mine = reinterpret_cast<float4 *>(my_tile + lane * kEpiRowBytes);
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4)
-                            stg_f4(dst + i, make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
-                                                        __uint_as_float(r[i + 3])));
-                    }
+                for (int i = 0; i < 8; ++i)
+                    mine[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                                          __uint_as_float(r[4 * i + 3]));
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int rr = j * 4 + (lane >> 3);
+                    const float4 v = *reinterpret_cast<const float4 *>(my_tile + rr * kEpiRowBytes + (lane & 7) * 16);
+                    if (row0 + rr < M) stg_f4(C + (size_t)(row0 + rr) * N + col + (lane & 7) * 4, v);
                 }
-                tc_fence_before();
-                mbar_arrive(smem_u32(&s_acc_empty[buf]));
+                __syncwarp();  // the tile is rewritten by the next column block
             }
+            tc_fence_before();
+            mbar_arrive(smem_u32(&s_acc_empty[buf]));
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8)
+    if (warp == 12)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)(2 * acc_cols)) : "memory");
 }
 
@@ -362,8 +390,8 @@ void dense_preload()
     if (cudaGetDevice(&dev) == cudaSuccess) {
         split_pool(dev);
         // opt in to the largest dynamic shared memory either variant can ask for, now rather than at the first launch
-        ensure_dynamic_smem(dense_tf32x3_ws_kernel<false>, 0, dev, 2 * ((size_t)2 * kStageBytes + (size_t)2 * 256 * 128));
-        ensure_dynamic_smem(dense_tf32x3_ws_kernel<true>, 1, dev, (size_t)2 * kMaxNK * 4 + (size_t)3 * 2 * kStageBytes);
+        ensure_dynamic_smem(dense_tf32x3_ws_kernel<false>, 0, dev, 227 * 1024 - 1024);
+        ensure_dynamic_smem(dense_tf32x3_ws_kernel<true>, 1, dev, 227 * 1024 - 1024);
     }
 }
 
@@ -391,14 +419,21 @@ int dense_nn_launch(const float *A, const float *B, float *C, int64_t M, int N, 
     float *whi = wsplit, *wlo = wsplit + (size_t)K * N;
     split_w_kernel<<<(K * N + 255) / 256, 256, 0, st>>>(B, whi, wlo, K, N);
     cudaError_t e = cudaSuccess;
+    constexpr size_t kSmemBudget = 227 * 1024 - 1024;  // opt-in limit minus the static barriers
     if (N * K > kMaxNK) {  // W does not fit in shared memory next to the A ring: stream it stage by stage
-        const size_t smem_s = 2 * ((size_t)2 * kStageBytes + (size_t)2 * N * 128);
+        const size_t stage = (size_t)2 * kStageBytes + (size_t)2 * N * 128;
+        int S = (int)((kSmemBudget - kEpiBytes) / stage);
+        S = S > kMaxStages ? kMaxStages : S;
+        const size_t smem_s = (size_t)S * stage + kEpiBytes;
         e = ensure_dynamic_smem(dense_tf32x3_ws_kernel<false>, 0, dev, smem_s);
-        if (e == cudaSuccess) dense_tf32x3_ws_kernel<false><<<grid, kWsThreads, smem_s, st>>>(A, whi, wlo, C, M, N, K, acc_cols);
+        if (e == cudaSuccess) dense_tf32x3_ws_kernel<false><<<grid, kWsThreads, smem_s, st>>>(A, whi, wlo, C, M, N, K, acc_cols, S);
     } else {
-        const size_t smem = (size_t)2 * N * K * 4 + (size_t)3 * 2 * kStageBytes;  // W hi/lo resident + 3 ring stages
+        const size_t wres = (size_t)2 * N * K * 4;  // W hi/lo resident
+        int S = (int)((kSmemBudget - kEpiBytes - wres) / ((size_t)2 * kStageBytes));
+        S = S > kMaxStages ? kMaxStages : S;
+        const size_t smem = wres + (size_t)S * 2 * kStageBytes + kEpiBytes;
         e = ensure_dynamic_smem(dense_tf32x3_ws_kernel<true>, 1, dev, smem);
-        if (e == cudaSuccess) dense_tf32x3_ws_kernel<true><<<grid, kWsThreads, smem, st>>>(A, whi, wlo, C, M, N, K, acc_cols);
+        if (e == cudaSuccess) dense_tf32x3_ws_kernel<true><<<grid, kWsThreads, smem, st>>>(A, whi, wlo, C, M, N, K, acc_cols, S);
     }
     if (e == cudaSuccess) e = cudaPeekAtLastError();
     cudaFreeAsync(wsplit, st);

@@ -100,6 +100,7 @@ _SIGS = {
     "gnnagg_launch_count": (C.c_int64, [C.c_void_p]),
     "gnnagg_set_warp_edges": (C.c_int, [C.c_void_p, C.c_int]),
     "gnnagg_set_host_pipeline": (C.c_int, [C.c_void_p, C.c_int]),
+    "gnnagg_set_locality_slices": (C.c_int, [C.c_void_p, C.c_int]),
     "gnnagg_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "gnnagg_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "gnnagg_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
@@ -333,6 +334,9 @@ class Aggregator:
 
     def set_warp_edges(self, warp_edges):
         check(lib().gnnagg_set_warp_edges(self.h, int(warp_edges)))
+
+    def set_locality_slices(self, slices):
+        check(lib().gnnagg_set_locality_slices(self.h, int(slices)))
 
     def set_host_pipeline(self, slices):
         check(lib().gnnagg_set_host_pipeline(self.h, int(slices)))

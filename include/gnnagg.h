@@ -351,6 +351,16 @@ int gnnagg_gat_run_host(gnnagg_aggregator *a, const float *h_X, const float *h_a
  * Results are deterministic for a given setting; slices change the fp32 summation order (slice by slice). */
 int gnnagg_set_host_pipeline(gnnagg_aggregator *a, int slices);
 
+/* Locality slices of the device-resident, un-scheduled GCN aggregation / layer -- the idea of locality_schedule
+ * (graph_schedule.h:17-89: process the edges source range by source range so that the gathered rows stay in cache)
+ * without its float atomics: the CSR is split once, on the GPU, into `slices` sub-CSRs by source range and the
+ * deterministic kernel accumulates them one after the other; lanes whose partial sum is zero skip the pass over Y.
+ *   0  automatic (default): only when X is >= 8x the L2 and the average degree is >= 20 (products-shape F=256: 8
+ *      slices); the BASELINE.json reddit / proteins / arxiv shapes run un-sliced
+ *   1  off;  2..16  forced.   Square graphs (sources in [0, num_v)); out-of-range sources fall into the last slice.
+ * Results are deterministic for a given setting; slices change the fp32 summation order (slice by slice). */
+int gnnagg_set_locality_slices(gnnagg_aggregator *a, int slices);
+
 /* tuning knob (the reference's analogue is the BLOCK_SIZE argument of run(), aggr_gcn.h:381-386):
  * edges staged per warp by the aggregation kernels: 0 = automatic (128 below 4M edges, else 512),
  * or force 128 / 512.  Results do not depend on it beyond fp32 summation order. */
