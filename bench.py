@@ -144,8 +144,8 @@ def auto_stages(shape, N):
     chosen from the sweeps in profiles/r2_sweep_*.jsonl."""
     if N <= 1:
         return 0
-    if shape in RMAT_SCALES:            # 16 edges per output row: the passes over Y are expensive
-        return 1 if N <= 2 else 2
+    if shape in RMAT_SCALES:            # 16 edges per output row: every extra pass over Y costs more than it hides
+        return 0
     return min(N - 1, 3)                # 490 edges per output row: Y passes are cheap, overlap pays
 
 
@@ -207,6 +207,9 @@ class Workload:
             self.agg = gnnagg.Aggregator(ptr, idx, val)
             if args.scheduled:
                 self.agg.schedule(gnnagg.SCHED_NEIGHBOR_GROUPING, [32])
+            if getattr(args, "locality_slices", -1) >= 0:
+                self.agg.set_locality_slices(args.locality_slices)
+                self.config["locality_slices"] = args.locality_slices
         torch.cuda.synchronize()
         self.setup_s = time.time() - t0
         self.hX = self.hW = self.hH = None
@@ -220,7 +223,7 @@ class Workload:
 
         N, rank, dev, dist = self.N, self.rank, self.dev, self.dist
         n, fin = self.n, self.fin
-        self.stages = stages if stages else (self.args.stages or auto_stages(self.shape, N))
+        self.stages = stages if stages is not None else (self.args.stages if self.args.stages >= 0 else auto_stages(self.shape, N))
         err = ""
         if halo in ("auto", "peer"):
             try:
@@ -234,10 +237,11 @@ class Workload:
                 self.halo = "peer"
                 self.ph.x(0, fin).copy_(self.Xs)
                 self.config["halo"] = (
-                    "peer memory: each rank pulls the %.1f%% of X its block references (rank 0: %d distinct remote rows) straight "
-                    "from the owners' shards with 128-bit loads over NVLink (cudaIpc mappings, no NCCL in the step); %d remote "
-                    "stage(s) accumulated as their owners land, stage 0 = local sources" % (
-                        100.0 * (self.ph.num_recv + 0.0) / self.src_n, self.ph.num_recv, self.ph.num_stages - 1))
+                    "peer memory: every owner pushes the rows its peers' blocks reference (rank 0 receives %d distinct remote rows = "
+                    "%.1f%% of X) straight into their receive slots with 128-bit stores over NVLink (cudaIpc mappings, no NCCL in "
+                    "the step); %s" % (self.ph.num_recv, 100.0 * (self.ph.num_recv + 0.0) / self.src_n,
+                                       "one aggregation pass after all arrivals" if self.ph.num_stages == 1 else
+                                       "stage 0 = local sources, %d remote stage(s) accumulated as their owners land" % (self.ph.num_stages - 1)))
                 return
             if self.ph is not None:
                 self.ph = None
@@ -479,10 +483,10 @@ def c5_block(args, N, rank, dev, dist, timed, steps, warmup):
     """BASELINE.json configs[4] on the same ranks, after the headline.  Collective."""
     import torch
 
-    stage_list = [int(s) for s in args.c5_sweep.split(",")] if args.c5_sweep else [0]
+    stage_list = [int(s) for s in args.c5_sweep.split(",")] if args.c5_sweep else [None]
     best = None
     for st in stage_list:
-        wl = Workload(args, C5_WORKLOAD, N, rank, dev, dist, stages=st or None)
+        wl = Workload(args, C5_WORKLOAD, N, rank, dev, dist, stages=st)
         r = measure(wl, timed, steps, warmup, e2e=False)
         par = parity_check(wl) if N > 1 else None
         nbytes = N * spmm_bytes(wl.n, wl.m, wl.fin)
@@ -495,7 +499,7 @@ def c5_block(args, N, rank, dev, dist, timed, steps, warmup):
             d["compute_only_ms"] = round(r["compute_ms"], 4)
             d["exposed_exchange_ms"] = round(r["ms"] - r["compute_ms"], 4)
             if wl.ph is not None:
-                ex_bytes = wl.ph.num_recv * wl.fin * 4
+                ex_bytes = wl.ph.num_send * wl.fin * 4
                 d["remote_stages"] = wl.ph.num_stages - 1
                 d["bytes_exchanged_per_rank"] = ex_bytes
                 d["exchange_ms"] = round(r["exchange_ms"], 4)
@@ -538,8 +542,10 @@ def main():
     ap.add_argument("--halo", default="auto", choices=["auto", "peer", "pruned", "allgather"],
                     help="N>1: peer = the library's own NVLink peer-memory exchange (default); pruned / allgather = the NCCL "
                          "paths of round 1 (also the automatic fallback when peer mappings cannot be opened)")
-    ap.add_argument("--stages", type=int, default=0, help="N>1, peer halo: remote stages (0 = automatic)")
+    ap.add_argument("--stages", type=int, default=-1, help="N>1, peer halo: remote stages (-1 = automatic, 0 = one pass after all arrivals)")
     ap.add_argument("--sweep", default="", help="N>1: comma-separated remote-stage counts to time on the headline workload")
+    ap.add_argument("--locality-slices", type=int, default=-1,
+                    help="N=1: gnnagg_set_locality_slices (-1 = library default: automatic; 1 = off; 2..16 forced)")
     ap.add_argument("--c5", type=int, default=-1, help="1/0: also measure the RMAT-26 strong-scaling config (default: only "
                                                         "with the default workload)")
     ap.add_argument("--c5-sweep", default="", help="comma-separated remote-stage counts for the c5 block")
@@ -641,11 +647,13 @@ def main():
     if args.sweep and N > 1 and wl.ph is not None:
         for st in [int(s) for s in args.sweep.split(",")]:
             w2 = wl if st == wl.ph.num_stages - 1 else Workload(args, args.workload, N, rank, dev, dist, stages=st)
+            if w2.ph is None:
+                continue
             r = measure(w2, timed, max(5, args.steps // 2), 3, e2e=False)
             if rank == 0:
                 print(json.dumps({"sweep": {"workload": args.workload, "n_gpus": N, "remote_stages": st, "ms_per_step": round(r["ms"], 4),
                                             "compute_only_ms": round(r["compute_ms"], 4), "exchange_ms": round(r["exchange_ms"], 4),
-                                            "nvlink_GBps_per_rank": round(w2.ph.num_recv * fin * 4 / (r["exchange_ms"] * 1e-3) / 1e9, 1),
+                                            "nvlink_GBps_per_rank": round(w2.ph.num_send * fin * 4 / (r["exchange_ms"] * 1e-3) / 1e9, 1),
                                             "stage_edges": w2.ph.stage_edges}}), flush=True)
             if w2 is not wl:
                 w2.close()
@@ -764,13 +772,14 @@ def main():
             line["e2e"]["note"] = "copies_only_ms = the H2D + D2H of the same buffers alone, all ranks at once: what the host side of this box allows at this N"
             hal = {"kind": wl.halo, "exposed_ms": round(ms - r["compute_ms"], 4)}
             if wl.ph is not None:
-                ex_bytes = wl.ph.num_recv * fin * 4
+                ex_bytes = wl.ph.num_send * fin * 4
                 hal.update({"remote_stages": wl.ph.num_stages - 1, "stage_edges": wl.ph.stage_edges,
                             "bytes_per_rank": ex_bytes, "exchange_ms": round(r["exchange_ms"], 4),
                             "nvlink_GBps_per_rank": round(ex_bytes / (r["exchange_ms"] * 1e-3) / 1e9, 1),
                             "nvlink_frac_of_770": round(ex_bytes / (r["exchange_ms"] * 1e-3) / 1e9 / NVLINK_PEAK_GBS, 3),
-                            "note": "exchange_ms = first pull issued .. last row landed on the comm stream (max over ranks), "
-                                    "running concurrently with the aggregation; exposed_ms = step - kernels-only step"})
+                            "note": "bytes_per_rank = what rank 0 pushes per step; exchange_ms = its first push issued .. last push "
+                                    "complete on the comm stream (max over ranks), running concurrently with the aggregation; "
+                                    "exposed_ms = step - kernels-only step"})
             line["halo"] = hal
             line["parity"] = parity
 

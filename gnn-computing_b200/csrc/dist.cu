@@ -6,19 +6,25 @@
 // destination row; rank r owns a row block and the matching shard of X.  The only exchange step is the
 // source-feature halo.  It is NOT a library collective:
 //
-//   * every rank keeps its X shard in a peer-visible allocation (same process: peer access; one process per
-//     GPU: cudaIpc handles exchanged once at set-up);
 //   * at set-up each rank finds the distinct REMOTE source rows its block references (mark / scan / fill on the
-//     GPU), re-indexes its CSR into [own shard | compact receive buffer] coordinates and splits it by the OWNER
-//     of the source into stages (the slices of locality_schedule, graph_schedule.h:24-29, kept as CSRs);
-//   * a step: stage 0 (edges whose source is local) is aggregated straight from the shard while
-//     halo_pull_kernel -- plain 128-bit loads from the owners' shards over NVLink, no pack kernel, no send
-//     buffer, no NCCL -- fills the receive buffer owner by owner on a high-priority stream, every rank
-//     starting with a different owner; stage s is accumulated (gnnagg_gcn_run_acc, deterministic) as soon as
-//     its owners have landed.  Cross-GPU ordering is a pair of epoch flags per peer in peer-visible memory:
-//     ready[p] ("p's shard holds the X of epoch e": release store after the producer, acquire spin in the
-//     puller) and done[p] ("p has finished reading my shard for epoch e", write-after-read protection for
-//     the next producer).  Spins are bounded (globaltimer) and report through an error word instead of hanging.
+//     GPU), re-indexes its CSR into [own shard rows | receive slots] coordinates -- the receive buffer sits right
+//     behind the shard, so one base pointer serves both -- and splits it by the OWNER of the source into stages
+//     (the slices of locality_schedule, graph_schedule.h:24-29, kept as CSRs).  Shard, receive buffer, the list
+//     of wanted rows and a page of flags live in ONE peer-visible allocation (same process: peer access; one
+//     process per GPU: a cudaIpc handle, exchanged once).  At connect time every owner copies, once, the lists
+//     of rows its peers want from it;
+//   * a step: every OWNER pushes.  halo_push_kernel gathers the wanted rows from its own shard (local HBM, local
+//     TLB) and writes them with 128-bit stores straight into the receiver's buffer over NVLink -- posted writes
+//     into a contiguous destination, no pack buffer, no NCCL, no read round trips (a first version PULLED the rows
+//     with remote loads and reached 300-400 GB/s per GPU; profiles/r2_sweep_n8_pull.jsonl).  Owner p serves the
+//     receivers in the order p-1, p-2, ..., so at any time every receiver is written by exactly one owner;
+//   * the receiver aggregates stage 0 (edges whose source is local) meanwhile, and stage s as soon as the owners
+//     of that stage have landed (gnnagg_gcn_run_acc, deterministic).  remote_stages = 0 runs ONE pass after all
+//     arrivals: no extra pass over Y, for graphs whose rows are too short to pay for it.
+//   Cross-GPU ordering is two epoch flags per pair in peer-visible memory: arrived[p] at the receiver ("owner p's
+//   rows of epoch e are in your buffer": the last CTA of the push kernel, after a system-scope fence) and
+//   consumed[q] at the owner ("receiver q has finished reading what you pushed in epoch e": write-after-read
+//   protection of q's buffer).  Spins are one-warp kernels, bounded by globaltimer, and report through an error word.
 #include <cub/cub.cuh>
 #include <cuda_runtime.h>
 #include <unistd.h>
@@ -35,13 +41,15 @@ namespace gnnagg {
 
 constexpr int kMaxWorld = GNNAGG_DIST_MAX_WORLD;
 constexpr uint64_t kSpinLimitNs = 20ull * 1000 * 1000 * 1000;  // a peer that does not answer within 20 s is reported
+constexpr size_t kFlagBytes = 512;
 
 struct HaloFlags {
-    uint32_t ready[kMaxWorld];  // ready[p]: epoch of the X that rank p's shard currently holds (written by p)
-    uint32_t done[kMaxWorld];   // done[p]: last epoch rank p finished pulling from MY shard (written by p)
-    uint32_t err;               // first protocol error seen by a kernel of this rank (0 = none)
-    uint32_t pad[31];
+    uint32_t arrived[kMaxWorld];   // arrived[p]: last epoch whose rows owner p has written into MY receive buffer (written by p)
+    uint32_t consumed[kMaxWorld];  // consumed[q]: last epoch receiver q finished reading what I pushed to it (written by q)
+    uint32_t push_cnt[kMaxWorld];  // local: CTAs of the running push kernel towards q that are done
+    uint32_t err;                  // first protocol error seen by a kernel of this rank (0 = none)
 };
+static_assert(sizeof(HaloFlags) <= kFlagBytes, "flags page too small");
 
 struct PeerTable {
     HaloFlags *flags[kMaxWorld];
@@ -93,47 +101,37 @@ __device__ __forceinline__ bool spin_until(const uint32_t *flag, uint32_t epoch,
     return true;
 }
 
-// "my shard holds the X of `epoch`": first make sure every peer has finished reading the previous contents
-// (done flags in MY memory), then publish the epoch into every peer's ready[rank]
-__global__ void __launch_bounds__(32) halo_signal_kernel(HaloFlags *mine, PeerTable peers, int rank, int world, uint32_t epoch)
+// start of a step at the OWNER: every receiver must have finished reading what was pushed to it in the previous epoch
+// before its buffer is written again
+__global__ void __launch_bounds__(32) halo_begin_kernel(HaloFlags *mine, int rank, int world, uint32_t epoch)
+{
+    const int q = threadIdx.x;
+    if (q < world && q != rank) spin_until(&mine->consumed[q], epoch - 1u, &mine->err, 0x100u + (uint32_t)q);
+}
+
+// at the RECEIVER, in front of a stage: the rows of the owners in `mask` have landed
+__global__ void __launch_bounds__(32) halo_wait_kernel(HaloFlags *mine, uint32_t mask, uint32_t epoch)
 {
     const int p = threadIdx.x;
-    if (p < world && p != rank) spin_until(&mine->done[p], epoch - 1u, &mine->err, 0x100u + (uint32_t)p);
-    __syncwarp();
-    __threadfence_system();
-    if (p < world) st_release_sys(&peers.flags[p]->ready[rank], epoch);
+    if (p < kMaxWorld && ((mask >> p) & 1u)) spin_until(&mine->arrived[p], epoch, &mine->err, (uint32_t)p);
 }
 
-// "I have finished reading everybody's shard for `epoch`"
-__global__ void __launch_bounds__(32) halo_done_kernel(PeerTable peers, int rank, int world, uint32_t epoch)
+// end of a step at the RECEIVER: tell every owner that its rows of this epoch have been read
+__global__ void __launch_bounds__(32) halo_consumed_kernel(PeerTable peers, int rank, int world, uint32_t epoch)
 {
     const int p = threadIdx.x;
-    __threadfence_system();
-    if (p < world && p != rank) st_release_sys(&peers.flags[p]->done[rank], epoch);
+    if (p < world && p != rank) st_release_sys(&peers.flags[p]->consumed[rank], epoch);
 }
 
-__device__ __forceinline__ float4 ld_stream_f4(const float4 *p)
-{
-    float4 v;
-    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
-
-// dst[i, :] = src[rows[i], :] for the `count` receive slots of one owner; src is that owner's shard, mapped peer
-// memory: the loads travel over NVLink (or stay local when the "peer" lives on the same device).  U independent
-// 128-bit loads per thread are issued before the first store: 2 CTAs/SM x 256 threads x U x 16 B keep ~64 KB per
-// SM in flight, several times the NVLink latency-bandwidth product.
+// dst[i, :] = X[rows[i], :] for the `count` rows receiver q wants from this owner: X is the own shard (local gathers),
+// dst the slice of q's receive buffer reserved for this owner (peer memory: the stores travel over NVLink, or stay
+// local when the "peer" lives on the same device).  U independent 128-bit loads per thread before the first store.
+// The last CTA to finish publishes `epoch` in q's arrived[] flag.
 template <int U>
-__global__ void __launch_bounds__(256) halo_pull_kernel(const float4 *__restrict__ src, const int *__restrict__ rows,
+__global__ void __launch_bounds__(256) halo_push_kernel(const float4 *__restrict__ X, const int *__restrict__ rows,
                                                         float4 *__restrict__ dst, int64_t count4, int F4, int f4_shift,
-                                                        const uint32_t *ready, uint32_t epoch, uint32_t *err, uint32_t code)
+                                                        uint32_t *done_cnt, uint32_t *arrived_flag, uint32_t epoch)
 {
-    if (ready != nullptr) {
-        __shared__ int ok;
-        if (threadIdx.x == 0) ok = spin_until(ready, epoch, err, code) ? 1 : 0;
-        __syncthreads();
-        if (!ok) return;  // reported through the error word; the receive buffer keeps its old contents
-    }
     const int64_t stride = (int64_t)gridDim.x * 256 * U;
     for (int64_t base = (int64_t)blockIdx.x * 256 * U + threadIdx.x; base < count4; base += stride) {
         float4 v[U];
@@ -143,13 +141,24 @@ __global__ void __launch_bounds__(256) halo_pull_kernel(const float4 *__restrict
             if (e < count4) {
                 const int64_t r = (f4_shift >= 0) ? (e >> f4_shift) : (e / F4);
                 const int c = (int)(e - r * F4);
-                v[u] = ld_stream_f4(src + (int64_t)__ldg(rows + r) * F4 + c);
+                v[u] = __ldg(X + (int64_t)__ldg(rows + r) * F4 + c);
             }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int64_t e = base + (int64_t)u * 256;
             if (e < count4) dst[e] = v[u];
+        }
+    }
+    // every thread's stores are ordered before this CTA's count, the count before the flag (system scope)
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t before = atomicAdd(done_cnt, 1u);
+        if (before == gridDim.x - 1) {
+            atomicExch(done_cnt, 0u);  // ready for the next launch towards this receiver (stream-ordered after this one)
+            __threadfence_system();
+            st_release_sys(arrived_flag, epoch);
         }
     }
 }
@@ -182,10 +191,10 @@ __global__ void __launch_bounds__(256) dist_fill_recv_kernel(const int *__restri
     recv_local[pos[g]] = (int)(g - b.b[owner_of(b, g)]);
 }
 
-// new index of every edge (local row of the own shard, or slot of the receive buffer) and its stage
+// new index of every edge -- local row of the own shard, or `rows_own + receive slot` -- and its stage
 __global__ void __launch_bounds__(256) dist_reindex_kernel(const int *__restrict__ idx, int64_t m, const int *__restrict__ pos,
-                                                           int64_t own_lo, int64_t own_hi, Bounds b, int *__restrict__ idx_new,
-                                                           int *__restrict__ keys)
+                                                           int64_t own_lo, int64_t own_hi, int rows_own, Bounds b,
+                                                           int *__restrict__ idx_new, int *__restrict__ keys)
 {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= m) return;
@@ -194,7 +203,7 @@ __global__ void __launch_bounds__(256) dist_reindex_kernel(const int *__restrict
         idx_new[e] = (int)(g - own_lo);
         keys[e] = 0;
     } else {
-        idx_new[e] = __ldg(pos + g);
+        idx_new[e] = rows_own + __ldg(pos + g);
         keys[e] = b.stage_of[owner_of(b, g)];
     }
 }
@@ -207,6 +216,7 @@ __global__ void __launch_bounds__(256) dist_gather_val_kernel(const float *__res
 }
 
 static inline unsigned nblocks(int64_t n) { return (unsigned)((n + 255) / 256); }
+static inline size_t round512(size_t b) { return (b + 511) & ~(size_t)511; }
 
 struct DeviceGuard {
     int prev = -1;
@@ -227,7 +237,7 @@ using namespace gnnagg;
 
 constexpr int kMaxStages = kMaxWorld;
 
-// what a rank publishes to its peers (gnnagg_dist_export): fits GNNAGG_DIST_BLOB_BYTES
+// what a rank publishes to its peers after gnnagg_dist_set_graph (gnnagg_dist_export): fits GNNAGG_DIST_BLOB_BYTES
 struct DistBlob {
     uint32_t magic;
     int rank, world, device, pid;
@@ -235,7 +245,8 @@ struct DistBlob {
     int64_t rows;
     uint64_t raw_base;  // usable as is inside the exporting process
     uint64_t bytes;
-    uint64_t off_x[2];
+    uint64_t off_x[2], off_req;
+    int recv_off[kMaxWorld + 1];  // receive slots of every owner inside this rank's buffer / request list
     cudaIpcMemHandle_t mem;
 };
 static_assert(sizeof(DistBlob) <= GNNAGG_DIST_BLOB_BYTES, "blob too large");
@@ -245,23 +256,25 @@ struct gnnagg_dist {
     int64_t bounds[kMaxWorld + 1] = {0};
     int rows = 0;  // rows of the own shard = rows of the CSR block
     int feat_cap = 0;
-    // peer-visible allocation: [flags | x0 | x1]
+    // peer-visible allocation (made by set_graph): [flags | wanted-row list | x0 + receive 0 | x1 + receive 1]
     char *base = nullptr;
-    size_t bytes = 0, off_x[2] = {0, 0};
+    size_t bytes = 0, off_x[2] = {0, 0}, off_req = 0;
     // peers as seen from this rank
     char *peer_base[kMaxWorld] = {nullptr};
     size_t peer_off_x[kMaxWorld][2] = {{0, 0}};
+    int peer_rows[kMaxWorld] = {0};         // rows of q's shard: its receive buffer starts that many rows behind its x
+    int peer_slot[kMaxWorld] = {0};         // first receive slot of q's buffer that belongs to this owner
+    int send_cnt[kMaxWorld] = {0};          // rows q wants from this owner
+    int *send_rows[kMaxWorld] = {nullptr};  // which ones (local row numbers; owned copy of q's list)
     bool peer_ipc[kMaxWorld] = {false};
     bool connected = false;
     // plan
     int64_t num_e = 0;
-    int remote_stages = 0, num_stages = 0;  // stage 0 = local sources; 1..remote_stages = groups of owners
+    int remote_stages = 0, num_stages = 0;  // R = 0: one pass; else stage 0 = local sources, 1..R = groups of owners
     int stage_of[kMaxWorld] = {0};
-    int pull_order[kMaxWorld] = {0};  // the world-1 remote owners in the order they are pulled
+    uint32_t stage_mask[kMaxStages] = {0};  // owners whose arrival a stage waits for
     int64_t num_recv = 0;
     int recv_off[kMaxWorld + 1] = {0};
-    int *recv_local = nullptr;
-    float *recv_buf = nullptr;
     // sub-CSRs, one per stage
     int *sl_ptr = nullptr, *sl_idx = nullptr, *sl_perm = nullptr;
     float *sl_val = nullptr;
@@ -271,7 +284,7 @@ struct gnnagg_dist {
     size_t ax_cap = 0;
     // step machinery
     cudaStream_t comm = nullptr;
-    cudaEvent_t ev_sig = nullptr, ev_done = nullptr, ev_stage[kMaxStages] = {nullptr};
+    cudaEvent_t ev_sig = nullptr, ev_done = nullptr;
     cudaEvent_t t_m0 = nullptr, t_m1 = nullptr, t_m2 = nullptr, t_m3 = nullptr, t_c0 = nullptr, t_c1 = nullptr;
     bool prof = false;
     uint32_t epoch = 0;
@@ -283,19 +296,37 @@ struct gnnagg_dist {
 
 static HaloFlags *flags_of(char *base) { return reinterpret_cast<HaloFlags *>(base); }
 
+static void close_peers(gnnagg_dist *d)
+{
+    for (int p = 0; p < d->world; ++p) {
+        if (p != d->rank && d->peer_base[p] && d->peer_ipc[p]) cudaIpcCloseMemHandle(d->peer_base[p]);
+        if (p != d->rank) d->peer_base[p] = nullptr;
+        d->peer_ipc[p] = false;
+        cudaFree(d->send_rows[p]);
+        d->send_rows[p] = nullptr;
+        d->send_cnt[p] = 0;
+    }
+    d->connected = d->world == 1 && d->base != nullptr;
+}
+
 static void free_graph(gnnagg_dist *d)
 {
+    close_peers(d);
     for (int s = 0; s < kMaxStages; ++s) {
         if (d->stage[s]) gnnagg_destroy(d->stage[s]);
         d->stage[s] = nullptr;
     }
     cudaFree(d->sl_ptr), cudaFree(d->sl_idx), cudaFree(d->sl_perm), cudaFree(d->sl_val);
-    cudaFree(d->recv_local), cudaFree(d->recv_buf);
-    d->sl_ptr = d->sl_idx = d->sl_perm = d->recv_local = nullptr;
-    d->sl_val = d->recv_buf = nullptr;
+    cudaFree(d->base);
+    d->sl_ptr = d->sl_idx = d->sl_perm = nullptr;
+    d->sl_val = nullptr;
+    d->base = nullptr;
+    d->bytes = 0;
     d->num_stages = 0;
     d->num_recv = 0;
     d->prepared_feat = 0;
+    d->connected = false;
+    d->peer_base[d->rank] = nullptr;
 }
 
 extern "C" {
@@ -324,49 +355,62 @@ int gnnagg_dist_create_rank(int rank, int world, const int64_t *shard_bounds, in
     cudaError_t e = cudaGetDevice(&d->device);
     if (e != cudaSuccess) return fail(e, "cudaGetDevice");
     cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, d->device);
-    const size_t shard = (((size_t)d->rows * feat_cap * sizeof(float)) + 511) & ~(size_t)511;
-    d->off_x[0] = 512;  // flags occupy the first 512 bytes
-    d->off_x[1] = 512 + shard;
-    d->bytes = 512 + 2 * shard;
-    e = cudaMalloc((void **)&d->base, d->bytes);
-    if (e != cudaSuccess) return fail(e, "cudaMalloc of the peer-visible shard buffers");
-    e = cudaMemset(d->base, 0, 512);
-    if (e != cudaSuccess) return fail(e, "cudaMemset");
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = numerically lowest = highest priority
     e = cudaStreamCreateWithPriority(&d->comm, cudaStreamNonBlocking, hi);
     if (e != cudaSuccess) return fail(e, "cudaStreamCreateWithPriority");
     cudaEventCreateWithFlags(&d->ev_sig, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&d->ev_done, cudaEventDisableTiming);
-    for (int s = 0; s < kMaxStages; ++s) cudaEventCreateWithFlags(&d->ev_stage[s], cudaEventDisableTiming);
     {  // load the step's kernels now: a first launch while a peer's kernels spin on this rank could wait forever
         cudaFuncAttributes attr;
-        if (cudaFuncGetAttributes(&attr, halo_signal_kernel) != cudaSuccess) cudaGetLastError();
-        if (cudaFuncGetAttributes(&attr, halo_done_kernel) != cudaSuccess) cudaGetLastError();
-        if (cudaFuncGetAttributes(&attr, halo_pull_kernel<8>) != cudaSuccess) cudaGetLastError();
+        if (cudaFuncGetAttributes(&attr, halo_begin_kernel) != cudaSuccess) cudaGetLastError();
+        if (cudaFuncGetAttributes(&attr, halo_wait_kernel) != cudaSuccess) cudaGetLastError();
+        if (cudaFuncGetAttributes(&attr, halo_consumed_kernel) != cudaSuccess) cudaGetLastError();
+        if (cudaFuncGetAttributes(&attr, halo_push_kernel<8>) != cudaSuccess) cudaGetLastError();
         dense_preload();
     }
-    d->peer_base[rank] = d->base;
-    d->peer_off_x[rank][0] = d->off_x[0];
-    d->peer_off_x[rank][1] = d->off_x[1];
-    d->connected = world == 1;
     *out = d;
     return GNNAGG_OK;
+}
+
+int gnnagg_dist_create(int world, const int *devices, const int64_t *shard_bounds, int feat_cap, gnnagg_dist **out)
+{
+    if (!out || world < 1 || world > kMaxWorld) return set_error(GNNAGG_ERR_ARG, "gnnagg_dist_create: bad argument");
+    int prev = 0;
+    DT_TRY(cudaGetDevice(&prev));
+    for (int r = 0; r < world; ++r) out[r] = nullptr;
+    int rc = GNNAGG_OK;
+    for (int r = 0; r < world && rc == GNNAGG_OK; ++r) {
+        if (cudaSetDevice(devices ? devices[r] : r) != cudaSuccess) {
+            rc = set_error(GNNAGG_ERR_CUDA, "gnnagg_dist_create: cudaSetDevice failed");
+            break;
+        }
+        rc = gnnagg_dist_create_rank(r, world, shard_bounds, feat_cap, &out[r]);
+    }
+    if (rc != GNNAGG_OK)
+        for (int r = 0; r < world; ++r) {
+            if (out[r]) gnnagg_dist_destroy(out[r]);
+            out[r] = nullptr;
+        }
+    cudaSetDevice(prev);
+    return rc;
 }
 
 int gnnagg_dist_export(gnnagg_dist *d, void *blob)
 {
     if (!d || !blob) return set_error(GNNAGG_ERR_ARG, "gnnagg_dist_export: NULL argument");
+    if (!d->base) return set_error(GNNAGG_ERR_STATE, "gnnagg_dist_export: no graph yet (gnnagg_dist_set_graph comes first)");
     DeviceGuard guard(d->device);
     DistBlob b;
     memset(&b, 0, sizeof b);
-    b.magic = 0x676e6e61u;
+    b.magic = 0x676e6e62u;
     b.rank = d->rank, b.world = d->world, b.device = d->device, b.pid = d->pid;
     b.feat_cap = d->feat_cap;
     b.rows = d->rows;
     b.raw_base = (uint64_t)(uintptr_t)d->base;
     b.bytes = d->bytes;
-    b.off_x[0] = d->off_x[0], b.off_x[1] = d->off_x[1];
+    b.off_x[0] = d->off_x[0], b.off_x[1] = d->off_x[1], b.off_req = d->off_req;
+    for (int p = 0; p <= d->world; ++p) b.recv_off[p] = d->recv_off[p];
     // a handle is only needed by OTHER processes; a failure here (IPC not permitted) is reported at connect time
     if (cudaIpcGetMemHandle(&b.mem, d->base) != cudaSuccess) {
         cudaGetLastError();
@@ -380,18 +424,17 @@ int gnnagg_dist_export(gnnagg_dist *d, void *blob)
 int gnnagg_dist_connect(gnnagg_dist *d, const void *blobs)
 {
     if (!d || !blobs) return set_error(GNNAGG_ERR_ARG, "gnnagg_dist_connect: NULL argument");
+    if (!d->base) return set_error(GNNAGG_ERR_STATE, "gnnagg_dist_connect: no graph yet (gnnagg_dist_set_graph comes first)");
     DeviceGuard guard(d->device);
+    close_peers(d);
     int same = 1;
     for (int p = 0; p < d->world; ++p) {
         if (p == d->rank) continue;
         DistBlob b;
         memcpy(&b, (const char *)blobs + (size_t)p * GNNAGG_DIST_BLOB_BYTES, sizeof b);
-        if (b.magic != 0x676e6e61u || b.rank != p || b.world != d->world || b.feat_cap != d->feat_cap ||
+        if (b.magic != 0x676e6e62u || b.rank != p || b.world != d->world || b.feat_cap != d->feat_cap ||
             b.rows != d->bounds[p + 1] - d->bounds[p])
             return set_error(GNNAGG_ERR_ARG, "gnnagg_dist_connect: blob does not describe the expected peer");
-        if (d->peer_base[p] && d->peer_ipc[p]) cudaIpcCloseMemHandle(d->peer_base[p]);
-        d->peer_base[p] = nullptr;
-        d->peer_ipc[p] = false;
         if (b.pid == d->pid) {  // same process: the pointer is valid here once peer access is on
             if (b.device != d->device) {
                 int can = 0;
@@ -418,6 +461,15 @@ int gnnagg_dist_connect(gnnagg_dist *d, const void *blobs)
         }
         d->peer_off_x[p][0] = b.off_x[0];
         d->peer_off_x[p][1] = b.off_x[1];
+        d->peer_rows[p] = (int)b.rows;
+        // the rows p wants from this owner: slots [recv_off[rank], recv_off[rank + 1]) of ITS list; copied once
+        d->peer_slot[p] = b.recv_off[d->rank];
+        d->send_cnt[p] = b.recv_off[d->rank + 1] - b.recv_off[d->rank];
+        if (d->send_cnt[p] > 0) {
+            DT_TRY(cudaMalloc((void **)&d->send_rows[p], (size_t)d->send_cnt[p] * sizeof(int)));
+            DT_TRY(cudaMemcpy(d->send_rows[p], d->peer_base[p] + b.off_req + (size_t)d->peer_slot[p] * sizeof(int),
+                              (size_t)d->send_cnt[p] * sizeof(int), cudaMemcpyDefault));
+        }
         if (b.device == d->device) ++same;
     }
     d->same_device_ranks = same;
@@ -425,33 +477,29 @@ int gnnagg_dist_connect(gnnagg_dist *d, const void *blobs)
     return GNNAGG_OK;
 }
 
-int gnnagg_dist_create(int world, const int *devices, const int64_t *shard_bounds, int feat_cap, gnnagg_dist **out)
+int gnnagg_dist_connect_local(gnnagg_dist **ranks, int world)
 {
-    if (!out || world < 1 || world > kMaxWorld) return set_error(GNNAGG_ERR_ARG, "gnnagg_dist_create: bad argument");
-    int prev = 0;
-    DT_TRY(cudaGetDevice(&prev));
-    for (int r = 0; r < world; ++r) out[r] = nullptr;
+    if (!ranks || world < 1 || world > kMaxWorld) return set_error(GNNAGG_ERR_ARG, "gnnagg_dist_connect_local: bad argument");
+    char *blobs = new char[(size_t)world * GNNAGG_DIST_BLOB_BYTES];
     int rc = GNNAGG_OK;
     for (int r = 0; r < world && rc == GNNAGG_OK; ++r) {
-        if (cudaSetDevice(devices ? devices[r] : r) != cudaSuccess) {
-            rc = set_error(GNNAGG_ERR_CUDA, "gnnagg_dist_create: cudaSetDevice failed");
-            break;
-        }
-        rc = gnnagg_dist_create_rank(r, world, shard_bounds, feat_cap, &out[r]);
+        if (!ranks[r] || ranks[r]->rank != r || ranks[r]->world != world)
+            rc = set_error(GNNAGG_ERR_ARG, "gnnagg_dist_connect_local: handles must be the ranks 0..world-1 of one group");
+        else
+            rc = gnnagg_dist_export(ranks[r], blobs + (size_t)r * GNNAGG_DIST_BLOB_BYTES);
     }
-    if (rc == GNNAGG_OK) {
-        char *blobs = new char[(size_t)world * GNNAGG_DIST_BLOB_BYTES];
-        for (int r = 0; r < world && rc == GNNAGG_OK; ++r) rc = gnnagg_dist_export(out[r], blobs + (size_t)r * GNNAGG_DIST_BLOB_BYTES);
-        for (int r = 0; r < world && rc == GNNAGG_OK; ++r) rc = gnnagg_dist_connect(out[r], blobs);
-        delete[] blobs;
-    }
-    if (rc != GNNAGG_OK)
-        for (int r = 0; r < world; ++r) {
-            if (out[r]) gnnagg_dist_destroy(out[r]);
-            out[r] = nullptr;
-        }
-    cudaSetDevice(prev);
+    for (int r = 0; r < world && rc == GNNAGG_OK; ++r) rc = gnnagg_dist_connect(ranks[r], blobs);
+    delete[] blobs;
     return rc;
+}
+
+int gnnagg_dist_disconnect(gnnagg_dist *d)
+{
+    if (!d) return GNNAGG_OK;
+    DeviceGuard guard(d->device);
+    cudaDeviceSynchronize();
+    close_peers(d);
+    return GNNAGG_OK;
 }
 
 int gnnagg_dist_destroy(gnnagg_dist *d)
@@ -460,49 +508,46 @@ int gnnagg_dist_destroy(gnnagg_dist *d)
     DeviceGuard guard(d->device);
     cudaDeviceSynchronize();
     free_graph(d);
-    for (int p = 0; p < d->world; ++p)
-        if (p != d->rank && d->peer_base[p] && d->peer_ipc[p]) cudaIpcCloseMemHandle(d->peer_base[p]);
-    cudaFree(d->base);
     cudaFree(d->ax);
     if (d->comm) cudaStreamDestroy(d->comm);
     cudaEvent_t evs[] = {d->ev_sig, d->ev_done, d->t_m0, d->t_m1, d->t_m2, d->t_m3, d->t_c0, d->t_c1};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
-    for (int s = 0; s < kMaxStages; ++s)
-        if (d->ev_stage[s]) cudaEventDestroy(d->ev_stage[s]);
     delete d;
     return GNNAGG_OK;
 }
 
 float *gnnagg_dist_x(gnnagg_dist *d, int buf)
 {
-    if (!d || buf < 0 || buf > 1) return nullptr;
+    if (!d || !d->base || buf < 0 || buf > 1) return nullptr;
     return reinterpret_cast<float *>(d->base + d->off_x[buf]);
 }
 
 int gnnagg_dist_set_graph(gnnagg_dist *d, const int *d_ptr, const int *d_idx, const float *d_val, int64_t num_e,
                           int remote_stages, void *stream)
 {
-    if (!d || !d_ptr || (num_e > 0 && (!d_idx || !d_val)) || num_e < 0 || num_e > INT32_MAX)
+    if (!d || !d_ptr || (num_e > 0 && (!d_idx || !d_val)) || num_e < 0 || num_e > INT32_MAX || remote_stages < 0)
         return set_error(GNNAGG_ERR_ARG, "gnnagg_dist_set_graph: bad argument");
+    if (d->base)
+        return set_error(GNNAGG_ERR_STATE, "gnnagg_dist_set_graph: this rank already has a graph (peers may have it mapped); "
+                                           "create a new handle for a new graph");
     DeviceGuard guard(d->device);
     cudaStream_t st = (cudaStream_t)stream;
-    free_graph(d);
     const int W = d->world, n = d->rows, m = (int)num_e;
     const int64_t total = d->bounds[W];
     const int64_t own_lo = d->bounds[d->rank], own_hi = d->bounds[d->rank + 1];
-    // stages: 0 = local sources; the W-1 remote owners, taken in the order rank+1, rank+2, ... (every rank starts
-    // with a different owner, so no shard is read by everybody at once), are cut into `remote_stages` groups
+    // stages: R = 0 -> a single pass once everything has arrived.  Otherwise stage 0 = local sources and the W-1 remote
+    // owners, taken in the order rank+1, rank+2, ... (the order in which they push to this rank), cut into R groups
     int R = W > 1 ? remote_stages : 0;
-    if (W > 1 && R < 1) R = 1;
     if (R > W - 1) R = W - 1;
     d->remote_stages = R;
     d->num_stages = 1 + R;
+    for (int s = 0; s < kMaxStages; ++s) d->stage_mask[s] = 0;
     d->stage_of[d->rank] = 0;
     for (int k = 0; k < W - 1; ++k) {
         const int p = (d->rank + 1 + k) % W;
-        d->pull_order[k] = p;
-        d->stage_of[p] = 1 + (int)((int64_t)k * R / (W - 1));
+        d->stage_of[p] = R == 0 ? 0 : 1 + (int)((int64_t)k * R / (W - 1));
+        d->stage_mask[d->stage_of[p]] |= 1u << p;
     }
     Bounds b;
     memset(&b, 0, sizeof b);
@@ -547,12 +592,30 @@ int gnnagg_dist_set_graph(gnnagg_dist *d, const int *d_ptr, const int *d_idx, co
     }
     for (int p = 0; p <= W; ++p) d->recv_off[p] = h_off[p];
     d->num_recv = h_off[W];
-    SG_TRY(cudaMalloc((void **)&d->recv_local, (size_t)(d->num_recv > 0 ? d->num_recv : 1) * sizeof(int)));
-    SG_TRY(cudaMalloc((void **)&d->recv_buf, (size_t)(d->num_recv > 0 ? d->num_recv : 1) * d->feat_cap * sizeof(float)));
-    if (total > 0) dist_fill_recv_kernel<<<nblocks(total), 256, 0, st>>>(mark, pos, total, b, d->recv_local);
+    if ((int64_t)n + d->num_recv > INT32_MAX) {
+        cleanup();
+        free_graph(d);
+        return set_error(GNNAGG_ERR_ARG, "gnnagg_dist_set_graph: shard rows + receive slots exceed int32");
+    }
+    // the peer-visible allocation: flags | wanted rows | 2 x (shard + receive buffer)
+    {
+        const size_t req = round512((size_t)(d->num_recv > 0 ? d->num_recv : 1) * sizeof(int));
+        const size_t xbuf = round512(((size_t)n + (size_t)d->num_recv) * d->feat_cap * sizeof(float) + 16);
+        d->off_req = kFlagBytes;
+        d->off_x[0] = kFlagBytes + req;
+        d->off_x[1] = d->off_x[0] + xbuf;
+        d->bytes = d->off_x[1] + xbuf;
+        SG_TRY(cudaMalloc((void **)&d->base, d->bytes));
+        SG_TRY(cudaMemsetAsync(d->base, 0, kFlagBytes, st));
+        d->peer_base[d->rank] = d->base;
+        d->peer_off_x[d->rank][0] = d->off_x[0];
+        d->peer_off_x[d->rank][1] = d->off_x[1];
+    }
+    if (total > 0)
+        dist_fill_recv_kernel<<<nblocks(total), 256, 0, st>>>(mark, pos, total, b, reinterpret_cast<int *>(d->base + d->off_req));
     SG_TRY(cudaMalloc((void **)&idx_new, me * sizeof(int)));
     SG_TRY(cudaMalloc((void **)&keys, me * sizeof(int)));
-    if (m > 0) dist_reindex_kernel<<<nblocks(m), 256, 0, st>>>(d_idx, m, pos, own_lo, own_hi, b, idx_new, keys);
+    if (m > 0) dist_reindex_kernel<<<nblocks(m), 256, 0, st>>>(d_idx, m, pos, own_lo, own_hi, n, b, idx_new, keys);
     SG_TRY(cudaGetLastError());
     SG_TRY(cudaStreamSynchronize(st));
     cudaFree(mark), cudaFree(pos), cudaFree(tmp);
@@ -594,6 +657,7 @@ int gnnagg_dist_set_graph(gnnagg_dist *d, const int *d_ptr, const int *d_idx, co
     }
     d->num_e = num_e;
     d->launches += 6 + 3 * d->num_stages;
+    d->connected = W == 1;
     return gnnagg_dist_prepare(d, d->feat_cap, stream);
 #undef SG_TRY
 }
@@ -618,7 +682,8 @@ int gnnagg_dist_prepare(gnnagg_dist *d, int feat, void *stream)
     return GNNAGG_OK;
 }
 
-int gnnagg_dist_info(const gnnagg_dist *d, int64_t *num_recv, int64_t *recv_counts, int *num_stages, int64_t *stage_edges)
+int gnnagg_dist_info(const gnnagg_dist *d, int64_t *num_recv, int64_t *recv_counts, int *num_stages, int64_t *stage_edges,
+                     int64_t *send_counts)
 {
     if (!d) return set_error(GNNAGG_ERR_ARG, "gnnagg_dist_info: NULL handle");
     if (num_recv) *num_recv = d->num_recv;
@@ -627,6 +692,8 @@ int gnnagg_dist_info(const gnnagg_dist *d, int64_t *num_recv, int64_t *recv_coun
     if (num_stages) *num_stages = d->num_stages;
     if (stage_edges)
         for (int s = 0; s < d->num_stages; ++s) stage_edges[s] = d->sl_cnt[s];
+    if (send_counts)
+        for (int p = 0; p < d->world; ++p) send_counts[p] = d->send_cnt[p];
     return GNNAGG_OK;
 }
 
@@ -648,9 +715,9 @@ int gnnagg_dist_profile_read(gnnagg_dist *d, float *ms)
     DeviceGuard guard(d->device);
     DT_TRY(cudaEventSynchronize(d->t_m3));
     DT_TRY(cudaEventSynchronize(d->t_c1));
-    DT_TRY(cudaEventElapsedTime(&ms[0], d->t_c0, d->t_c1));  // halo exchange: first pull issued .. last pull landed
+    DT_TRY(cudaEventElapsedTime(&ms[0], d->t_c0, d->t_c1));  // halo: first push issued .. last push complete (comm stream)
     DT_TRY(cudaEventElapsedTime(&ms[1], d->t_m0, d->t_m3));  // whole step
-    DT_TRY(cudaEventElapsedTime(&ms[2], d->t_m0, d->t_m1));  // stage 0 (local sources)
+    DT_TRY(cudaEventElapsedTime(&ms[2], d->t_m0, d->t_m1));  // stage 0
     DT_TRY(cudaEventElapsedTime(&ms[3], d->t_m2, d->t_m3));  // dense combination
     return GNNAGG_OK;
 }
@@ -658,13 +725,14 @@ int gnnagg_dist_profile_read(gnnagg_dist *d, float *ms)
 int gnnagg_dist_check(gnnagg_dist *d)
 {
     if (!d) return set_error(GNNAGG_ERR_ARG, "gnnagg_dist_check: NULL handle");
+    if (!d->base) return GNNAGG_OK;
     DeviceGuard guard(d->device);
     uint32_t err = 0;
     DT_TRY(cudaMemcpy(&err, &flags_of(d->base)->err, sizeof err, cudaMemcpyDeviceToHost));
     if (err) {
         char buf[160];
         snprintf(buf, sizeof buf, "halo protocol: rank %d gave up waiting for rank %u (%s flag, code 0x%x)", d->rank, err & 0xffu,
-                 (err & 0x100u) ? "done" : "ready", err);
+                 (err & 0x100u) ? "consumed" : "arrived", err);
         return set_error(GNNAGG_ERR_STATE, buf);
     }
     return GNNAGG_OK;
@@ -684,8 +752,8 @@ static int dist_run(gnnagg_dist *d, int buf, float *Y, const float *W, float *H,
                     cudaStream_t st)
 {
     if (!d || (!Y && d->rows > 0) || buf < 0 || buf > 1) return set_error(GNNAGG_ERR_ARG, "gnnagg_dist_gcn_run: bad argument");
-    if (!d->connected) return set_error(GNNAGG_ERR_STATE, "gnnagg_dist_gcn_run: peers not connected (gnnagg_dist_connect)");
     if (d->num_stages == 0) return set_error(GNNAGG_ERR_STATE, "gnnagg_dist_gcn_run: no graph (gnnagg_dist_set_graph)");
+    if (!d->connected) return set_error(GNNAGG_ERR_STATE, "gnnagg_dist_gcn_run: peers not connected (gnnagg_dist_connect)");
     if (feat_in < 4 || (feat_in & 3) || feat_in > d->feat_cap)
         return set_error(GNNAGG_ERR_ARG, "gnnagg_dist_gcn_run: feat must be a multiple of 4, at most feat_cap");
     DeviceGuard guard(d->device);
@@ -694,18 +762,17 @@ static int dist_run(gnnagg_dist *d, int buf, float *Y, const float *W, float *H,
     // per-stage fix-up tables for this feature width (set_graph builds them for feat_cap).  Building them waits for the
     // device, which is harmless with one process per GPU; a process that drives SEVERAL ranks must call
     // gnnagg_dist_prepare for every rank before the first step of a new width (a device-wide wait while another rank's
-    // kernels spin on this rank's signal would never return)
+    // kernels spin on this rank's flags would never return)
     if (d->prepared_feat != feat_in)
         if (int rc = gnnagg_dist_prepare(d, feat_in, st)) return rc;
-    const float *xs = reinterpret_cast<const float *>(d->base + d->off_x[buf]);
+    const float *xs = reinterpret_cast<const float *>(d->base + d->off_x[buf]);  // shard rows, then the receive slots
+    HaloFlags *mine = flags_of(d->base);
+    uint32_t epoch = d->epoch;
     if (d->prof) DT_TRY(cudaEventRecord(d->t_m0, st));
     if (exchange) {
-        const uint32_t epoch = ++d->epoch;
-        PeerTable peers;
-        memset(&peers, 0, sizeof peers);
-        for (int p = 0; p < Wd; ++p) peers.flags[p] = flags_of(d->peer_base[p]);
-        HaloFlags *mine = flags_of(d->base);
-        halo_signal_kernel<<<1, 32, 0, st>>>(mine, peers, d->rank, Wd, epoch);
+        epoch = ++d->epoch;
+        // owner side: wait until every receiver has consumed the previous epoch, then push, receiver by receiver
+        halo_begin_kernel<<<1, 32, 0, st>>>(mine, d->rank, Wd, epoch);
         DT_TRY(cudaPeekAtLastError());
         DT_TRY(cudaEventRecord(d->ev_sig, st));
         DT_TRY(cudaStreamWaitEvent(d->comm, d->ev_sig, 0));
@@ -714,64 +781,53 @@ static int dist_run(gnnagg_dist *d, int buf, float *Y, const float *W, float *H,
         int shift = -1;
         for (int s = 0; s < 16; ++s)
             if ((1 << s) == F4) shift = s;
-        int stage_now = 1;
         for (int k = 0; k < Wd - 1; ++k) {
-            const int p = d->pull_order[k];
-            if (d->stage_of[p] != stage_now) {  // the previous stage is complete
-                DT_TRY(cudaEventRecord(d->ev_stage[stage_now], d->comm));
-                stage_now = d->stage_of[p];
-            }
-            const int64_t cnt = d->recv_off[p + 1] - d->recv_off[p];
-            if (cnt > 0) {
-                const int64_t count4 = cnt * F4;
-                // 2 CTAs per SM saturate the link; ranks sharing one device (tests) split that, so that CTAs spinning on
-                // a peer's flag can never fill the device and keep that peer's signal kernel out
-                int64_t grid = (count4 + 256 * 8 - 1) / (256 * 8);
-                const int64_t cap = d->same_device_ranks > 1 ? std::max(4, d->sm_count / (2 * d->same_device_ranks)) : 2 * d->sm_count;
-                if (grid > cap) grid = cap;
-                halo_pull_kernel<8><<<(unsigned)grid, 256, 0, d->comm>>>(
-                    reinterpret_cast<const float4 *>(d->peer_base[p] + d->peer_off_x[p][buf]), d->recv_local + d->recv_off[p],
-                    reinterpret_cast<float4 *>(d->recv_buf + (size_t)d->recv_off[p] * feat_in), count4, F4, shift, &mine->ready[p], epoch,
-                    &mine->err, (uint32_t)p);
-                DT_TRY(cudaPeekAtLastError());
-                ++d->launches;
-            }
+            const int q = (d->rank - 1 - k + 2 * Wd) % Wd;  // receiver q takes this owner as its k-th
+            const int64_t count4 = (int64_t)d->send_cnt[q] * F4;
+            // 2 CTAs per SM saturate the link; ranks sharing one device (tests) split that
+            int64_t grid = (count4 + 256 * 8 - 1) / (256 * 8);
+            const int64_t cap = d->same_device_ranks > 1 ? std::max(4, d->sm_count / (2 * d->same_device_ranks)) : 2 * d->sm_count;
+            grid = grid < 1 ? 1 : (grid > cap ? cap : grid);  // an empty push still raises the flag
+            float *dst = reinterpret_cast<float *>(d->peer_base[q] + d->peer_off_x[q][buf]) +
+                         ((size_t)d->peer_rows[q] + (size_t)d->peer_slot[q]) * feat_in;
+            halo_push_kernel<8><<<(unsigned)grid, 256, 0, d->comm>>>(reinterpret_cast<const float4 *>(xs), d->send_rows[q],
+                                                                   reinterpret_cast<float4 *>(dst), count4, F4, shift,
+                                                                   &mine->push_cnt[q], &flags_of(d->peer_base[q])->arrived[d->rank], epoch);
+            DT_TRY(cudaPeekAtLastError());
+            ++d->launches;
         }
-        DT_TRY(cudaEventRecord(d->ev_stage[stage_now], d->comm));
-        halo_done_kernel<<<1, 32, 0, d->comm>>>(peers, d->rank, Wd, epoch);
-        DT_TRY(cudaPeekAtLastError());
         DT_TRY(cudaEventRecord(d->ev_done, d->comm));
         if (d->prof) DT_TRY(cudaEventRecord(d->t_c1, d->comm));
-        d->launches += 2;
+        d->launches += 1;
     } else if (d->prof) {
         DT_TRY(cudaEventRecord(d->t_c0, st));
         DT_TRY(cudaEventRecord(d->t_c1, st));
     }
-    float *agg_out = Y;
-    if (W) {
-        const size_t need = (size_t)d->rows * feat_in;
-        if (need > d->ax_cap) {
-            cudaFree(d->ax);
-            d->ax = nullptr;
-            d->ax_cap = 0;
-            DT_TRY(cudaMalloc((void **)&d->ax, (need ? need : 1) * sizeof(float)));
-            d->ax_cap = need;
+    float *agg_out = W ? d->ax : Y;
+    // receiver side: stage by stage, each behind the arrival of its owners
+    for (int s = 0; s < d->num_stages; ++s) {
+        if (exchange && d->stage_mask[s]) {
+            halo_wait_kernel<<<1, 32, 0, st>>>(mine, d->stage_mask[s], epoch);
+            DT_TRY(cudaPeekAtLastError());
+            ++d->launches;
         }
-        agg_out = d->ax;
-    }
-    // stage 0: sources of the own shard, no communication needed
-    if (int rc = gnnagg_gcn_run_acc(d->stage[0], xs, agg_out, feat_in, 0, st)) return rc;
-    if (d->prof) DT_TRY(cudaEventRecord(d->t_m1, st));
-    for (int s = 1; s < d->num_stages; ++s) {
-        if (exchange) DT_TRY(cudaStreamWaitEvent(st, d->ev_stage[s], 0));
-        if (int rc = gnnagg_gcn_run_acc(d->stage[s], d->recv_buf, agg_out, feat_in, 1, st)) return rc;
+        if (int rc = gnnagg_gcn_run_acc(d->stage[s], xs, agg_out, feat_in, s > 0, st)) return rc;
+        if (s == 0 && d->prof) DT_TRY(cudaEventRecord(d->t_m1, st));
     }
     if (d->prof) DT_TRY(cudaEventRecord(d->t_m2, st));
     if (W && d->rows > 0) {
         if (int rc = gnnagg_dense_nn(d->ax, W, H, d->rows, feat_out, feat_in, st)) return rc;
         d->launches += 2;
     }
-    if (exchange) DT_TRY(cudaStreamWaitEvent(st, d->ev_done, 0));  // the caller's stream covers the comm stream's work too
+    if (exchange) {
+        PeerTable peers;
+        memset(&peers, 0, sizeof peers);
+        for (int p = 0; p < Wd; ++p) peers.flags[p] = flags_of(d->peer_base[p]);
+        halo_consumed_kernel<<<1, 32, 0, st>>>(peers, d->rank, Wd, epoch);
+        DT_TRY(cudaPeekAtLastError());
+        ++d->launches;
+        DT_TRY(cudaStreamWaitEvent(st, d->ev_done, 0));  // the caller's stream covers this rank's pushes too: X may be rewritten
+    }
     if (d->prof) DT_TRY(cudaEventRecord(d->t_m3, st));
     return GNNAGG_OK;
 }

@@ -116,7 +116,9 @@ _SIGS = {
     "gnnagg_dist_gcn_run": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "gnnagg_dist_gcn_layer": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "gnnagg_dist_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int),
-                                   C.POINTER(C.c_int64)]),
+                                   C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "gnnagg_dist_connect_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "gnnagg_dist_disconnect": (C.c_int, [C.c_void_p]),
     "gnnagg_dist_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "gnnagg_dist_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "gnnagg_dist_check": (C.c_int, [C.c_void_p]),

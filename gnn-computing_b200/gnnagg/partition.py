@@ -303,11 +303,11 @@ class PipelinedPrunedHalo:
 
 
 # ------------------------------------------------------------------------------------------------
-# peer-memory halo: binding over gnnagg_dist_* (csrc/dist.cu).  The exchange is not a collective: every
-# rank pulls the distinct remote source rows its block references straight out of the owners' X shards
-# with 128-bit loads over NVLink, owner group by owner group, while the edges whose sources have already
-# landed are being aggregated.  torch.distributed is only used once, to all-gather the 256-byte
-# connection blobs (cudaIpc handles) at set-up.
+# peer-memory halo: binding over gnnagg_dist_* (csrc/dist.cu).  The exchange is not a collective: every owner
+# pushes the rows each peer wants from its shard straight into that peer's receive slots with 128-bit stores
+# over NVLink, receiver by receiver, while the receivers aggregate the edges whose sources have already
+# landed.  torch.distributed is only used once, to all-gather the 256-byte connection blobs (cudaIpc
+# handles) at set-up, and for the barriers of the teardown.
 # ------------------------------------------------------------------------------------------------
 class _DeviceMemory:
     """a library-owned device buffer exposed through __cuda_array_interface__ (zero-copy torch view)"""
@@ -325,9 +325,11 @@ def _bounds_array(bounds):
 
 
 class PeerHalo:
-    """one rank of the peer-memory multi-GPU aggregation.  `handle` may be passed in by LocalDist (single process
-    driving several ranks); otherwise the rank is created on the current device and connected to its peers through
-    torch.distributed (any backend: the blobs are plain bytes)."""
+    """one rank of the peer-memory multi-GPU aggregation.  `handle` is passed in by LocalDist (single process
+    driving several ranks, which connects them itself); otherwise the rank is created on the current device and
+    connected to its peers through torch.distributed (any backend: the blobs are plain bytes).
+    remote_stages = 0: one pass after all rows have arrived; R >= 1: stage 0 = local sources, then R groups of
+    owners accumulated as they land."""
 
     def __init__(self, ptr, idx, val, bounds, rank, world, feat_cap, remote_stages=1, group=None, handle=None):
         import ctypes as C
@@ -342,33 +344,42 @@ class PeerHalo:
         self.rows = self.bounds[rank + 1] - self.bounds[rank]
         self.device = ptr.device
         self._owns = handle is None
+        assert ptr.dtype == torch.int32 and idx.dtype == torch.int32 and val.dtype == torch.float32
+        assert ptr.numel() - 1 == self.rows, "the row block must match the rank's shard of X"
         if handle is None:
             h = C.c_void_p()
             check(L.gnnagg_dist_create_rank(rank, world, _bounds_array(self.bounds), feat_cap, C.byref(h)))
             self.h = h
-            if world > 1:
-                import torch.distributed as dist
-
-                blob = C.create_string_buffer(DIST_BLOB_BYTES)
-                check(L.gnnagg_dist_export(self.h, blob))
-                on_gpu = dist.get_backend(group) == "nccl"
-                mine = torch.frombuffer(bytearray(blob.raw), dtype=torch.uint8)
-                mine = mine.to(self.device) if on_gpu else mine
-                every = torch.empty(world * DIST_BLOB_BYTES, dtype=torch.uint8, device=mine.device)
-                dist.all_gather_into_tensor(every, mine, group=group)
-                raw = every.cpu().numpy().tobytes()
-                check(L.gnnagg_dist_connect(self.h, raw))
         else:
             self.h = handle
-        assert ptr.dtype == torch.int32 and idx.dtype == torch.int32 and val.dtype == torch.float32
-        assert ptr.numel() - 1 == self.rows, "the row block must match the rank's shard of X"
         check(L.gnnagg_dist_set_graph(self.h, _dp(ptr.contiguous()), _dp(idx.contiguous()), _dp(val.contiguous()), idx.numel(),
                                       int(remote_stages), _stream()))
+        if handle is None and world > 1:
+            import torch.distributed as dist
+
+            blob = C.create_string_buffer(DIST_BLOB_BYTES)
+            check(L.gnnagg_dist_export(self.h, blob))
+            on_gpu = dist.get_backend(group) == "nccl"
+            mine = torch.frombuffer(bytearray(blob.raw), dtype=torch.uint8)
+            mine = mine.to(self.device) if on_gpu else mine
+            every = torch.empty(world * DIST_BLOB_BYTES, dtype=torch.uint8, device=mine.device)
+            dist.all_gather_into_tensor(every, mine, group=group)
+            check(L.gnnagg_dist_connect(self.h, every.cpu().numpy().tobytes()))
+        self.refresh_info()
+
+    def refresh_info(self):
+        import ctypes as C
+
+        from . import check, lib
+
+        world = self.world
         nrecv, counts, nst = C.c_int64(), (C.c_int64 * world)(), C.c_int()
-        edges = (C.c_int64 * 16)()
-        check(L.gnnagg_dist_info(self.h, C.byref(nrecv), counts, C.byref(nst), edges))
+        edges, sends = (C.c_int64 * 16)(), (C.c_int64 * world)()
+        check(lib().gnnagg_dist_info(self.h, C.byref(nrecv), counts, C.byref(nst), edges, sends))
         self.num_recv, self.recv_counts, self.num_stages = int(nrecv.value), [int(c) for c in counts], int(nst.value)
         self.stage_edges = [int(edges[s]) for s in range(self.num_stages)]
+        self.send_counts = [int(c) for c in sends]
+        self.num_send = sum(self.send_counts)
         self.referenced_fraction = (self.num_recv + 0.0) / max(1, self.bounds[-1])
 
     def x(self, buf=0, feat=None):
@@ -424,7 +435,7 @@ class PeerHalo:
         return lib().gnnagg_dist_launch_count(self.h)
 
     def close(self):
-        """collective when world > 1 and the rank was created here: peers must have stopped reading this shard"""
+        """collective when world > 1 and the rank was created here: everybody idle -> unmap the peers -> free"""
         from . import lib
 
         if getattr(self, "h", None) and self._owns:
@@ -434,13 +445,16 @@ class PeerHalo:
 
                 torch.cuda.synchronize()
                 dist.barrier(group=self.group)
+                lib().gnnagg_dist_disconnect(self.h)
+                dist.barrier(group=self.group)
             lib().gnnagg_dist_destroy(self.h)
         self.h = None
 
 
 class LocalDist:
     """gnnagg_dist_create: ONE process drives `world` ranks (devices[r], default r; the same device may be given
-    several times, which is how the single-GPU tests exercise the whole protocol)"""
+    several times, which is how the single-GPU tests exercise the whole protocol).  set_graph for every rank, then
+    connect()."""
 
     def __init__(self, bounds, feat_cap, devices=None):
         import ctypes as C
@@ -450,15 +464,22 @@ class LocalDist:
         world = len(bounds) - 1
         self.world, self.bounds, self.feat_cap = world, [int(b) for b in bounds], feat_cap
         self.devices = list(range(world)) if devices is None else [int(d) for d in devices]
-        hs = (C.c_void_p * world)()
-        check(lib().gnnagg_dist_create(world, (C.c_int * world)(*self.devices), _bounds_array(self.bounds), feat_cap, hs))
-        self.handles = [C.c_void_p(hs[r]) for r in range(world)]
+        self._hs = (C.c_void_p * world)()
+        check(lib().gnnagg_dist_create(world, (C.c_int * world)(*self.devices), _bounds_array(self.bounds), feat_cap, self._hs))
+        self.handles = [C.c_void_p(self._hs[r]) for r in range(world)]
         self.ranks = [None] * world
 
     def set_graph(self, rank, ptr, idx, val, remote_stages=1):
         self.ranks[rank] = PeerHalo(ptr, idx, val, self.bounds, rank, self.world, self.feat_cap, remote_stages,
                                     handle=self.handles[rank])
         return self.ranks[rank]
+
+    def connect(self):
+        from . import check, lib
+
+        check(lib().gnnagg_dist_connect_local(self._hs, self.world))
+        for r in self.ranks:
+            r.refresh_info()
 
     def close(self):
         import torch
@@ -467,6 +488,8 @@ class LocalDist:
 
         torch.cuda.synchronize()
         for h in self.handles:
+            lib().gnnagg_dist_disconnect(h)
+        for h in self.handles:
             lib().gnnagg_dist_destroy(h)
         self.handles = []
 
@@ -474,13 +497,13 @@ class LocalDist:
 def peer_plan(idx, bounds, rank, remote_stages):
     """numpy restatement of the index bookkeeping of gnnagg_dist_set_graph (csrc/dist.cu), for tests and for
     reasoning about traffic without a GPU.  Returns a dict:
-      recv_rows   global ids of the distinct REMOTE sources of this block, ascending (= receive-buffer order)
+      recv_rows   global ids of the distinct REMOTE sources of this block, ascending (= receive-slot order)
       recv_off    [world+1] slot range of every owner inside recv_rows
-      recv_local  recv_rows as local row numbers inside their owner's shard (what the pull kernel reads)
-      stage_of    [world] stage of every owner: 0 = this rank, 1..R = groups of the owners taken in the order
-                  rank+1, rank+2, ... (mod world)
-      pull_order  the world-1 remote owners in that order
-      idx_new     per edge: local row of the own shard (stage 0) or receive-buffer slot (stages >= 1)
+      recv_local  recv_rows as local row numbers inside their owner's shard (the rows that owner pushes)
+      stage_of    [world] stage of every owner: R = 0 -> everything is stage 0 (one pass after all arrivals); else
+                  0 = this rank, 1..R = groups of the owners taken in the order rank+1, rank+2, ... (mod world)
+      recv_order  the world-1 remote owners in the order their rows arrive (owner p pushes to p-1, p-2, ...)
+      idx_new     per edge: local row of the own shard, or rows_own + receive slot (one buffer: shard, then slots)
       stage       per edge: its stage"""
     bounds = np.asarray(bounds, np.int64)
     W = len(bounds) - 1
@@ -489,13 +512,13 @@ def peer_plan(idx, bounds, rank, remote_stages):
     remote = (g < own_lo) | (g >= own_hi)
     U = np.unique(g[remote])
     owner_u = np.searchsorted(bounds, U, side="right") - 1
-    R = 0 if W == 1 else max(1, min(int(remote_stages), W - 1))
+    R = 0 if W == 1 else max(0, min(int(remote_stages), W - 1))
     order = [(rank + 1 + k) % W for k in range(W - 1)]
     stage_of = np.zeros(W, np.int64)
     for k, p in enumerate(order):
-        stage_of[p] = 1 + (k * R) // (W - 1)
+        stage_of[p] = 0 if R == 0 else 1 + (k * R) // (W - 1)
     owner_e = np.clip(np.searchsorted(bounds, g, side="right") - 1, 0, W - 1)
     return {"recv_rows": U, "recv_off": np.searchsorted(U, bounds, side="left"), "recv_local": U - bounds[owner_u],
-            "stage_of": stage_of, "pull_order": order, "num_stages": 1 + R,
-            "idx_new": np.where(remote, np.searchsorted(U, g), g - own_lo).astype(np.int32),
+            "stage_of": stage_of, "recv_order": order, "num_stages": 1 + R,
+            "idx_new": np.where(remote, (own_hi - own_lo) + np.searchsorted(U, g), g - own_lo).astype(np.int32),
             "stage": np.where(remote, stage_of[owner_e], 0).astype(np.int32)}

@@ -282,48 +282,58 @@ int gnnagg_validate_reordered(const float *d_ref, const float *d_ans, const int 
  * syncAll (include/util.h:135-142) and the prepare*Multi prototypes (include/data.h:48-58).
  * These entry points are that missing piece.  Rank r owns the destination rows
  * [shard_bounds[r], shard_bounds[r+1]) and the matching rows of X; its CSR block keeps GLOBAL
- * source ids.  A gnnagg_dist handle is ONE rank (one GPU).  Two ways to get connected ranks:
- *   single process : gnnagg_dist_create(world, devices, ...) -> world handles with peer access on
- *                    (the shape SURVEY 8(b) names; per-rank calls may be issued from one thread,
- *                    none of them blocks the host);
- *   process per GPU: gnnagg_dist_create_rank on the current device, gnnagg_dist_export a
- *                    GNNAGG_DIST_BLOB_BYTES blob, all-gather the blobs with whatever the caller has
- *                    (MPI, torch.distributed, a file), gnnagg_dist_connect (cudaIpc mapping).
- * The X shard lives in library-owned, peer-visible memory (two buffers, gnnagg_dist_x(d, 0|1), so a layer can
- * write the next layer's input while peers may still read this one's): fill it on `stream`, then run.
- * A run = stage 0 (edges with local sources) while the remote rows are pulled from the owners' shards by plain
- * 128-bit loads over NVLink into a compact receive buffer, then one accumulating stage per group of owners as
- * it lands (`remote_stages` groups; more groups = finer overlap, more passes over Y).  Deterministic: no atomics,
- * a fixed summation order per (world, remote_stages).  No NCCL, no pack kernel, no send buffer.
+ * source ids.  A gnnagg_dist handle is ONE rank (one GPU).  Life cycle:
+ *   1. create   single process : gnnagg_dist_create(world, devices, ...) -> world handles (the shape SURVEY
+ *                                8(b) names; per-rank calls may come from one thread, no step call blocks the host)
+ *               process per GPU: gnnagg_dist_create_rank on the current device
+ *   2. gnnagg_dist_set_graph on every rank: finds the distinct remote rows the block references, builds the
+ *      per-stage CSRs and allocates the rank's ONE peer-visible buffer (flags | wanted rows | 2 x [X shard +
+ *      receive slots])
+ *   3. connect  single process : gnnagg_dist_connect_local(handles, world)
+ *               process per GPU: gnnagg_dist_export a GNNAGG_DIST_BLOB_BYTES blob, all-gather the blobs with
+ *                                whatever the caller has (MPI, torch.distributed, a file), gnnagg_dist_connect
+ *                                (cudaIpc mapping; every owner copies the lists of rows its peers want, once)
+ *   4. steps    write the X shard into gnnagg_dist_x(d, buf) on `stream`, then gnnagg_dist_gcn_run / _gcn_layer.
+ *               Two shard buffers: a layer may write the next layer's input into the other one.
+ *   5. teardown all ranks idle -> gnnagg_dist_disconnect on every rank -> (barrier) -> gnnagg_dist_destroy
+ * A step: every OWNER pushes the rows each peer wants from its shard straight into that peer's receive slots with
+ * 128-bit stores over NVLink (local gathers, posted remote writes, contiguous destination; owner p serves receivers
+ * p-1, p-2, ... so each receiver is written by one owner at a time); the receiver aggregates stage 0 (edges with
+ * local sources) meanwhile and one accumulating stage per group of owners as it lands.  remote_stages = 0: a single
+ * pass after all arrivals (no extra pass over Y; for short rows).  Deterministic: no atomics, a fixed summation order
+ * per (world, remote_stages).  No NCCL, no pack buffer.
  * ------------------------------------------------------------------------------------------ */
 #define GNNAGG_DIST_MAX_WORLD 16
 #define GNNAGG_DIST_BLOB_BYTES 256
-#define GNNAGG_DIST_NO_EXCHANGE 1 /* run flag: re-use the receive buffer of the previous run (kernels-only timing) */
+#define GNNAGG_DIST_NO_EXCHANGE 1 /* run flag: re-use the receive slots of the previous run (kernels-only timing) */
 typedef struct gnnagg_dist gnnagg_dist;
 int gnnagg_dist_create(int world, const int *devices /* NULL: 0..world-1 */, const int64_t *shard_bounds /* world+1 */,
                        int feat_cap, gnnagg_dist **out /* [world] */);
 int gnnagg_dist_create_rank(int rank, int world, const int64_t *shard_bounds, int feat_cap, gnnagg_dist **out);
-int gnnagg_dist_export(gnnagg_dist *d, void *blob /* GNNAGG_DIST_BLOB_BYTES */);
-int gnnagg_dist_connect(gnnagg_dist *d, const void *blobs /* world * GNNAGG_DIST_BLOB_BYTES, indexed by rank */);
-int gnnagg_dist_destroy(gnnagg_dist *d);
 /* the rank's row block (borrowed only during the call: the library keeps its own re-indexed per-stage CSRs);
- * synchronises `stream`.  remote_stages in [1, world-1]. */
+ * synchronises `stream`.  remote_stages in [0, world-1].  Once per handle. */
 int gnnagg_dist_set_graph(gnnagg_dist *d, const int *d_ptr, const int *d_idx, const float *d_val, int64_t num_e,
                           int remote_stages, void *stream);
+int gnnagg_dist_export(gnnagg_dist *d, void *blob /* GNNAGG_DIST_BLOB_BYTES */);
+int gnnagg_dist_connect(gnnagg_dist *d, const void *blobs /* world * GNNAGG_DIST_BLOB_BYTES, indexed by rank */);
+int gnnagg_dist_connect_local(gnnagg_dist **ranks, int world); /* export + connect of all ranks of one process */
+int gnnagg_dist_disconnect(gnnagg_dist *d); /* unmaps the peers; the rank cannot step afterwards */
+int gnnagg_dist_destroy(gnnagg_dist *d);
 /* builds the per-stage tables for a feature width other than feat_cap (set_graph prepares feat_cap).  Waits for the
  * device: with one process per GPU the first run of a new width does it by itself; a process driving several ranks
  * must call it for EVERY rank before the first step of that width. */
 int gnnagg_dist_prepare(gnnagg_dist *d, int feat, void *stream);
-float *gnnagg_dist_x(gnnagg_dist *d, int buf); /* [rows of the shard, feat] row-major, feat <= feat_cap */
+float *gnnagg_dist_x(gnnagg_dist *d, int buf); /* [rows of the shard, feat] row-major, feat <= feat_cap; NULL before set_graph */
 /* Y = A_block * X  /  H = (A_block * X) * W, with X = buffer `buf` of every rank (all ranks must call with the same
- * buf and feat).  Asynchronous on `stream`; Y/H may be the other shard buffer. */
+ * buf and feat).  Asynchronous on `stream`. */
 int gnnagg_dist_gcn_run(gnnagg_dist *d, int buf, float *Y, int feat, int flags, void *stream);
 int gnnagg_dist_gcn_layer(gnnagg_dist *d, int buf, const float *W, float *H, int feat_in, int feat_out, int flags,
                           void *stream);
-/* distinct remote source rows this rank receives per step (in total / per owner), stages and their edge counts */
+/* distinct remote source rows this rank receives per step (in total / per owner), stages and their edge counts,
+ * rows this rank pushes to every peer (after connect); any pointer may be NULL */
 int gnnagg_dist_info(const gnnagg_dist *d, int64_t *num_recv, int64_t *recv_counts /* [world] */, int *num_stages,
-                     int64_t *stage_edges /* [num_stages] */);
-/* device timing of the last run: ms[0] halo exchange (first pull issued .. last row landed, comm stream),
+                     int64_t *stage_edges /* [num_stages] */, int64_t *send_counts /* [world] */);
+/* device timing of the last run: ms[0] halo pushes of this rank (first issued .. last complete, comm stream),
  * ms[1] whole step, ms[2] stage 0, ms[3] dense combination */
 int gnnagg_dist_profile_enable(gnnagg_dist *d, int on);
 int gnnagg_dist_profile_read(gnnagg_dist *d, float *ms /* [4] */);

@@ -109,10 +109,11 @@ int main(int argc, char **argv)
         CK(cudaMalloc((void **)&d_h[r], (size_t)(r1 - r0 + 1) * OUT * sizeof(float)));
         GK(gnnagg_dist_set_graph(ranks[r], d_ptr[r], d_idx[r], d_val[r], e1 - e0, stages, nullptr));
     }
+    GK(gnnagg_dist_connect_local(ranks, world));
     {
         int64_t nrecv = 0, counts[GNNAGG_DIST_MAX_WORLD] = {0}, edges[GNNAGG_DIST_MAX_WORLD] = {0};
         int nst = 0;
-        GK(gnnagg_dist_info(ranks[0], &nrecv, counts, &nst, edges));
+        GK(gnnagg_dist_info(ranks[0], &nrecv, counts, &nst, edges, nullptr));
         printf("world %d on %d GPU(s): n=%d m=%d F=%d; rank 0 receives %lld remote rows in %d stages\n", world, ngpu, n, m, F,
                (long long)nrecv, nst);
     }
@@ -187,6 +188,7 @@ int main(int argc, char **argv)
                worst_h);
         failures += !(worst <= 1.0) + !(worst1 <= 1.0) + !(worst_h <= 1.0);
     }
+    for (int r = 0; r < world; ++r) GK(gnnagg_dist_disconnect(ranks[r]));
     for (int r = 0; r < world; ++r) GK(gnnagg_dist_destroy(ranks[r]));
     gnnagg_destroy(single);
     if (failures) {

@@ -18,7 +18,7 @@ def _stage_csr(ptr, plan, val, s):
     return p, np.ascontiguousarray(plan["idx_new"][sel]), np.ascontiguousarray(val[sel])
 
 
-@pytest.mark.parametrize("world,stages", [(1, 1), (2, 1), (3, 1), (3, 2), (4, 3), (8, 2), (8, 7)])
+@pytest.mark.parametrize("world,stages", [(1, 1), (2, 0), (2, 1), (3, 1), (3, 2), (4, 0), (4, 3), (8, 2), (8, 7)])
 def test_staged_plan_reproduces_the_full_aggregation(orc, world, stages):
     rng = np.random.default_rng(world * 10 + stages)
     sizes = rng.integers(20, 60, world)
@@ -34,8 +34,8 @@ def test_staged_plan_reproduces_the_full_aggregation(orc, world, stages):
         rows = len(lp) - 1
         plan = partition.peer_plan(li, bounds, rank, stages)
         assert plan["num_stages"] == (1 if world == 1 else 1 + min(stages, world - 1))
-        assert sorted(plan["pull_order"]) == [p for p in range(world) if p != rank]
-        # the receive buffer: rows pulled from the owners' shards, owner by owner
+        assert sorted(plan["recv_order"]) == [p for p in range(world) if p != rank]
+        # the receive slots: rows pushed by the owners out of their shards, owner by owner
         recv = np.zeros((len(plan["recv_rows"]), F), np.float32)
         for p in range(world):
             a, b = plan["recv_off"][p], plan["recv_off"][p + 1]
@@ -43,23 +43,31 @@ def test_staged_plan_reproduces_the_full_aggregation(orc, world, stages):
             recv[a:b] = shard[plan["recv_local"][a:b]]
             assert p != rank or a == b                                  # own rows never travel
         assert np.array_equal(recv, X[plan["recv_rows"]])
-        # stages are monotone along the pull order, every stage non-empty in owners
-        st = [plan["stage_of"][p] for p in plan["pull_order"]]
-        assert st == sorted(st) and (world == 1 or set(st) == set(range(1, plan["num_stages"])))
+        # stages are monotone along the arrival order, every stage non-empty in owners
+        st = [plan["stage_of"][p] for p in plan["recv_order"]]
+        assert st == sorted(st) and (world == 1 or stages == 0 or set(st) == set(range(1, plan["num_stages"])))
         acc = np.zeros((rows, F), np.float64)
-        own = np.ascontiguousarray(X[bounds[rank]:bounds[rank + 1]])
+        # ONE buffer serves every stage: the own shard, then the receive slots
+        src = np.ascontiguousarray(np.concatenate([X[bounds[rank]:bounds[rank + 1]], recv])) if rows + len(recv) else np.zeros((1, F), np.float32)
         for s in range(plan["num_stages"]):
             p_s, i_s, v_s = _stage_csr(lp, plan, lv, s)
-            src = own if s == 0 else recv
             if len(i_s):
                 assert i_s.max() < len(src)
-                y, _ = orc.spmm_f64(p_s, i_s, v_s, np.ascontiguousarray(src) if len(src) else np.zeros((1, F), np.float32))
+                if s == 0 and plan["num_stages"] > 1:
+                    assert i_s.max() < rows                           # stage 0 only touches local rows
+                y, _ = orc.spmm_f64(p_s, i_s, v_s, src)
                 acc += y
         lo, hi = int(bounds[rank]), int(bounds[rank + 1])
         assert np.all(np.abs(acc - want[lo:hi]) <= 1e-5 * scale[lo:hi] + 1e-30)
 
 
-def test_every_rank_starts_with_a_different_owner():
+def test_every_receiver_is_written_by_one_owner_at_a_time():
+    """owner p pushes to p-1, p-2, ...; receiver q expects q+1, q+2, ...: in slot k the pairs form a permutation"""
     world = 8
-    firsts = [partition.peer_plan(np.zeros(1, np.int32), np.arange(world + 1) * 4, r, 3)["pull_order"][0] for r in range(world)]
-    assert sorted(firsts) == list(range(world))
+    orders = [partition.peer_plan(np.zeros(1, np.int32), np.arange(world + 1) * 4, r, 3)["recv_order"] for r in range(world)]
+    for k in range(world - 1):
+        owners = [orders[q][k] for q in range(world)]
+        assert sorted(owners) == list(range(world))
+        for q in range(world):
+            p = owners[q]
+            assert (p - 1 - k) % world == q       # what dist.cu's push loop computes on the owner side

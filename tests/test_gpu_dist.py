@@ -35,6 +35,9 @@ def _run_local(gn, cuda, ptr, idx, val, X, bounds, stages, layer_W=None, steps=1
             assert ph.recv_counts == [int(plan["recv_off"][p + 1] - plan["recv_off"][p]) for p in range(world)]
             assert ph.num_stages == plan["num_stages"]
             assert ph.stage_edges == [int((plan["stage"] == s).sum()) for s in range(plan["num_stages"])]
+        ld.connect()
+        for r in range(world):   # what every owner pushes is what the receivers asked for
+            assert ld.ranks[r].send_counts == [ld.ranks[q].recv_counts[r] for q in range(world)]
         Wd = None if layer_W is None else torch.from_numpy(layer_W).to(cuda)
         for step in range(steps):
             buf = step & 1
@@ -58,7 +61,7 @@ def _run_local(gn, cuda, ptr, idx, val, X, bounds, stages, layer_W=None, steps=1
     return outs
 
 
-@pytest.mark.parametrize("world,stages", [(1, 1), (2, 1), (3, 1), (3, 2), (4, 3)])
+@pytest.mark.parametrize("world,stages", [(1, 1), (2, 0), (2, 1), (3, 1), (3, 2), (4, 0), (4, 3)])
 @pytest.mark.parametrize("F", [32, 64, 128, 100])
 def test_local_ranks_match_oracle(gn, orc, cuda, world, stages, F):
     rng = np.random.default_rng(world * 100 + stages * 10 + F)
@@ -98,6 +101,8 @@ def test_bad_source_id_is_rejected(gn, cuda):
         idx = torch.tensor([25], dtype=torch.int32, device=cuda)
         with pytest.raises(gn.GnnaggError):
             ld.set_graph(0, ptr, idx, torch.ones(1, device=cuda), 1)
+        with pytest.raises(gn.GnnaggError):       # connecting ranks without a graph is a state error, not a crash
+            ld.connect()
     finally:
         ld.close()
 
