@@ -301,9 +301,11 @@ class Workload:
             self.agg.gcn_run_host(self.hX, self.hH, scheduled=sched)
         elif self.N == 1:
             self.agg.gcn_layer_host(self.hX, self.hW, self.hH, scheduled=sched)  # H2D + layer + D2H + sync inside
+        elif self.ph is not None:
+            # H2D of the shard into the peer-visible buffer, the step, row-chunked copy back overlapping the last stage
+            self.ph.gcn_layer_host(self.hX, None if self.agg_only else self.hW, self.hH)
         else:
-            dst = self.ph.x(0, self.fin) if self.ph is not None else self.Xs
-            dst.copy_(self.hX, non_blocking=True)
+            self.Xs.copy_(self.hX, non_blocking=True)
             self.step()
             self.hH.copy_(self.H, non_blocking=True)
             torch.cuda.current_stream().synchronize()
@@ -759,7 +761,8 @@ def main():
                         "h2d_bytes_per_step": 4 * n * fin + (4 * fin * fout if (N == 1 and not agg_only) else 0),
                         "d2h_bytes_per_step": 4 * n * (fout or fin),
                         "api": ("gnnagg_gcn_run_host (pinned host X -> Y)" if agg_only else "gnnagg_gcn_layer_host (pinned host X, W -> H)") if N == 1 else
-                               "pinned H2D of the X shard into the peer-visible buffer + the step (halo pulls + aggregation + combination) + D2H of the H shard"},
+                               "gnnagg_dist_gcn_layer_host: pinned H2D of the X shard into the peer-visible buffer + the step (halo pushes + "
+                               "staged aggregation + combination) with the copy back of the H shard overlapping the last stage"},
                 "gpu_launches": int(round(r["launches_per_step"] * args.steps)),
                 "compute_only": {"ms_per_step": round(total_ms, 4),
                                  "value": round(N * bytes_rank / (total_ms * 1e-3) / 1e9, 1), "unit": "GB/s",

@@ -60,7 +60,7 @@ constexpr int kMaxSlices = 16;
 // kLocalitySliceL2Multiples x L2, average degree at least kLocalityMinDegree
 constexpr double kLocalityMinL2Multiples = 8.0;
 constexpr double kLocalitySliceL2Multiples = 2.5;
-constexpr double kLocalityMinDegree = 20.0;
+constexpr double kLocalityMinDegree = 128.0;
 constexpr int kLocalityMaxAuto = 8;
 
 struct gnnagg_aggregator {
@@ -1010,7 +1010,20 @@ int gnnagg_prepare(gnnagg_aggregator *a, int feat, void *stream)
     const int *list = nullptr;
     const int2 *records = nullptr;
     int num_long = 0;
-    return long_rows_of(a, p, EB, (cudaStream_t)stream, &list, &num_long, &records);
+    if (int rc = long_rows_of(a, p, EB, (cudaStream_t)stream, &list, &num_long, &records)) return rc;
+    const int *hp = nullptr;
+    return host_ptr(a, &hp);  // row-range launches (gnnagg_gcn_run_rows) cut edge ranges on the host
+}
+
+int gnnagg_gcn_run_rows(gnnagg_aggregator *a, const float *X, float *Y, int feat, int accumulate, int row_lo, int row_hi,
+                        void *stream)
+{
+    if (!a) return set_error(GNNAGG_ERR_ARG, "gnnagg_gcn_run_rows: NULL aggregator");
+    if (row_lo < 0 || row_hi > a->n || row_lo > row_hi) return set_error(GNNAGG_ERR_ARG, "gnnagg_gcn_run_rows: bad row range");
+    if (row_lo == row_hi) return GNNAGG_OK;
+    const int *hp = nullptr;
+    if (int rc = host_ptr(a, &hp)) return rc;
+    return gcn_run_core(a, X, Y, feat, 0, (cudaStream_t)stream, accumulate != 0, row_lo, row_hi, hp[row_lo], hp[row_hi]);
 }
 
 int gnnagg_gcn_run(gnnagg_aggregator *a, const float *X, float *Y, int feat, int scheduled, void *stream)

@@ -282,6 +282,11 @@ struct gnnagg_dist {
     gnnagg_aggregator *stage[kMaxStages] = {nullptr};
     float *ax = nullptr;
     size_t ax_cap = 0;
+    // host-buffer entry point: device staging of W and of the result, copy-back stream
+    float *st_w = nullptr, *st_out = nullptr;
+    size_t st_w_cap = 0, st_out_cap = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t chunk_done[4] = {nullptr, nullptr, nullptr, nullptr}, copies_done = nullptr;
     // step machinery
     cudaStream_t comm = nullptr;
     cudaEvent_t ev_sig = nullptr, ev_done = nullptr;
@@ -509,6 +514,12 @@ int gnnagg_dist_destroy(gnnagg_dist *d)
     cudaDeviceSynchronize();
     free_graph(d);
     cudaFree(d->ax);
+    cudaFree(d->st_w);
+    cudaFree(d->st_out);
+    if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
+    for (cudaEvent_t e : d->chunk_done)
+        if (e) cudaEventDestroy(e);
+    if (d->copies_done) cudaEventDestroy(d->copies_done);
     if (d->comm) cudaStreamDestroy(d->comm);
     cudaEvent_t evs[] = {d->ev_sig, d->ev_done, d->t_m0, d->t_m1, d->t_m2, d->t_m3, d->t_c0, d->t_c1};
     for (cudaEvent_t e : evs)
@@ -748,8 +759,12 @@ int64_t gnnagg_dist_launch_count(const gnnagg_dist *d)
 
 // One step: Y = A_block * X with X = the shards `buf` of all ranks.  flags: GNNAGG_DIST_NO_EXCHANGE re-uses the
 // receive buffer of the previous step (kernels-only timing).
+// host_out != NULL: the LAST stage runs in kHostChunks row chunks; chunk c is aggregated (and combined) on `st` while
+// the finished rows of chunk c-1 travel to host_out on a second stream (Y / H then are device staging).
+constexpr int kHostChunks = 4;
+
 static int dist_run(gnnagg_dist *d, int buf, float *Y, const float *W, float *H, int feat_in, int feat_out, int flags,
-                    cudaStream_t st)
+                    cudaStream_t st, float *host_out = nullptr)
 {
     if (!d || (!Y && d->rows > 0) || buf < 0 || buf > 1) return set_error(GNNAGG_ERR_ARG, "gnnagg_dist_gcn_run: bad argument");
     if (d->num_stages == 0) return set_error(GNNAGG_ERR_STATE, "gnnagg_dist_gcn_run: no graph (gnnagg_dist_set_graph)");
@@ -804,12 +819,35 @@ static int dist_run(gnnagg_dist *d, int buf, float *Y, const float *W, float *H,
         DT_TRY(cudaEventRecord(d->t_c1, st));
     }
     float *agg_out = W ? d->ax : Y;
+    const int fo = W ? feat_out : feat_in;
     // receiver side: stage by stage, each behind the arrival of its owners
     for (int s = 0; s < d->num_stages; ++s) {
         if (exchange && d->stage_mask[s]) {
             halo_wait_kernel<<<1, 32, 0, st>>>(mine, d->stage_mask[s], epoch);
             DT_TRY(cudaPeekAtLastError());
             ++d->launches;
+        }
+        if (host_out && s == d->num_stages - 1 && d->rows >= 4096) {
+            float *out_dev = W ? H : Y;
+            for (int c = 0; c < kHostChunks; ++c) {
+                const int r0 = (int)((int64_t)d->rows * c / kHostChunks), r1 = (int)((int64_t)d->rows * (c + 1) / kHostChunks);
+                if (r1 <= r0) continue;
+                if (int rc = gnnagg_gcn_run_rows(d->stage[s], xs, agg_out, feat_in, s > 0, r0, r1, st)) return rc;
+                if (W) {
+                    if (int rc = gnnagg_dense_nn(d->ax + (size_t)r0 * feat_in, W, H + (size_t)r0 * feat_out, r1 - r0, feat_out, feat_in, st))
+                        return rc;
+                    d->launches += 2;
+                }
+                DT_TRY(cudaEventRecord(d->chunk_done[c], st));
+                DT_TRY(cudaStreamWaitEvent(d->copy_stream, d->chunk_done[c], 0));
+                DT_TRY(cudaMemcpyAsync(host_out + (size_t)r0 * fo, out_dev + (size_t)r0 * fo, (size_t)(r1 - r0) * fo * sizeof(float),
+                                       cudaMemcpyDeviceToHost, d->copy_stream));
+            }
+            DT_TRY(cudaEventRecord(d->copies_done, d->copy_stream));
+            host_out = nullptr;  // done: nothing left for the tail below
+            W = nullptr;
+            if (d->prof) DT_TRY(cudaEventRecord(d->t_m1, st));
+            continue;
         }
         if (int rc = gnnagg_gcn_run_acc(d->stage[s], xs, agg_out, feat_in, s > 0, st)) return rc;
         if (s == 0 && d->prof) DT_TRY(cudaEventRecord(d->t_m1, st));
@@ -818,6 +856,9 @@ static int dist_run(gnnagg_dist *d, int buf, float *Y, const float *W, float *H,
     if (W && d->rows > 0) {
         if (int rc = gnnagg_dense_nn(d->ax, W, H, d->rows, feat_out, feat_in, st)) return rc;
         d->launches += 2;
+    }
+    if (host_out && d->rows > 0) {  // small shard: one copy after everything
+        DT_TRY(cudaMemcpyAsync(host_out, agg_out == d->ax ? H : Y, (size_t)d->rows * fo * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     if (exchange) {
         PeerTable peers;
@@ -841,6 +882,42 @@ int gnnagg_dist_gcn_layer(gnnagg_dist *d, int buf, const float *W, float *H, int
 {
     if (!W || (!H && d && d->rows > 0)) return set_error(GNNAGG_ERR_ARG, "gnnagg_dist_gcn_layer: NULL argument");
     return dist_run(d, buf, H, W, H, feat_in, feat_out, flags, (cudaStream_t)stream);
+}
+
+int gnnagg_dist_gcn_layer_host(gnnagg_dist *d, int buf, const float *h_X, const float *h_W, float *h_out, int feat_in,
+                               int feat_out, void *stream)
+{
+    if (!d || (d->rows > 0 && (!h_X || !h_out)) || buf < 0 || buf > 1)
+        return set_error(GNNAGG_ERR_ARG, "gnnagg_dist_gcn_layer_host: bad argument");
+    if (!d->base) return set_error(GNNAGG_ERR_STATE, "gnnagg_dist_gcn_layer_host: no graph (gnnagg_dist_set_graph)");
+    if (feat_in < 4 || (feat_in & 3) || feat_in > d->feat_cap) return set_error(GNNAGG_ERR_ARG, "gnnagg_dist_gcn_layer_host: bad feat");
+    DeviceGuard guard(d->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int fo = h_W ? feat_out : feat_in;
+    auto grow = [](float *&p, size_t &cap, size_t need) -> cudaError_t {
+        if (need <= cap && p) return cudaSuccess;
+        cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc((void **)&p, (need ? need : 1) * sizeof(float));
+        if (e == cudaSuccess) cap = need;
+        return e;
+    };
+    DT_TRY(grow(d->st_out, d->st_out_cap, (size_t)d->rows * fo));
+    if (h_W) DT_TRY(grow(d->st_w, d->st_w_cap, (size_t)feat_in * feat_out));
+    if (!d->copy_stream) {
+        DT_TRY(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+        for (cudaEvent_t &e : d->chunk_done) DT_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        DT_TRY(cudaEventCreateWithFlags(&d->copies_done, cudaEventDisableTiming));
+    }
+    DT_TRY(cudaEventRecord(d->copies_done, d->copy_stream));  // so that the wait below is defined when no chunk copy is issued
+    if (d->rows > 0)
+        DT_TRY(cudaMemcpyAsync(d->base + d->off_x[buf], h_X, (size_t)d->rows * feat_in * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (h_W) DT_TRY(cudaMemcpyAsync(d->st_w, h_W, (size_t)feat_in * feat_out * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (int rc = dist_run(d, buf, d->st_out, h_W ? d->st_w : nullptr, d->st_out, feat_in, feat_out, 0, st, h_out)) return rc;
+    DT_TRY(cudaStreamWaitEvent(st, d->copies_done, 0));
+    DT_TRY(cudaStreamSynchronize(st));
+    return GNNAGG_OK;
 }
 
 }  // extern "C"

@@ -69,6 +69,7 @@ _SIGS = {
     "gnnagg_sched_dev_val": (C.c_void_p, [C.c_void_p]),
     "gnnagg_prepare": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "gnnagg_gcn_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "gnnagg_gcn_run_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "gnnagg_gcn_run_acc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "gnnagg_gcn_run_edgewise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "gnnagg_csr2edgelist": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -115,6 +116,7 @@ _SIGS = {
     "gnnagg_dist_x": (C.c_void_p, [C.c_void_p, C.c_int]),
     "gnnagg_dist_gcn_run": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "gnnagg_dist_gcn_layer": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "gnnagg_dist_gcn_layer_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "gnnagg_dist_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int),
                                    C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "gnnagg_dist_connect_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
@@ -378,6 +380,11 @@ class Aggregator:
 
     def gcn_run_acc(self, X, Y, accumulate=True):
         check(lib().gnnagg_gcn_run_acc(self.h, _f32(X, "X"), _f32(Y, "Y"), X.shape[1], int(accumulate), _stream()))
+        return Y
+
+    def gcn_run_rows(self, X, Y, row_lo, row_hi, accumulate=False):
+        check(lib().gnnagg_gcn_run_rows(self.h, _f32(X, "X"), _f32(Y, "Y"), X.shape[1], int(accumulate), int(row_lo), int(row_hi),
+                                        _stream()))
         return Y
 
     def gcn_run_edgewise(self, X, Y):

@@ -408,6 +408,15 @@ class PeerHalo:
                                           0 if exchange else DIST_NO_EXCHANGE, _stream()))
         return H
 
+    def gcn_layer_host(self, hX, hW, hH, buf=0):
+        """pinned host X shard (and W) -> host H (or A*X when hW is None); copies inside, synchronises the stream"""
+        from . import _f32, _stream, check, lib
+
+        fin = hX.shape[1]
+        check(lib().gnnagg_dist_gcn_layer_host(self.h, int(buf), _f32(hX, "hX", cuda=False), _f32(hW, "hW", cuda=False),
+                                               _f32(hH, "hH", cuda=False), fin, fin if hW is None else hW.shape[1], _stream()))
+        return hH
+
     def profile(self, on=True):
         from . import check, lib
 

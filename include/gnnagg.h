@@ -163,6 +163,12 @@ int gnnagg_gcn_run(gnnagg_aggregator *a, const float *X, float *Y, int feat, int
  * accumulate = 0 it is gnnagg_gcn_run(scheduled = 0).  Deterministic (no atomics). */
 int gnnagg_gcn_run_acc(gnnagg_aggregator *a, const float *X, float *Y, int feat, int accumulate, void *stream);
 
+/* the same for the destination rows [row_lo, row_hi) only (Y is still indexed by global row): lets a caller
+ * pipeline the aggregation of one row chunk with the copy-out / combination of the previous one.  Cuts the edge
+ * range on a host mirror of the row pointers (copied once; gnnagg_prepare does it ahead of time). */
+int gnnagg_gcn_run_rows(gnnagg_aggregator *a, const float *X, float *Y, int feat, int accumulate, int row_lo, int row_hi,
+                        void *stream);
+
 /* out[i,:] = X[rows[i],:] for i < count (feat a multiple of 4).  Packs the rows of the local X shard that
  * another rank's row block references before the pruned halo exchange (multi-GPU path, new functionality:
  * the reference is single-GPU). */
@@ -329,6 +335,11 @@ float *gnnagg_dist_x(gnnagg_dist *d, int buf); /* [rows of the shard, feat] row-
 int gnnagg_dist_gcn_run(gnnagg_dist *d, int buf, float *Y, int feat, int flags, void *stream);
 int gnnagg_dist_gcn_layer(gnnagg_dist *d, int buf, const float *W, float *H, int feat_in, int feat_out, int flags,
                           void *stream);
+/* host-buffer variants (bench.py's e2e number at N > 1): X shard host -> peer-visible buffer, the step, result ->
+ * host; the last stage runs row chunk by row chunk so the copy back overlaps it.  Synchronise `stream`.  Pinned host
+ * memory makes the copies asynchronous.  h_W NULL: aggregation only (h_out is [rows, feat_in]). */
+int gnnagg_dist_gcn_layer_host(gnnagg_dist *d, int buf, const float *h_X, const float *h_W, float *h_out, int feat_in,
+                               int feat_out, void *stream);
 /* distinct remote source rows this rank receives per step (in total / per owner), stages and their edge counts,
  * rows this rank pushes to every peer (after connect); any pointer may be NULL */
 int gnnagg_dist_info(const gnnagg_dist *d, int64_t *num_recv, int64_t *recv_counts /* [world] */, int *num_stages,
@@ -365,8 +376,10 @@ int gnnagg_set_host_pipeline(gnnagg_aggregator *a, int slices);
  * (graph_schedule.h:17-89: process the edges source range by source range so that the gathered rows stay in cache)
  * without its float atomics: the CSR is split once, on the GPU, into `slices` sub-CSRs by source range and the
  * deterministic kernel accumulates them one after the other; lanes whose partial sum is zero skip the pass over Y.
- *   0  automatic (default): only when X is >= 8x the L2 and the average degree is >= 20 (products-shape F=256: 8
- *      slices); the BASELINE.json reddit / proteins / arxiv shapes run un-sliced
+ *   0  automatic (default): only when X is >= 8x the L2 AND the average degree is >= 128 -- every slice walks all
+ *      rows, so short rows make the passes cost more than the locality returns (products-shape, 25 edges per row,
+ *      F=256: 4.43 ms un-sliced, 5.78 / 7.88 / 12.4 ms with 4 / 8 / 16 slices); none of the BASELINE.json shapes
+ *      qualifies on one GPU
  *   1  off;  2..16  forced.   Square graphs (sources in [0, num_v)); out-of-range sources fall into the last slice.
  * Results are deterministic for a given setting; slices change the fp32 summation order (slice by slice). */
 int gnnagg_set_locality_slices(gnnagg_aggregator *a, int slices);

@@ -55,6 +55,14 @@ def main():
         torch.cuda.synchronize()
         ph.check()
         same = bool(torch.equal(Y, Y2))
+        # the host-buffer entry point (H2D of the shard, the step, row-chunked copy back) must agree with the device run
+        hX = torch.empty((r1 - r0, F)).pin_memory().copy_(X[r0:r1])
+        hY = torch.empty((r1 - r0, F)).pin_memory()
+        ph.gcn_layer_host(hX, None, hY)
+        ph.check()
+        host_diff = float((hY.to(dev) - Y).abs().max().item()) if r1 > r0 else 0.0
+        host_ref = float(Y.abs().max().item()) if r1 > r0 else 1.0
+        same = same and host_diff <= 2e-5 * max(host_ref, 1e-30)
         # collect the blocks on rank 0
         if rank == 0:
             full = torch.empty((n, F), device=dev)

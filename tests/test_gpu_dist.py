@@ -93,6 +93,34 @@ def test_local_ranks_layer_and_determinism(gn, orc, cuda):
     assert np.array_equal(a, b)                  # no atomics anywhere: bit-reproducible
 
 
+@pytest.mark.parametrize("layer", [False, True])
+def test_host_buffer_entry_point_single_rank(gn, orc, cuda, layer):
+    """gnnagg_dist_gcn_layer_host on a one-rank group (it synchronises the stream, so several ranks need one process or
+    host thread each: tests/multirank_worker.py covers that): row-chunked last stage + copy back vs the oracle"""
+    rng = np.random.default_rng(11)
+    n, F = 9000, 64
+    ptr, idx = synth.small_random_csr(n, 25.0, 21, hub=30000)
+    val = rng.standard_normal(len(idx)).astype(np.float32)
+    X = rng.standard_normal((n, F)).astype(np.float32)
+    W = (rng.standard_normal((F, 96)) / 8).astype(np.float32)
+    ld = partition.LocalDist([0, n], F, devices=[0])
+    try:
+        ph = ld.set_graph(0, *(torch.from_numpy(a).to(cuda) for a in (ptr, idx, val)), 0)
+        ld.connect()
+        hX = torch.from_numpy(X).pin_memory()
+        hW = torch.from_numpy(W).pin_memory() if layer else None
+        hH = torch.empty((n, 96 if layer else F)).pin_memory()
+        ph.gcn_layer_host(hX, hW, hH)
+        ph.check()
+    finally:
+        ld.close()
+    if layer:
+        _, want, scale = orc.gcn_layer_f64(ptr, idx, val, X, W)
+    else:
+        want, scale = orc.spmm_f64(ptr, idx, val, X)
+    assert np.all(np.abs(hH.numpy().astype(np.float64) - want) <= 1e-5 * scale + 1e-30)
+
+
 def test_bad_source_id_is_rejected(gn, cuda):
     bounds = [0, 10, 20]
     ld = partition.LocalDist(bounds, 32, devices=[0, 0])
