@@ -42,6 +42,8 @@ namespace gnnagg {
 constexpr int kMaxWorld = GNNAGG_DIST_MAX_WORLD;
 constexpr uint64_t kSpinLimitNs = 20ull * 1000 * 1000 * 1000;  // a peer that does not answer within 20 s is reported
 constexpr size_t kFlagBytes = 512;
+constexpr int kMaxRounds = 16;          // row chunks of the row-pipelined mode
+constexpr size_t kMetaBytes = 1536;     // int recv_tab[kMaxRounds][kMaxWorld + 1] behind the flags, read by the owners at connect
 
 struct HaloFlags {
     uint32_t arrived[kMaxWorld];   // arrived[p]: last epoch whose rows owner p has written into MY receive buffer (written by p)
@@ -123,21 +125,24 @@ __global__ void __launch_bounds__(32) halo_consumed_kernel(PeerTable peers, int 
     if (p < world && p != rank) st_release_sys(&peers.flags[p]->consumed[rank], epoch);
 }
 
-// dst[i, :] = X[rows[i], :] for the `count` rows receiver q wants from this owner: X is the own shard (local gathers),
-// dst the slice of q's receive buffer reserved for this owner (peer memory: the stores travel over NVLink, or stay
-// local when the "peer" lives on the same device).  U independent 128-bit loads per thread before the first store.
-// The last CTA to finish publishes `epoch` in q's arrived[] flag.
+// dst[i, :] = X[rows[i], :] for the `count` rows receiver q wants from this owner (in this round): X is the own shard
+// (local gathers), dst the slice of q's receive slots reserved for them (peer memory: the stores travel over NVLink, or
+// stay local when the "peer" lives on the same device).  The last CTA to finish publishes `value` in q's arrived[] flag.
+// Built to run BESIDE the aggregation kernel, not instead of it: 128 threads and at most 32 registers, so a CTA fits
+// into what three aggregation CTAs (3 x 256 threads x 80 registers) leave free on an SM; the first version (256 threads,
+// 8 loads in flight per thread, 2 CTAs per SM) displaced one aggregation CTA per SM for as long as the exchange ran.
+// Posted writes need no latency hiding; U loads per thread cover the local gather latency.
 template <int U>
-__global__ void __launch_bounds__(256) halo_push_kernel(const float4 *__restrict__ X, const int *__restrict__ rows,
-                                                        float4 *__restrict__ dst, int64_t count4, int F4, int f4_shift,
-                                                        uint32_t *done_cnt, uint32_t *arrived_flag, uint32_t epoch)
+__global__ void __launch_bounds__(128, 16) halo_push_kernel(const float4 *__restrict__ X, const int *__restrict__ rows,
+                                                            float4 *__restrict__ dst, int64_t count4, int F4, int f4_shift,
+                                                            uint32_t *done_cnt, uint32_t *arrived_flag, uint32_t value)
 {
-    const int64_t stride = (int64_t)gridDim.x * 256 * U;
-    for (int64_t base = (int64_t)blockIdx.x * 256 * U + threadIdx.x; base < count4; base += stride) {
+    const int64_t stride = (int64_t)gridDim.x * 128 * U;
+    for (int64_t base = (int64_t)blockIdx.x * 128 * U + threadIdx.x; base < count4; base += stride) {
         float4 v[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int64_t e = base + (int64_t)u * 256;
+            const int64_t e = base + (int64_t)u * 128;
             if (e < count4) {
                 const int64_t r = (f4_shift >= 0) ? (e >> f4_shift) : (e / F4);
                 const int c = (int)(e - r * F4);
@@ -146,7 +151,7 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const float4 *__restrict
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int64_t e = base + (int64_t)u * 256;
+            const int64_t e = base + (int64_t)u * 128;
             if (e < count4) dst[e] = v[u];
         }
     }
@@ -158,7 +163,7 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const float4 *__restrict
         if (before == gridDim.x - 1) {
             atomicExch(done_cnt, 0u);  // ready for the next launch towards this receiver (stream-ordered after this one)
             __threadfence_system();
-            st_release_sys(arrived_flag, epoch);
+            st_release_sys(arrived_flag, value);
         }
     }
 }
@@ -208,6 +213,67 @@ __global__ void __launch_bounds__(256) dist_reindex_kernel(const int *__restrict
     }
 }
 
+// ---- row-pipelined mode: the round (row chunk) in which every remote source is needed first
+struct ChunkRows {
+    int lo[kMaxRounds + 1];
+    int rounds;
+};
+
+__global__ void __launch_bounds__(256) dist_first_use_kernel(const int *__restrict__ ptr, const int *__restrict__ idx,
+                                                             const int *__restrict__ item_row, int num_items, int n, int64_t m,
+                                                             int64_t own_lo, int64_t own_hi, int64_t total, ChunkRows cr,
+                                                             int *__restrict__ first, int *__restrict__ bad)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= m) return;
+    const int64_t g = __ldg(idx + e);
+    if (g < 0 || g >= total) {
+        *bad = 1;
+        return;
+    }
+    if (g >= own_lo && g < own_hi) return;
+    const int row = row_of_edge(ptr, item_row, num_items, n, (int)e);
+    int c = 0;
+    while (c + 1 < cr.rounds && row >= cr.lo[c + 1]) ++c;
+    atomicMin(first + g, c);
+}
+
+__global__ void __launch_bounds__(256) dist_round_mark_kernel(const int *__restrict__ first, int64_t total, int round, int any,
+                                                              int *__restrict__ mark)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > total) return;
+    mark[g] = (g < total && (any ? first[g] < kMaxRounds + 1 : first[g] == round)) ? 1 : 0;
+}
+
+// receive slots of round `round` start at `base`; inside a round ascending global id (owner by owner)
+__global__ void __launch_bounds__(256) dist_round_fill_kernel(const int *__restrict__ mark, const int *__restrict__ pos, int64_t total,
+                                                              Bounds b, int base, int *__restrict__ recv_local, int *__restrict__ slot)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total || !mark[g]) return;
+    const int s = base + pos[g];
+    recv_local[s] = (int)(g - b.b[owner_of(b, g)]);
+    slot[g] = s;
+}
+
+__global__ void __launch_bounds__(256) dist_reindex_slot_kernel(const int *__restrict__ idx, int64_t m, const int *__restrict__ slot,
+                                                                int64_t own_lo, int64_t own_hi, int rows_own,
+                                                                int *__restrict__ idx_new, int *__restrict__ keys)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= m) return;
+    const int64_t g = __ldg(idx + e);
+    idx_new[e] = (g >= own_lo && g < own_hi) ? (int)(g - own_lo) : rows_own + __ldg(slot + g);
+    keys[e] = 0;
+}
+
+__global__ void __launch_bounds__(256) dist_fill_int_kernel(int *__restrict__ out, int64_t count, int value)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = value;
+}
+
 __global__ void __launch_bounds__(256) dist_gather_val_kernel(const float *__restrict__ val, const int *__restrict__ perm,
                                                               float *__restrict__ out, int count)
 {
@@ -245,8 +311,8 @@ struct DistBlob {
     int64_t rows;
     uint64_t raw_base;  // usable as is inside the exporting process
     uint64_t bytes;
-    uint64_t off_x[2], off_req;
-    int recv_off[kMaxWorld + 1];  // receive slots of every owner inside this rank's buffer / request list
+    uint64_t off_x[2], off_req, off_meta;
+    int rounds;  // 1, or the row chunks of the row-pipelined mode: rows of recv_tab (in the buffer, at off_meta) in use
     cudaIpcMemHandle_t mem;
 };
 static_assert(sizeof(DistBlob) <= GNNAGG_DIST_BLOB_BYTES, "blob too large");
@@ -258,14 +324,15 @@ struct gnnagg_dist {
     int feat_cap = 0;
     // peer-visible allocation (made by set_graph): [flags | wanted-row list | x0 + receive 0 | x1 + receive 1]
     char *base = nullptr;
-    size_t bytes = 0, off_x[2] = {0, 0}, off_req = 0;
+    size_t bytes = 0, off_x[2] = {0, 0}, off_req = 0, off_meta = 0;
     // peers as seen from this rank
     char *peer_base[kMaxWorld] = {nullptr};
     size_t peer_off_x[kMaxWorld][2] = {{0, 0}};
     int peer_rows[kMaxWorld] = {0};         // rows of q's shard: its receive buffer starts that many rows behind its x
-    int peer_slot[kMaxWorld] = {0};         // first receive slot of q's buffer that belongs to this owner
-    int send_cnt[kMaxWorld] = {0};          // rows q wants from this owner
-    int *send_rows[kMaxWorld] = {nullptr};  // which ones (local row numbers; owned copy of q's list)
+    int peer_slot[kMaxWorld][kMaxRounds] = {{0}};  // first receive slot of q's buffer for this owner's rows of round c
+    int send_cnt[kMaxWorld][kMaxRounds] = {{0}};   // rows q wants from this owner in round c
+    int send_off[kMaxWorld][kMaxRounds] = {{0}};   // where they start inside send_rows[q]
+    int *send_rows[kMaxWorld] = {nullptr};         // which ones (local row numbers; owned copy of q's lists, round by round)
     bool peer_ipc[kMaxWorld] = {false};
     bool connected = false;
     // plan
@@ -274,7 +341,13 @@ struct gnnagg_dist {
     int stage_of[kMaxWorld] = {0};
     uint32_t stage_mask[kMaxStages] = {0};  // owners whose arrival a stage waits for
     int64_t num_recv = 0;
-    int recv_off[kMaxWorld + 1] = {0};
+    // rounds = 1: receive slots ascending by global id (owner by owner).  Row-pipelined mode (rounds = K row chunks):
+    // slots ordered by the round in which a row is needed first, then by id; recv_tab[c][p] = first slot of owner p's
+    // rows of round c, recv_tab[c][world] = end of round c
+    int rounds = 1;
+    int recv_tab[kMaxRounds][kMaxWorld + 1] = {{0}};
+    int chunk_rows[kMaxRounds + 1] = {0};
+    int64_t recv_cnt[kMaxWorld] = {0};
     // sub-CSRs, one per stage
     int *sl_ptr = nullptr, *sl_idx = nullptr, *sl_perm = nullptr;
     float *sl_val = nullptr;
@@ -309,7 +382,7 @@ static void close_peers(gnnagg_dist *d)
         d->peer_ipc[p] = false;
         cudaFree(d->send_rows[p]);
         d->send_rows[p] = nullptr;
-        d->send_cnt[p] = 0;
+        for (int c = 0; c < kMaxRounds; ++c) d->send_cnt[p][c] = 0;
     }
     d->connected = d->world == 1 && d->base != nullptr;
 }
@@ -371,7 +444,7 @@ int gnnagg_dist_create_rank(int rank, int world, const int64_t *shard_bounds, in
         if (cudaFuncGetAttributes(&attr, halo_begin_kernel) != cudaSuccess) cudaGetLastError();
         if (cudaFuncGetAttributes(&attr, halo_wait_kernel) != cudaSuccess) cudaGetLastError();
         if (cudaFuncGetAttributes(&attr, halo_consumed_kernel) != cudaSuccess) cudaGetLastError();
-        if (cudaFuncGetAttributes(&attr, halo_push_kernel<8>) != cudaSuccess) cudaGetLastError();
+        if (cudaFuncGetAttributes(&attr, halo_push_kernel<4>) != cudaSuccess) cudaGetLastError();
         dense_preload();
     }
     *out = d;
@@ -414,8 +487,8 @@ int gnnagg_dist_export(gnnagg_dist *d, void *blob)
     b.rows = d->rows;
     b.raw_base = (uint64_t)(uintptr_t)d->base;
     b.bytes = d->bytes;
-    b.off_x[0] = d->off_x[0], b.off_x[1] = d->off_x[1], b.off_req = d->off_req;
-    for (int p = 0; p <= d->world; ++p) b.recv_off[p] = d->recv_off[p];
+    b.off_x[0] = d->off_x[0], b.off_x[1] = d->off_x[1], b.off_req = d->off_req, b.off_meta = d->off_meta;
+    b.rounds = d->rounds;
     // a handle is only needed by OTHER processes; a failure here (IPC not permitted) is reported at connect time
     if (cudaIpcGetMemHandle(&b.mem, d->base) != cudaSuccess) {
         cudaGetLastError();
@@ -467,13 +540,24 @@ int gnnagg_dist_connect(gnnagg_dist *d, const void *blobs)
         d->peer_off_x[p][0] = b.off_x[0];
         d->peer_off_x[p][1] = b.off_x[1];
         d->peer_rows[p] = (int)b.rows;
-        // the rows p wants from this owner: slots [recv_off[rank], recv_off[rank + 1]) of ITS list; copied once
-        d->peer_slot[p] = b.recv_off[d->rank];
-        d->send_cnt[p] = b.recv_off[d->rank + 1] - b.recv_off[d->rank];
-        if (d->send_cnt[p] > 0) {
-            DT_TRY(cudaMalloc((void **)&d->send_rows[p], (size_t)d->send_cnt[p] * sizeof(int)));
-            DT_TRY(cudaMemcpy(d->send_rows[p], d->peer_base[p] + b.off_req + (size_t)d->peer_slot[p] * sizeof(int),
-                              (size_t)d->send_cnt[p] * sizeof(int), cudaMemcpyDefault));
+        // the rows p wants from this owner: per round c the slots [tab[c][rank], tab[c][rank + 1]) of ITS list; copied once
+        if (b.rounds != d->rounds) return set_error(GNNAGG_ERR_ARG, "gnnagg_dist_connect: ranks disagree on the pipelining mode");
+        int tab[kMaxRounds][kMaxWorld + 1];
+        DT_TRY(cudaMemcpy(tab, d->peer_base[p] + b.off_meta, sizeof tab, cudaMemcpyDefault));
+        int total_rows = 0;
+        for (int c = 0; c < d->rounds; ++c) {
+            d->peer_slot[p][c] = tab[c][d->rank];
+            d->send_cnt[p][c] = tab[c][d->rank + 1] - tab[c][d->rank];
+            d->send_off[p][c] = total_rows;
+            total_rows += d->send_cnt[p][c];
+        }
+        if (total_rows > 0) {
+            DT_TRY(cudaMalloc((void **)&d->send_rows[p], (size_t)total_rows * sizeof(int)));
+            for (int c = 0; c < d->rounds; ++c)
+                if (d->send_cnt[p][c] > 0)
+                    DT_TRY(cudaMemcpy(d->send_rows[p] + d->send_off[p][c],
+                                      d->peer_base[p] + b.off_req + (size_t)d->peer_slot[p][c] * sizeof(int),
+                                      (size_t)d->send_cnt[p][c] * sizeof(int), cudaMemcpyDefault));
         }
         if (b.device == d->device) ++same;
     }
@@ -537,7 +621,7 @@ float *gnnagg_dist_x(gnnagg_dist *d, int buf)
 int gnnagg_dist_set_graph(gnnagg_dist *d, const int *d_ptr, const int *d_idx, const float *d_val, int64_t num_e,
                           int remote_stages, void *stream)
 {
-    if (!d || !d_ptr || (num_e > 0 && (!d_idx || !d_val)) || num_e < 0 || num_e > INT32_MAX || remote_stages < 0)
+    if (!d || !d_ptr || (num_e > 0 && (!d_idx || !d_val)) || num_e < 0 || num_e > INT32_MAX)
         return set_error(GNNAGG_ERR_ARG, "gnnagg_dist_set_graph: bad argument");
     if (d->base)
         return set_error(GNNAGG_ERR_STATE, "gnnagg_dist_set_graph: this rank already has a graph (peers may have it mapped); "
@@ -547,12 +631,17 @@ int gnnagg_dist_set_graph(gnnagg_dist *d, const int *d_ptr, const int *d_idx, co
     const int W = d->world, n = d->rows, m = (int)num_e;
     const int64_t total = d->bounds[W];
     const int64_t own_lo = d->bounds[d->rank], own_hi = d->bounds[d->rank + 1];
-    // stages: R = 0 -> a single pass once everything has arrived.  Otherwise stage 0 = local sources and the W-1 remote
-    // owners, taken in the order rank+1, rank+2, ... (the order in which they push to this rank), cut into R groups
-    int R = W > 1 ? remote_stages : 0;
-    if (R > W - 1) R = W - 1;
+    // pipelining mode.  remote_stages = R > 0: stage 0 = local sources, the W-1 remote owners -- taken in the order
+    // rank+1, rank+2, ... in which they push to this rank -- cut into R groups, one accumulating stage each.
+    // R = 0: a single pass once everything has arrived.  R < 0: ROW pipelining with K = -R row chunks: the receive
+    // slots are ordered by the chunk that needs a row first, the owners push round by round and chunk c (a row range
+    // of the ONE CSR: no extra pass over Y) starts when round c has landed.
+    int R = 0, K = 1;
+    if (W > 1 && remote_stages > 0) R = remote_stages > W - 1 ? W - 1 : remote_stages;
+    if (W > 1 && remote_stages < 0) K = -remote_stages > kMaxRounds ? kMaxRounds : -remote_stages;
     d->remote_stages = R;
     d->num_stages = 1 + R;
+    d->rounds = K;
     for (int s = 0; s < kMaxStages; ++s) d->stage_mask[s] = 0;
     d->stage_of[d->rank] = 0;
     for (int k = 0; k < W - 1; ++k) {
@@ -566,10 +655,15 @@ int gnnagg_dist_set_graph(gnnagg_dist *d, const int *d_ptr, const int *d_idx, co
     for (int p = 0; p <= W; ++p) b.b[p] = d->bounds[p];
     for (int p = 0; p < W; ++p) b.stage_of[p] = d->stage_of[p];
 
-    int *mark = nullptr, *pos = nullptr, *bad = nullptr, *idx_new = nullptr, *keys = nullptr, *item_row = nullptr;
+    int *mark = nullptr, *pos = nullptr, *bad = nullptr, *idx_new = nullptr, *keys = nullptr, *item_row = nullptr, *first = nullptr,
+        *slot = nullptr;
     void *tmp = nullptr;
+    size_t tmp_bytes = 0;
     int rc = GNNAGG_OK;
-    auto cleanup = [&]() { cudaFree(mark), cudaFree(pos), cudaFree(bad), cudaFree(idx_new), cudaFree(keys), cudaFree(item_row), cudaFree(tmp); };
+    auto cleanup = [&]() {
+        cudaFree(mark), cudaFree(pos), cudaFree(bad), cudaFree(idx_new), cudaFree(keys), cudaFree(item_row), cudaFree(first),
+            cudaFree(slot), cudaFree(tmp);
+    };
 #define SG_TRY(expr)                                                                             \
     do {                                                                                         \
         cudaError_t _e = (expr);                                                                 \
@@ -581,63 +675,122 @@ int gnnagg_dist_set_graph(gnnagg_dist *d, const int *d_ptr, const int *d_idx, co
             return set_error(GNNAGG_ERR_CUDA, _buf);                                             \
         }                                                                                        \
     } while (0)
+#define SG_FAIL(code, msg)      \
+    do {                        \
+        cleanup();              \
+        free_graph(d);          \
+        return set_error(code, msg); \
+    } while (0)
     const size_t me = (size_t)(m > 0 ? m : 1);
+    int items = 0;
+    rc = build_item_rows_device(d_ptr, n, m, &item_row, &items, st);
+    if (rc != GNNAGG_OK) {
+        cleanup();
+        free_graph(d);
+        return rc;
+    }
     SG_TRY(cudaMalloc((void **)&mark, ((size_t)total + 1) * sizeof(int)));
     SG_TRY(cudaMalloc((void **)&pos, ((size_t)total + 1) * sizeof(int)));
     SG_TRY(cudaMalloc((void **)&bad, sizeof(int)));
-    SG_TRY(cudaMemsetAsync(mark, 0, ((size_t)total + 1) * sizeof(int), st));
     SG_TRY(cudaMemsetAsync(bad, 0, sizeof(int), st));
-    if (m > 0) dist_mark_kernel<<<nblocks(m), 256, 0, st>>>(d_idx, m, own_lo, own_hi, total, mark, bad);
-    size_t need = 0;
-    SG_TRY(cub::DeviceScan::ExclusiveSum(nullptr, need, mark, pos, (int)(total + 1), st));
-    SG_TRY(cudaMalloc(&tmp, need ? need : 1));
-    SG_TRY(cub::DeviceScan::ExclusiveSum(tmp, need, mark, pos, (int)(total + 1), st));
-    int h_bad = 0, h_off[kMaxWorld + 1] = {0};
+    {
+        size_t need = 0;
+        SG_TRY(cub::DeviceScan::ExclusiveSum(nullptr, need, mark, pos, (int)(total + 1), st));
+        SG_TRY(cudaMalloc(&tmp, need ? need : 1));
+        tmp_bytes = need;
+    }
+    // row chunks (edge balanced, cut on a host mirror of the row pointers); K = 1: the whole block
+    d->chunk_rows[0] = 0;
+    for (int c = 1; c <= kMaxRounds; ++c) d->chunk_rows[c] = n;
+    if (K > 1) {
+        int *hp = new int[(size_t)n + 1];
+        cudaError_t e = cudaMemcpyAsync(hp, d_ptr, ((size_t)n + 1) * sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess)
+            for (int c = 1; c < K; ++c) {
+                const int64_t target = (int64_t)m * c / K;
+                d->chunk_rows[c] = (int)(std::lower_bound(hp, hp + n + 1, (int)target) - hp);
+                if (d->chunk_rows[c] > n) d->chunk_rows[c] = n;
+                if (d->chunk_rows[c] < d->chunk_rows[c - 1]) d->chunk_rows[c] = d->chunk_rows[c - 1];
+            }
+        delete[] hp;
+        SG_TRY(e);
+    }
+    // ---- which remote rows, and in which round each is needed first (first[g]; kMaxRounds + 1 = never)
+    SG_TRY(cudaMalloc((void **)&first, ((size_t)total + 1) * sizeof(int)));
+    dist_fill_int_kernel<<<nblocks(total + 1), 256, 0, st>>>(first, total + 1, kMaxRounds + 1);
+    {
+        ChunkRows cr;
+        memset(&cr, 0, sizeof cr);
+        cr.rounds = K;
+        for (int c = 0; c <= kMaxRounds; ++c) cr.lo[c] = d->chunk_rows[c];
+        if (m > 0)
+            dist_first_use_kernel<<<nblocks(m), 256, 0, st>>>(d_ptr, d_idx, item_row, items, n, m, own_lo, own_hi, total, cr, first, bad);
+    }
+    int h_bad = 0, h_total = 0;
+    dist_round_mark_kernel<<<nblocks(total + 1), 256, 0, st>>>(first, total, 0, 1, mark);
+    SG_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, mark, pos, (int)(total + 1), st));
     SG_TRY(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
-    for (int p = 0; p <= W; ++p) SG_TRY(cudaMemcpyAsync(&h_off[p], pos + d->bounds[p], sizeof(int), cudaMemcpyDeviceToHost, st));
-    SG_TRY(cudaStreamSynchronize(st));
-    if (h_bad) {
-        cleanup();
-        free_graph(d);
-        return set_error(GNNAGG_ERR_ARG, "gnnagg_dist_set_graph: a source id lies outside [0, shard_bounds[world])");
+    SG_TRY(cudaMemcpyAsync(&h_total, pos + total, sizeof(int), cudaMemcpyDeviceToHost, st));
+    {
+        int h_off[kMaxWorld + 1] = {0};
+        for (int p = 0; p <= W; ++p) SG_TRY(cudaMemcpyAsync(&h_off[p], pos + d->bounds[p], sizeof(int), cudaMemcpyDeviceToHost, st));
+        SG_TRY(cudaStreamSynchronize(st));
+        for (int p = 0; p < W; ++p) d->recv_cnt[p] = h_off[p + 1] - h_off[p];
     }
-    for (int p = 0; p <= W; ++p) d->recv_off[p] = h_off[p];
-    d->num_recv = h_off[W];
-    if ((int64_t)n + d->num_recv > INT32_MAX) {
-        cleanup();
-        free_graph(d);
-        return set_error(GNNAGG_ERR_ARG, "gnnagg_dist_set_graph: shard rows + receive slots exceed int32");
-    }
-    // the peer-visible allocation: flags | wanted rows | 2 x (shard + receive buffer)
+    if (h_bad) SG_FAIL(GNNAGG_ERR_ARG, "gnnagg_dist_set_graph: a source id lies outside [0, shard_bounds[world])");
+    d->num_recv = h_total;
+    if ((int64_t)n + d->num_recv > INT32_MAX) SG_FAIL(GNNAGG_ERR_ARG, "gnnagg_dist_set_graph: shard rows + receive slots exceed int32");
+    // ---- the peer-visible allocation: flags | slot table | wanted rows | 2 x (shard + receive slots)
     {
         const size_t req = round512((size_t)(d->num_recv > 0 ? d->num_recv : 1) * sizeof(int));
         const size_t xbuf = round512(((size_t)n + (size_t)d->num_recv) * d->feat_cap * sizeof(float) + 16);
-        d->off_req = kFlagBytes;
-        d->off_x[0] = kFlagBytes + req;
+        d->off_meta = kFlagBytes;
+        d->off_req = kFlagBytes + kMetaBytes;
+        d->off_x[0] = d->off_req + req;
         d->off_x[1] = d->off_x[0] + xbuf;
         d->bytes = d->off_x[1] + xbuf;
         SG_TRY(cudaMalloc((void **)&d->base, d->bytes));
-        SG_TRY(cudaMemsetAsync(d->base, 0, kFlagBytes, st));
+        SG_TRY(cudaMemsetAsync(d->base, 0, kFlagBytes + kMetaBytes, st));
         d->peer_base[d->rank] = d->base;
         d->peer_off_x[d->rank][0] = d->off_x[0];
         d->peer_off_x[d->rank][1] = d->off_x[1];
     }
-    if (total > 0)
-        dist_fill_recv_kernel<<<nblocks(total), 256, 0, st>>>(mark, pos, total, b, reinterpret_cast<int *>(d->base + d->off_req));
+    // ---- receive slots round by round (one round unless row-pipelined), inside a round ascending global id
+    SG_TRY(cudaMalloc((void **)&slot, ((size_t)total + 1) * sizeof(int)));
+    {
+        int base = 0;
+        for (int c = 0; c < K; ++c) {
+            dist_round_mark_kernel<<<nblocks(total + 1), 256, 0, st>>>(first, total, c, 0, mark);
+            SG_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, mark, pos, (int)(total + 1), st));
+            int h_off[kMaxWorld + 1] = {0};
+            for (int p = 0; p <= W; ++p) SG_TRY(cudaMemcpyAsync(&h_off[p], pos + d->bounds[p], sizeof(int), cudaMemcpyDeviceToHost, st));
+            if (total > 0)
+                dist_round_fill_kernel<<<nblocks(total), 256, 0, st>>>(mark, pos, total, b, base, reinterpret_cast<int *>(d->base + d->off_req),
+                                                                     slot);
+            SG_TRY(cudaStreamSynchronize(st));
+            for (int p = 0; p <= W; ++p) d->recv_tab[c][p] = base + h_off[p];
+            base += h_off[W];
+        }
+        if (base != (int)d->num_recv) SG_FAIL(GNNAGG_ERR_STATE, "gnnagg_dist_set_graph: internal error (receive slots do not add up)");
+        SG_TRY(cudaMemcpyAsync(d->base + d->off_meta, d->recv_tab, sizeof d->recv_tab, cudaMemcpyHostToDevice, st));
+    }
     SG_TRY(cudaMalloc((void **)&idx_new, me * sizeof(int)));
     SG_TRY(cudaMalloc((void **)&keys, me * sizeof(int)));
-    if (m > 0) dist_reindex_kernel<<<nblocks(m), 256, 0, st>>>(d_idx, m, pos, own_lo, own_hi, n, b, idx_new, keys);
+    if (m > 0) {
+        if (R == 0)
+            dist_reindex_slot_kernel<<<nblocks(m), 256, 0, st>>>(d_idx, m, slot, own_lo, own_hi, n, idx_new, keys);
+        else  // K = 1 here: the slot of a row is its rank among the marked ids, and edges carry the stage of their owner
+            dist_reindex_kernel<<<nblocks(m), 256, 0, st>>>(d_idx, m, pos, own_lo, own_hi, n, b, idx_new, keys);
+    }
     SG_TRY(cudaGetLastError());
     SG_TRY(cudaStreamSynchronize(st));
-    cudaFree(mark), cudaFree(pos), cudaFree(tmp);
-    mark = pos = nullptr;
+    cudaFree(mark), cudaFree(pos), cudaFree(tmp), cudaFree(first), cudaFree(slot);
+    mark = pos = first = slot = nullptr;
     tmp = nullptr;
     // sub-CSR per stage (stable split: CSR order inside a stage), then one ordinary aggregator per stage
-    int items = 0;
-    rc = build_item_rows_device(d_ptr, n, m, &item_row, &items, st);
-    if (rc == GNNAGG_OK)
-        rc = source_slices_build_device(d_ptr, idx_new, item_row, items, n, m, d->num_stages, 1, &d->sl_ptr, &d->sl_idx, &d->sl_perm,
-                                        d->sl_off, d->sl_cnt, st, keys);
+    rc = source_slices_build_device(d_ptr, idx_new, item_row, items, n, m, d->num_stages, 1, &d->sl_ptr, &d->sl_idx, &d->sl_perm,
+                                    d->sl_off, d->sl_cnt, st, keys);
     if (rc != GNNAGG_OK) {
         cleanup();
         free_graph(d);
@@ -653,7 +806,7 @@ int gnnagg_dist_set_graph(gnnagg_dist *d, const int *d_ptr, const int *d_idx, co
     SG_TRY(cudaGetLastError());
     SG_TRY(cudaStreamSynchronize(st));
     cleanup();
-    mark = pos = bad = idx_new = keys = item_row = nullptr;
+    mark = pos = bad = idx_new = keys = item_row = first = slot = nullptr;
     tmp = nullptr;
     cudaFree(d->sl_perm);  // only needed for the values
     d->sl_perm = nullptr;
@@ -667,10 +820,11 @@ int gnnagg_dist_set_graph(gnnagg_dist *d, const int *d_ptr, const int *d_idx, co
         }
     }
     d->num_e = num_e;
-    d->launches += 6 + 3 * d->num_stages;
+    d->launches += 8 + 3 * d->num_stages + 3 * K;
     d->connected = W == 1;
     return gnnagg_dist_prepare(d, d->feat_cap, stream);
 #undef SG_TRY
+#undef SG_FAIL
 }
 
 int gnnagg_dist_prepare(gnnagg_dist *d, int feat, void *stream)
@@ -699,12 +853,15 @@ int gnnagg_dist_info(const gnnagg_dist *d, int64_t *num_recv, int64_t *recv_coun
     if (!d) return set_error(GNNAGG_ERR_ARG, "gnnagg_dist_info: NULL handle");
     if (num_recv) *num_recv = d->num_recv;
     if (recv_counts)
-        for (int p = 0; p < d->world; ++p) recv_counts[p] = d->recv_off[p + 1] - d->recv_off[p];
+        for (int p = 0; p < d->world; ++p) recv_counts[p] = d->recv_cnt[p];
     if (num_stages) *num_stages = d->num_stages;
     if (stage_edges)
         for (int s = 0; s < d->num_stages; ++s) stage_edges[s] = d->sl_cnt[s];
     if (send_counts)
-        for (int p = 0; p < d->world; ++p) send_counts[p] = d->send_cnt[p];
+        for (int p = 0; p < d->world; ++p) {
+            send_counts[p] = 0;
+            for (int c = 0; c < d->rounds; ++c) send_counts[p] += d->send_cnt[p][c];
+        }
     return GNNAGG_OK;
 }
 
@@ -783,9 +940,12 @@ static int dist_run(gnnagg_dist *d, int buf, float *Y, const float *W, float *H,
     const float *xs = reinterpret_cast<const float *>(d->base + d->off_x[buf]);  // shard rows, then the receive slots
     HaloFlags *mine = flags_of(d->base);
     uint32_t epoch = d->epoch;
+    // arrived[] counts completed pushes: round c of epoch e raises it to (e - 1) * rounds + c + 1
+    uint32_t flag_base = 0;
     if (d->prof) DT_TRY(cudaEventRecord(d->t_m0, st));
     if (exchange) {
         epoch = ++d->epoch;
+        flag_base = (epoch - 1u) * (uint32_t)d->rounds;
         // owner side: wait until every receiver has consumed the previous epoch, then push, receiver by receiver
         halo_begin_kernel<<<1, 32, 0, st>>>(mine, d->rank, Wd, epoch);
         DT_TRY(cudaPeekAtLastError());
@@ -796,20 +956,23 @@ static int dist_run(gnnagg_dist *d, int buf, float *Y, const float *W, float *H,
         int shift = -1;
         for (int s = 0; s < 16; ++s)
             if ((1 << s) == F4) shift = s;
-        for (int k = 0; k < Wd - 1; ++k) {
-            const int q = (d->rank - 1 - k + 2 * Wd) % Wd;  // receiver q takes this owner as its k-th
-            const int64_t count4 = (int64_t)d->send_cnt[q] * F4;
-            // 2 CTAs per SM saturate the link; ranks sharing one device (tests) split that
-            int64_t grid = (count4 + 256 * 8 - 1) / (256 * 8);
-            const int64_t cap = d->same_device_ranks > 1 ? std::max(4, d->sm_count / (2 * d->same_device_ranks)) : 2 * d->sm_count;
-            grid = grid < 1 ? 1 : (grid > cap ? cap : grid);  // an empty push still raises the flag
-            float *dst = reinterpret_cast<float *>(d->peer_base[q] + d->peer_off_x[q][buf]) +
-                         ((size_t)d->peer_rows[q] + (size_t)d->peer_slot[q]) * feat_in;
-            halo_push_kernel<8><<<(unsigned)grid, 256, 0, d->comm>>>(reinterpret_cast<const float4 *>(xs), d->send_rows[q],
-                                                                   reinterpret_cast<float4 *>(dst), count4, F4, shift,
-                                                                   &mine->push_cnt[q], &flags_of(d->peer_base[q])->arrived[d->rank], epoch);
-            DT_TRY(cudaPeekAtLastError());
-            ++d->launches;
+        for (int c = 0; c < d->rounds; ++c) {
+            for (int k = 0; k < Wd - 1; ++k) {
+                const int q = (d->rank - 1 - k + 2 * Wd) % Wd;  // receiver q takes this owner as its k-th
+                const int64_t count4 = (int64_t)d->send_cnt[q][c] * F4;
+                // one light CTA per SM (two when the round is large) keeps the link busy; ranks sharing a device (tests) split that
+                int64_t grid = (count4 + 128 * 4 - 1) / (128 * 4);
+                const int64_t cap = d->same_device_ranks > 1 ? std::max(4, d->sm_count / (2 * d->same_device_ranks)) : 2 * d->sm_count;
+                grid = grid < 1 ? 1 : (grid > cap ? cap : grid);  // an empty push still raises the flag
+                float *dst = reinterpret_cast<float *>(d->peer_base[q] + d->peer_off_x[q][buf]) +
+                             ((size_t)d->peer_rows[q] + (size_t)d->peer_slot[q][c]) * feat_in;
+                halo_push_kernel<4><<<(unsigned)grid, 128, 0, d->comm>>>(
+                    reinterpret_cast<const float4 *>(xs), d->send_rows[q] ? d->send_rows[q] + d->send_off[q][c] : nullptr,
+                    reinterpret_cast<float4 *>(dst), count4, F4, shift, &mine->push_cnt[q], &flags_of(d->peer_base[q])->arrived[d->rank],
+                    flag_base + (uint32_t)c + 1u);
+                DT_TRY(cudaPeekAtLastError());
+                ++d->launches;
+            }
         }
         DT_TRY(cudaEventRecord(d->ev_done, d->comm));
         if (d->prof) DT_TRY(cudaEventRecord(d->t_c1, d->comm));
@@ -820,36 +983,56 @@ static int dist_run(gnnagg_dist *d, int buf, float *Y, const float *W, float *H,
     }
     float *agg_out = W ? d->ax : Y;
     const int fo = W ? feat_out : feat_in;
-    // receiver side: stage by stage, each behind the arrival of its owners
+    // receiver side.  Stage mode: stage by stage, each behind the arrival of its owners.  Row-pipelined mode: ONE stage,
+    // row chunk c behind the arrival of round c from every owner.  With a host destination the last stage is cut into
+    // row chunks in either mode, and every finished chunk is combined and sent on its way.
+    const uint32_t all_owners = exchange ? (((Wd >= 32 ? 0u : (1u << Wd)) - 1u) & ~(1u << d->rank)) : 0u;
     for (int s = 0; s < d->num_stages; ++s) {
-        if (exchange && d->stage_mask[s]) {
-            halo_wait_kernel<<<1, 32, 0, st>>>(mine, d->stage_mask[s], epoch);
+        const bool last = s == d->num_stages - 1;
+        const bool by_rounds = last && d->rounds > 1;
+        const bool by_chunks = last && host_out && d->rows >= 4096;
+        if (exchange && d->stage_mask[s] && !by_rounds) {
+            halo_wait_kernel<<<1, 32, 0, st>>>(mine, d->stage_mask[s], flag_base + 1u);
             DT_TRY(cudaPeekAtLastError());
             ++d->launches;
         }
-        if (host_out && s == d->num_stages - 1 && d->rows >= 4096) {
-            float *out_dev = W ? H : Y;
-            for (int c = 0; c < kHostChunks; ++c) {
-                const int r0 = (int)((int64_t)d->rows * c / kHostChunks), r1 = (int)((int64_t)d->rows * (c + 1) / kHostChunks);
-                if (r1 <= r0) continue;
-                if (int rc = gnnagg_gcn_run_rows(d->stage[s], xs, agg_out, feat_in, s > 0, r0, r1, st)) return rc;
-                if (W) {
-                    if (int rc = gnnagg_dense_nn(d->ax + (size_t)r0 * feat_in, W, H + (size_t)r0 * feat_out, r1 - r0, feat_out, feat_in, st))
-                        return rc;
-                    d->launches += 2;
-                }
-                DT_TRY(cudaEventRecord(d->chunk_done[c], st));
-                DT_TRY(cudaStreamWaitEvent(d->copy_stream, d->chunk_done[c], 0));
-                DT_TRY(cudaMemcpyAsync(host_out + (size_t)r0 * fo, out_dev + (size_t)r0 * fo, (size_t)(r1 - r0) * fo * sizeof(float),
-                                       cudaMemcpyDeviceToHost, d->copy_stream));
+        if (!by_rounds && !by_chunks) {
+            if (int rc = gnnagg_gcn_run_acc(d->stage[s], xs, agg_out, feat_in, s > 0, st)) return rc;
+            if (s == 0 && d->prof) DT_TRY(cudaEventRecord(d->t_m1, st));
+            continue;
+        }
+        const int chunks = by_rounds ? d->rounds : kHostChunks;
+        float *out_dev = W ? H : Y;
+        int copies = 0;
+        for (int c = 0; c < chunks; ++c) {
+            const int r0 = by_rounds ? d->chunk_rows[c] : (int)((int64_t)d->rows * c / chunks);
+            const int r1 = by_rounds ? d->chunk_rows[c + 1] : (int)((int64_t)d->rows * (c + 1) / chunks);
+            if (exchange && by_rounds) {
+                halo_wait_kernel<<<1, 32, 0, st>>>(mine, all_owners, flag_base + (uint32_t)c + 1u);
+                DT_TRY(cudaPeekAtLastError());
+                ++d->launches;
             }
+            if (r1 <= r0) continue;
+            if (int rc = gnnagg_gcn_run_rows(d->stage[s], xs, agg_out, feat_in, s > 0, r0, r1, st)) return rc;
+            if (!host_out) continue;
+            if (W) {
+                if (int rc = gnnagg_dense_nn(d->ax + (size_t)r0 * feat_in, W, H + (size_t)r0 * feat_out, r1 - r0, feat_out, feat_in, st))
+                    return rc;
+                d->launches += 2;
+            }
+            // copy-back events are a small ring: a chunk's event is re-recorded only after the copy stream has consumed it
+            cudaEvent_t ev = d->chunk_done[copies % 4];
+            DT_TRY(cudaEventRecord(ev, st));
+            DT_TRY(cudaStreamWaitEvent(d->copy_stream, ev, 0));
+            DT_TRY(cudaMemcpyAsync(host_out + (size_t)r0 * fo, out_dev + (size_t)r0 * fo, (size_t)(r1 - r0) * fo * sizeof(float),
+                                   cudaMemcpyDeviceToHost, d->copy_stream));
+            ++copies;
+        }
+        if (host_out) {
             DT_TRY(cudaEventRecord(d->copies_done, d->copy_stream));
             host_out = nullptr;  // done: nothing left for the tail below
             W = nullptr;
-            if (d->prof) DT_TRY(cudaEventRecord(d->t_m1, st));
-            continue;
         }
-        if (int rc = gnnagg_gcn_run_acc(d->stage[s], xs, agg_out, feat_in, s > 0, st)) return rc;
         if (s == 0 && d->prof) DT_TRY(cudaEventRecord(d->t_m1, st));
     }
     if (d->prof) DT_TRY(cudaEventRecord(d->t_m2, st));

@@ -503,31 +503,64 @@ class LocalDist:
         self.handles = []
 
 
-def peer_plan(idx, bounds, rank, remote_stages):
+def peer_plan(idx, bounds, rank, remote_stages, ptr=None):
     """numpy restatement of the index bookkeeping of gnnagg_dist_set_graph (csrc/dist.cu), for tests and for
-    reasoning about traffic without a GPU.  Returns a dict:
-      recv_rows   global ids of the distinct REMOTE sources of this block, ascending (= receive-slot order)
-      recv_off    [world+1] slot range of every owner inside recv_rows
+    reasoning about traffic without a GPU.  remote_stages = R > 0: stages by owner; 0: one pass; < 0: row pipelining
+    with K = -R edge-balanced row chunks (needs `ptr`).  Returns a dict:
+      recv_rows   global ids of the distinct REMOTE sources of this block in receive-slot order: ascending id, or --
+                  row-pipelined -- by the round (row chunk) that needs a row first, then ascending id
+      recv_tab    [rounds, world+1] first slot of every owner's rows of a round; recv_tab[c][world] = end of round c
       recv_local  recv_rows as local row numbers inside their owner's shard (the rows that owner pushes)
-      stage_of    [world] stage of every owner: R = 0 -> everything is stage 0 (one pass after all arrivals); else
-                  0 = this rank, 1..R = groups of the owners taken in the order rank+1, rank+2, ... (mod world)
+      stage_of    [world] stage of every owner: 0 = this rank (and everybody when R <= 0), 1..R = groups of the owners
+                  taken in the order rank+1, rank+2, ... (mod world)
       recv_order  the world-1 remote owners in the order their rows arrive (owner p pushes to p-1, p-2, ...)
+      chunk_rows  [rounds+1] row chunk boundaries
       idx_new     per edge: local row of the own shard, or rows_own + receive slot (one buffer: shard, then slots)
       stage       per edge: its stage"""
     bounds = np.asarray(bounds, np.int64)
     W = len(bounds) - 1
     g = np.asarray(idx, np.int64)
     own_lo, own_hi = int(bounds[rank]), int(bounds[rank + 1])
+    rows_own = own_hi - own_lo
     remote = (g < own_lo) | (g >= own_hi)
-    U = np.unique(g[remote])
-    owner_u = np.searchsorted(bounds, U, side="right") - 1
     R = 0 if W == 1 else max(0, min(int(remote_stages), W - 1))
+    K = 1 if (W == 1 or remote_stages >= 0) else min(-int(remote_stages), 16)
+    chunk_rows = np.array([0] + [rows_own] * K, np.int64)
+    U = np.unique(g[remote])
+    first = np.zeros(len(U), np.int64)
+    if K > 1:
+        ptr = np.asarray(ptr, np.int64)
+        m = int(ptr[-1])
+        for c in range(1, K):
+            chunk_rows[c] = max(min(int(np.searchsorted(ptr, (m * c) // K, side="left")), rows_own), chunk_rows[c - 1])
+        row = np.repeat(np.arange(rows_own), np.diff(ptr))
+        chunk_e = np.searchsorted(chunk_rows[1:K], row, side="right")          # chunk of every edge's row
+        first = np.full(len(U), K, np.int64)
+        np.minimum.at(first, np.searchsorted(U, g[remote]), chunk_e[remote])
+        order_u = np.lexsort((U, first))                                         # by round, then id
+        U, first = U[order_u], first[order_u]
+    owner_u = np.searchsorted(bounds, U, side="right") - 1
+    recv_tab = np.zeros((K, W + 1), np.int64)
+    for c in range(K):
+        lo = int(np.searchsorted(first, c, side="left")) if K > 1 else 0
+        sel = U[first == c] if K > 1 else U
+        recv_tab[c] = lo + np.searchsorted(sel, bounds, side="left")
     order = [(rank + 1 + k) % W for k in range(W - 1)]
     stage_of = np.zeros(W, np.int64)
     for k, p in enumerate(order):
         stage_of[p] = 0 if R == 0 else 1 + (k * R) // (W - 1)
     owner_e = np.clip(np.searchsorted(bounds, g, side="right") - 1, 0, W - 1)
-    return {"recv_rows": U, "recv_off": np.searchsorted(U, bounds, side="left"), "recv_local": U - bounds[owner_u],
-            "stage_of": stage_of, "recv_order": order, "num_stages": 1 + R,
-            "idx_new": np.where(remote, (own_hi - own_lo) + np.searchsorted(U, g), g - own_lo).astype(np.int32),
+    slot_of = np.empty(len(U), np.int64)
+    by_id = np.argsort(U, kind="stable")
+    slot_of[:] = 0
+    slots_sorted = np.empty(len(U), np.int64)
+    slots_sorted[:] = by_id                                                      # U[by_id] ascending -> slot = by_id
+    Us = U[by_id]
+    e_slot = slots_sorted[np.searchsorted(Us, g[remote])] if remote.any() else np.zeros(0, np.int64)
+    idx_new = (g - own_lo).astype(np.int64)
+    idx_new[remote] = rows_own + e_slot
+    counts = np.bincount(owner_u, minlength=W) if len(U) else np.zeros(W, np.int64)
+    return {"recv_rows": U, "recv_tab": recv_tab, "recv_off": recv_tab[0] if K == 1 else None, "recv_counts": counts,
+            "recv_local": U - bounds[owner_u], "stage_of": stage_of, "recv_order": order, "num_stages": 1 + R, "rounds": K,
+            "chunk_rows": chunk_rows, "idx_new": idx_new.astype(np.int32),
             "stage": np.where(remote, stage_of[owner_e], 0).astype(np.int32)}

@@ -304,10 +304,15 @@ int gnnagg_validate_reordered(const float *d_ref, const float *d_ans, const int 
  *   5. teardown all ranks idle -> gnnagg_dist_disconnect on every rank -> (barrier) -> gnnagg_dist_destroy
  * A step: every OWNER pushes the rows each peer wants from its shard straight into that peer's receive slots with
  * 128-bit stores over NVLink (local gathers, posted remote writes, contiguous destination; owner p serves receivers
- * p-1, p-2, ... so each receiver is written by one owner at a time); the receiver aggregates stage 0 (edges with
- * local sources) meanwhile and one accumulating stage per group of owners as it lands.  remote_stages = 0: a single
- * pass after all arrivals (no extra pass over Y; for short rows).  Deterministic: no atomics, a fixed summation order
- * per (world, remote_stages).  No NCCL, no pack buffer.
+ * p-1, p-2, ... so each receiver is written by one owner at a time).  What the receiver overlaps with the pushes
+ * depends on `remote_stages`:
+ *    R > 0  stages by OWNER: stage 0 (edges with local sources) at once, then one accumulating stage per group of owners
+ *           as it lands -- for long rows (reddit-shape: 490 edges per row), where R extra passes over Y cost little;
+ *    R = 0  a single pass after all arrivals;
+ *    R < 0  ROW pipelining with K = -R (<= 16) edge-balanced row chunks: receive slots are ordered by the chunk that
+ *           needs a row first, the owners push round by round and chunk c -- a row range of the ONE CSR, no extra pass
+ *           over Y -- starts when round c has landed.  For short rows (R-MAT: 16 edges per row).
+ * Deterministic: no atomics, a fixed summation order per (world, remote_stages).  No NCCL, no pack buffer.
  * ------------------------------------------------------------------------------------------ */
 #define GNNAGG_DIST_MAX_WORLD 16
 #define GNNAGG_DIST_BLOB_BYTES 256
@@ -317,7 +322,8 @@ int gnnagg_dist_create(int world, const int *devices /* NULL: 0..world-1 */, con
                        int feat_cap, gnnagg_dist **out /* [world] */);
 int gnnagg_dist_create_rank(int rank, int world, const int64_t *shard_bounds, int feat_cap, gnnagg_dist **out);
 /* the rank's row block (borrowed only during the call: the library keeps its own re-indexed per-stage CSRs);
- * synchronises `stream`.  remote_stages in [0, world-1].  Once per handle. */
+ * synchronises `stream`.  remote_stages: see above (clamped to world-1 / 16 chunks).  Once per handle; all ranks of a
+ * group must use the same value. */
 int gnnagg_dist_set_graph(gnnagg_dist *d, const int *d_ptr, const int *d_idx, const float *d_val, int64_t num_e,
                           int remote_stages, void *stream);
 int gnnagg_dist_export(gnnagg_dist *d, void *blob /* GNNAGG_DIST_BLOB_BYTES */);

@@ -24,6 +24,7 @@
 #include <iostream>
 #include <sstream>
 #include <string>
+#include <algorithm>
 #include <vector>
 
 #include "dbg.h"
@@ -101,48 +102,72 @@ static inline unsigned int roundUp(unsigned int nominator, unsigned int denomina
     return (nominator + denominator - 1) / denominator;
 }
 
+// ---- allocation helpers of the reference API (util.h:144-195 there): same names and behaviour, bodies written
+// against two small primitives of this shim (rounded allocation, upload of a host range)
+namespace gnnagg_compat {
+constexpr size_t kAllocQuantum = 512;  // the reference rounds every device allocation up to 512 bytes
+
+inline cudaError_t alloc_rounded(void **out, size_t bytes)
+{
+    const size_t quanta = (bytes + kAllocQuantum - 1) / kAllocQuantum;
+    return cudaMalloc(out, quanta * kAllocQuantum);
+}
+
+// device copy of host[0, count): one rounded allocation + one blocking H2D copy, aborting like the reference on failure
+template <class T>
+inline T *upload(const T *host, size_t count)
+{
+    void *dev = NULL;
+    const size_t bytes = count * sizeof(T);
+    if (bytes != 0) {
+        total_size += (int)bytes;
+        expect_cuda((long)alloc_rounded(&dev, bytes), __FILE__, __LINE__);
+        expect_cuda((long)cudaMemcpy(dev, host, bytes, cudaMemcpyHostToDevice), __FILE__, __LINE__);
+    }
+    return static_cast<T *>(dev);
+}
+
+inline bool externally_owned(const void *p)
+{
+    return std::find(registered_ptr.begin(), registered_ptr.end(), const_cast<void *>(p)) != registered_ptr.end();
+}
+}  // namespace gnnagg_compat
+
 inline cudaError_t cudaMalloc2(void **a, size_t s)
 {
-    if (s == 0) return cudaSuccess;
+    if (s == 0) return cudaSuccess;  // pointer left untouched, as in the reference
     total_size += (int)s;
-    return cudaMalloc(a, ((s + 511) / 512) * 512);
+    return gnnagg_compat::alloc_rounded(a, s);
 }
 
 template <class T>
 inline void registerPtr(T ptr)
 {
-    registered_ptr.push_back((void *)(ptr));
+    registered_ptr.push_back(reinterpret_cast<void *>(ptr));
 }
 
-// frees a device pointer unless it was registered as externally owned
+// releases a device pointer the aggregator owns; pointers announced through registerPtr stay with their owner
 template <class T>
 void safeFree(T *&a)
 {
-    for (void *item : registered_ptr)
-        if ((void *)a == item) return;
-    if (a != NULL) {
-        cudaFree(a);
-        cudaGetLastError();
-        a = NULL;
-    }
+    if (a == NULL || gnnagg_compat::externally_owned(a)) return;
+    cudaFree(a);
+    cudaGetLastError();  // a stale pointer must not poison later launches
+    a = NULL;
 }
 
 template <class T>
 T *createCopy(T *p, int size)
 {
-    T *p_d = NULL;
-    checkCudaErrors(cudaMalloc2((void **)&p_d, size * sizeof(T)));
-    checkCudaErrors(cudaMemcpy(p_d, p, sizeof(T) * size, cudaMemcpyHostToDevice));
-    return p_d;
+    return gnnagg_compat::upload(p, (size_t)size);
 }
 
 template <class T>
 void copyVec2Dev(std::vector<T> *vec, T *&output)
 {
     assert(output == NULL);
-    checkCudaErrors(cudaMalloc2((void **)&output, vec->size() * sizeof(T)));
-    checkCudaErrors(cudaMemcpy(output, vec->data(), vec->size() * sizeof(T), cudaMemcpyHostToDevice));
-    vector<T>().swap(*vec);
+    output = gnnagg_compat::upload(vec->data(), vec->size());
+    std::vector<T>().swap(*vec);  // the host vector gives its storage back
 }
 
 struct CSR {

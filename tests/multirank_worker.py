@@ -45,7 +45,7 @@ def main():
         single = gnnagg.Aggregator(ptr, idx, val)
         Y1 = single.gcn_run(X, torch.empty((n, F), device=dev))
         torch.cuda.synchronize()
-    for stages in sorted({0, 1, 2, world - 1}):
+    for stages in sorted({-8, -3, 0, 1, 2, world - 1}):
         ph = PeerHalo(lptr, lidx, lval, bounds, rank, world, F, remote_stages=stages)
         ph.x(0, F).copy_(X[r0:r1])
         Y = torch.empty((r1 - r0, F), device=dev)

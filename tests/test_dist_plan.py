@@ -18,7 +18,7 @@ def _stage_csr(ptr, plan, val, s):
     return p, np.ascontiguousarray(plan["idx_new"][sel]), np.ascontiguousarray(val[sel])
 
 
-@pytest.mark.parametrize("world,stages", [(1, 1), (2, 0), (2, 1), (3, 1), (3, 2), (4, 0), (4, 3), (8, 2), (8, 7)])
+@pytest.mark.parametrize("world,stages", [(1, 1), (2, 0), (2, 1), (3, 1), (3, 2), (4, 0), (4, 3), (8, 2), (8, 7), (2, -3), (4, -4), (8, -16)])
 def test_staged_plan_reproduces_the_full_aggregation(orc, world, stages):
     rng = np.random.default_rng(world * 10 + stages)
     sizes = rng.integers(20, 60, world)
@@ -32,20 +32,30 @@ def test_staged_plan_reproduces_the_full_aggregation(orc, world, stages):
     for rank in range(world):
         lp, li, lv = partition.local_block(ptr, idx, val, bounds, rank)
         rows = len(lp) - 1
-        plan = partition.peer_plan(li, bounds, rank, stages)
-        assert plan["num_stages"] == (1 if world == 1 else 1 + min(stages, world - 1))
+        plan = partition.peer_plan(li, bounds, rank, stages, ptr=lp)
+        assert plan["num_stages"] == (1 if world == 1 else 1 + max(0, min(stages, world - 1)))
         assert sorted(plan["recv_order"]) == [p for p in range(world) if p != rank]
         # the receive slots: rows pushed by the owners out of their shards, owner by owner
         recv = np.zeros((len(plan["recv_rows"]), F), np.float32)
-        for p in range(world):
-            a, b = plan["recv_off"][p], plan["recv_off"][p + 1]
-            shard = X[bounds[p]:bounds[p + 1]]
-            recv[a:b] = shard[plan["recv_local"][a:b]]
-            assert p != rank or a == b                                  # own rows never travel
+        for c in range(plan["rounds"]):
+            for p in range(world):
+                a, b = plan["recv_tab"][c][p], plan["recv_tab"][c][p + 1]
+                shard = X[bounds[p]:bounds[p + 1]]
+                recv[a:b] = shard[plan["recv_local"][a:b]]
+                assert p != rank or a == b                              # own rows never travel
         assert np.array_equal(recv, X[plan["recv_rows"]])
+        if plan["rounds"] > 1:
+            # row pipelining: chunk c only gathers rows that arrived in rounds <= c
+            row = np.repeat(np.arange(rows), np.diff(lp))
+            chunk_e = np.searchsorted(plan["chunk_rows"][1:plan["rounds"]], row, side="right")
+            rem = plan["idx_new"] >= rows
+            limit = plan["recv_tab"][:, world][chunk_e[rem]]            # end of the round of the edge's chunk
+            assert np.all(plan["idx_new"][rem] - rows < limit)
+            cr = plan["chunk_rows"]
+            assert cr[0] == 0 and cr[-1] == rows and np.all(np.diff(cr) >= 0)
         # stages are monotone along the arrival order, every stage non-empty in owners
         st = [plan["stage_of"][p] for p in plan["recv_order"]]
-        assert st == sorted(st) and (world == 1 or stages == 0 or set(st) == set(range(1, plan["num_stages"])))
+        assert st == sorted(st) and (world == 1 or stages <= 0 or set(st) == set(range(1, plan["num_stages"])))
         acc = np.zeros((rows, F), np.float64)
         # ONE buffer serves every stage: the own shard, then the receive slots
         src = np.ascontiguousarray(np.concatenate([X[bounds[rank]:bounds[rank + 1]], recv])) if rows + len(recv) else np.zeros((1, F), np.float32)

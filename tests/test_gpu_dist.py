@@ -29,10 +29,10 @@ def _run_local(gn, cuda, ptr, idx, val, X, bounds, stages, layer_W=None, steps=1
         for r in range(world):
             lp, li, lv = partition.local_block(ptr, idx, val, bounds, r)
             ld.set_graph(r, torch.from_numpy(lp).to(cuda), torch.from_numpy(li).to(cuda), torch.from_numpy(lv).to(cuda), stages)
-            plan = partition.peer_plan(li, bounds, r, stages)
+            plan = partition.peer_plan(li, bounds, r, stages, ptr=lp)
             ph = ld.ranks[r]
             assert ph.num_recv == len(plan["recv_rows"])
-            assert ph.recv_counts == [int(plan["recv_off"][p + 1] - plan["recv_off"][p]) for p in range(world)]
+            assert ph.recv_counts == [int(c) for c in plan["recv_counts"]]
             assert ph.num_stages == plan["num_stages"]
             assert ph.stage_edges == [int((plan["stage"] == s).sum()) for s in range(plan["num_stages"])]
         ld.connect()
@@ -61,7 +61,7 @@ def _run_local(gn, cuda, ptr, idx, val, X, bounds, stages, layer_W=None, steps=1
     return outs
 
 
-@pytest.mark.parametrize("world,stages", [(1, 1), (2, 0), (2, 1), (3, 1), (3, 2), (4, 0), (4, 3)])
+@pytest.mark.parametrize("world,stages", [(1, 1), (2, 0), (2, 1), (3, 1), (3, 2), (4, 0), (4, 3), (2, -4), (3, -16), (4, -3)])
 @pytest.mark.parametrize("F", [32, 64, 128, 100])
 def test_local_ranks_match_oracle(gn, orc, cuda, world, stages, F):
     rng = np.random.default_rng(world * 100 + stages * 10 + F)
