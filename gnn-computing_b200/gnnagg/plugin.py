@@ -102,3 +102,69 @@ def gat_schedule(at, neighbor_num):
 
 def destroy(at):
     _registry.pop(int(at)).close()
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd: the aggregations as differentiable torch ops (the reference's our.py trains nothing -- it times forward
+# passes, Figure7/our.py:247-290 -- but its kernel set includes an experimental backward, aggr_gat_fine_bwd,
+# include/aggr_gat.h:222-294; these tie the forward entry points to gnnagg_gcn_backward / gnnagg_gat_backward).
+# ------------------------------------------------------------------------------------------------
+def _transposed(agg, num_src):
+    if getattr(agg, "num_src", None) != num_src:
+        agg.transpose_build(num_src)
+    return agg
+
+
+class GCNAggregate(torch.autograd.Function):
+    """Y = A X for the aggregator `at` (edge values are constants of the graph).  backward: dX = A^T dY through the
+    GPU-built transposed CSR (deterministic gather, no atomics)."""
+
+    @staticmethod
+    def forward(ctx, at, X, scheduled=False):
+        agg = _get(at)
+        X = X.contiguous()
+        _check(X)
+        Y = torch.empty((agg.n, X.shape[1]), device=X.device, dtype=torch.float32)
+        agg.gcn_run(X, Y, bool(scheduled))
+        ctx.at, ctx.num_src = at, X.shape[0]
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        agg = _transposed(_get(ctx.at), ctx.num_src)
+        dX = torch.empty((ctx.num_src, dY.shape[1]), device=dY.device, dtype=torch.float32)
+        agg.gcn_backward(dY.contiguous(), dX)
+        return None, dX, None
+
+
+class GATAggregate(torch.autograd.Function):
+    """Y = fused GAT aggregation of X with the attention table att [n, 2] (destination term, source term), slope 0.2
+    as in the reference (aggr_gat.h:339).  backward: full gradient w.r.t. X and att."""
+
+    @staticmethod
+    def forward(ctx, at, X, att, slope=0.2):
+        agg = _get(at)
+        X, att = X.contiguous(), att.contiguous()
+        _check(X, att)
+        Y = torch.empty((agg.n, X.shape[1]), device=X.device, dtype=torch.float32)
+        agg.gat_run(X, att, Y, slope, False)
+        ctx.at, ctx.slope = at, slope
+        ctx.save_for_backward(X, att, Y)
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        X, att, Y = ctx.saved_tensors
+        agg = _transposed(_get(ctx.at), X.shape[0])
+        dX = torch.empty_like(X)
+        datt = torch.empty((max(agg.n, X.shape[0]), 2), device=X.device, dtype=torch.float32)
+        agg.gat_backward(X, att, Y, dY.contiguous(), dX, datt, ctx.slope)
+        return None, dX, datt[: att.shape[0]], None
+
+
+def gcn_aggregate(at, X, scheduled=False):
+    return GCNAggregate.apply(at, X, scheduled)
+
+
+def gat_aggregate(at, X, att, slope=0.2):
+    return GATAggregate.apply(at, X, att, slope)

@@ -92,3 +92,40 @@ def test_plugin_input_checks(gnc, cuda):
     x = torch.randn(gnc.n, 64, device=cuda)
     with pytest.raises(Exception):
         gnc.gcn_run(at, x.t()[:32].t(), torch.empty(gnc.n, 32, device=cuda), 128, 0)  # CHECK_CONTIGUOUS
+
+
+def test_autograd_functions_match_the_oracle_gradients(gnc, orc, cuda):
+    """gnc.gcn_aggregate / gnc.gat_aggregate under torch.autograd: forward against the fp64 oracle, backward against
+    the oracle's A^T dY and full GAT derivative (oracle pinned by finite differences in tests/test_backward.py)"""
+    from gnnagg import synth
+
+    ptr, idx = synth.small_random_csr(900, 12.0, 31, hub=3000)
+    rng = np.random.default_rng(4)
+    n, F = len(ptr) - 1, 32
+    val = (rng.random(len(idx)).astype(np.float32) + 0.1)
+    X = rng.standard_normal((n, F)).astype(np.float32)
+    att = rng.standard_normal((n, 2)).astype(np.float32)
+    dY = rng.standard_normal((n, F)).astype(np.float32)
+    dptr, didx, dval = (torch.from_numpy(a).to(cuda) for a in (ptr, idx, val))
+    at = gnc.gcn_init(dptr, didx, dval)
+    Xt = torch.from_numpy(X).to(cuda).requires_grad_(True)
+    Y = gnc.gcn_aggregate(at, Xt)
+    Y.backward(torch.from_numpy(dY).to(cuda))
+    y64, scale = orc.spmm_f64(ptr, idx, val, X)
+    assert rel_gate(Y.detach().cpu().numpy(), y64, scale, 1e-5)[0] == 0
+    dx64, dscale = orc.spmm_t_f64(ptr, idx, val, dY, n)
+    assert rel_gate(Xt.grad.cpu().numpy(), dx64, dscale, 1e-5)[0] == 0
+
+    at_gat = gnc.gat_init(dptr, didx)
+    Xg = torch.from_numpy(X).to(cuda).requires_grad_(True)
+    ag = torch.from_numpy(att).to(cuda).requires_grad_(True)
+    Yg = gnc.gat_aggregate(at_gat, Xg, ag)
+    Yg.backward(torch.from_numpy(dY).to(cuda))
+    g64, _, gs = orc.gat_f64(ptr, idx, att, X)
+    assert rel_gate(Yg.detach().cpu().numpy(), g64, gs, 1.2e-5)[0] == 0
+    ref = orc.gat_backward_f64(ptr, idx, att, X, dY)
+    dX64, datt64 = ref[0], ref[1]
+    assert np.abs(Xg.grad.cpu().numpy() - dX64).max() <= 5e-5 * max(1.0, np.abs(dX64).max())
+    assert np.abs(ag.grad.cpu().numpy() - datt64).max() <= 1e-4 * max(1.0, np.abs(datt64).max())
+    gnc.destroy(at)
+    gnc.destroy(at_gat)
