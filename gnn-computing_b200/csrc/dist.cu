@@ -31,6 +31,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -162,6 +163,88 @@ __global__ void __launch_bounds__(128, 16) halo_push_kernel(const float4 *__rest
         const uint32_t before = atomicAdd(done_cnt, 1u);
         if (before == gridDim.x - 1) {
             atomicExch(done_cnt, 0u);  // ready for the next launch towards this receiver (stream-ordered after this one)
+            __threadfence_system();
+            st_release_sys(arrived_flag, value);
+        }
+    }
+}
+
+// The same push with the rows STAGED THROUGH SHARED MEMORY BY THE TMA ENGINE: one warp per CTA keeps a ring of kPushBufs
+// batches (<= 8 KB each) in flight -- every lane issues one 1-D bulk copy (cp.async.bulk, global -> shared) for one
+// wanted row onto the batch's mbarrier; when the batch has landed ONE bulk copy (shared -> global) writes it to the
+// receiver's contiguous slots over NVLink.  32 threads, ~20 registers and kPushBufs x 8 KB of shared memory per CTA: it
+// runs in what the aggregation CTAs leave free on an SM, and its bytes in flight are bounded by shared memory instead of
+// registers -- the register version above slows down by a third as soon as the aggregation kernel saturates the
+// memory system next to it (387 instead of 615 GB/s on the RMAT-26 exchange), because 4 loads per thread no longer
+// cover the loaded latency.
+constexpr int kPushBufs = 6;        // ring depth
+constexpr int kPushAhead = 4;       // batches of loads in flight per warp
+constexpr int kPushBatchBytes = 8192;
+
+__device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__global__ void __launch_bounds__(32) halo_push_tma_kernel(const float *__restrict__ X, const int *__restrict__ rows,
+                                                           float *__restrict__ dst, int64_t count, int F, int rows_per_batch,
+                                                           uint32_t *done_cnt, uint32_t *arrived_flag, uint32_t value)
+{
+    extern __shared__ __align__(128) uint8_t push_smem[];
+    __shared__ __align__(8) uint64_t bars[kPushBufs];
+    const int lane = threadIdx.x;
+    const uint32_t row_bytes = (uint32_t)F * 4u;
+    const int64_t batches = (count + rows_per_batch - 1) / rows_per_batch;
+    const int64_t mine = batches > blockIdx.x ? (batches - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;  // batches of this warp
+    if (lane == 0) {
+        for (int i = 0; i < kPushBufs; ++i) mbar_init(smem_u32(&bars[i]), 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    // loads of this warp's j-th batch into ring slot j % kPushBufs
+    auto issue = [&](int64_t j) {
+        const int buf = (int)(j % kPushBufs);
+        const int64_t r0 = (blockIdx.x + j * gridDim.x) * rows_per_batch;
+        const int nr = (int)min((int64_t)rows_per_batch, count - r0);
+        const uint32_t bar = smem_u32(&bars[buf]);
+        if (lane == 0) mbar_expect_tx(bar, (uint32_t)nr * row_bytes);
+        __syncwarp();
+        if (lane < nr)
+            bulk_g2s(smem_u32(push_smem) + (uint32_t)buf * kPushBatchBytes + (uint32_t)lane * row_bytes,
+                     X + (size_t)__ldg(rows + r0 + lane) * F, row_bytes, bar);
+    };
+    for (int64_t j = 0; j < kPushAhead && j < mine; ++j) issue(j);
+    for (int64_t it = 0; it < mine; ++it) {
+        if (it + kPushAhead < mine) {
+            // slot (it + kPushAhead) % kPushBufs was last stored from kPushBufs - kPushAhead iterations ago: that bulk store
+            // must have finished READING shared memory (not the remote write) before the TMA overwrites it
+            if (lane == 0) bulk_wait_read<kPushBufs - kPushAhead - 1>();
+            __syncwarp();
+            issue(it + kPushAhead);
+        }
+        const int buf = (int)(it % kPushBufs);
+        mbar_wait(smem_u32(&bars[buf]), (uint32_t)((it / kPushBufs) & 1));
+        if (lane == 0) {
+            const int64_t r0 = (blockIdx.x + it * gridDim.x) * rows_per_batch;
+            const int nr = (int)min((int64_t)rows_per_batch, count - r0);
+            bulk_s2g(dst + (size_t)r0 * F, smem_u32(push_smem) + (uint32_t)buf * kPushBatchBytes, (uint32_t)nr * row_bytes);
+            bulk_commit();
+        }
+    }
+    if (lane == 0) {
+        bulk_wait_all();  // every bulk store of this warp has been performed
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __threadfence_system();
+        const uint32_t before = atomicAdd(done_cnt, 1u);
+        if (before == gridDim.x - 1) {
+            atomicExch(done_cnt, 0u);
             __threadfence_system();
             st_release_sys(arrived_flag, value);
         }
@@ -368,6 +451,7 @@ struct gnnagg_dist {
     uint32_t epoch = 0;
     int sm_count = 148;
     int prepared_feat = 0;
+    int push_tma = 1;           // 1: rows staged through shared memory by bulk copies (halo_push_tma_kernel); 0: register version
     int same_device_ranks = 1;  // ranks (including this one) living on this rank's device: > 1 only in single-GPU tests
     int64_t launches = 0;
 };
@@ -445,6 +529,10 @@ int gnnagg_dist_create_rank(int rank, int world, const int64_t *shard_bounds, in
         if (cudaFuncGetAttributes(&attr, halo_wait_kernel) != cudaSuccess) cudaGetLastError();
         if (cudaFuncGetAttributes(&attr, halo_consumed_kernel) != cudaSuccess) cudaGetLastError();
         if (cudaFuncGetAttributes(&attr, halo_push_kernel<4>) != cudaSuccess) cudaGetLastError();
+        if (cudaFuncGetAttributes(&attr, halo_push_tma_kernel) != cudaSuccess) cudaGetLastError();
+        if (cudaFuncSetAttribute(halo_push_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPushBufs * kPushBatchBytes) != cudaSuccess)
+            cudaGetLastError();
+        if (const char *env = getenv("GNNAGG_PUSH_TMA")) d->push_tma = atoi(env) != 0;
         dense_preload();
     }
     *out = d;
@@ -966,10 +1054,21 @@ static int dist_run(gnnagg_dist *d, int buf, float *Y, const float *W, float *H,
                 grid = grid < 1 ? 1 : (grid > cap ? cap : grid);  // an empty push still raises the flag
                 float *dst = reinterpret_cast<float *>(d->peer_base[q] + d->peer_off_x[q][buf]) +
                              ((size_t)d->peer_rows[q] + (size_t)d->peer_slot[q][c]) * feat_in;
-                halo_push_kernel<4><<<(unsigned)grid, 128, 0, d->comm>>>(
-                    reinterpret_cast<const float4 *>(xs), d->send_rows[q] ? d->send_rows[q] + d->send_off[q][c] : nullptr,
-                    reinterpret_cast<float4 *>(dst), count4, F4, shift, &mine->push_cnt[q], &flags_of(d->peer_base[q])->arrived[d->rank],
-                    flag_base + (uint32_t)c + 1u);
+                const int *list = d->send_rows[q] ? d->send_rows[q] + d->send_off[q][c] : nullptr;
+                uint32_t *flag = &flags_of(d->peer_base[q])->arrived[d->rank];
+                if (d->push_tma && feat_in * 4 <= kPushBatchBytes) {
+                    int rpb = kPushBatchBytes / (feat_in * 4);
+                    rpb = rpb > 32 ? 32 : rpb;
+                    int64_t g2 = (d->send_cnt[q][c] + rpb - 1) / rpb;
+                    const int64_t cap2 = d->same_device_ranks > 1 ? std::max(4, d->sm_count / (2 * d->same_device_ranks)) : 2 * d->sm_count;
+                    g2 = g2 < 1 ? 1 : (g2 > cap2 ? cap2 : g2);
+                    halo_push_tma_kernel<<<(unsigned)g2, 32, kPushBufs * kPushBatchBytes, d->comm>>>(
+                        xs, list, dst, d->send_cnt[q][c], feat_in, rpb, &mine->push_cnt[q], flag, flag_base + (uint32_t)c + 1u);
+                } else {
+                    halo_push_kernel<4><<<(unsigned)grid, 128, 0, d->comm>>>(reinterpret_cast<const float4 *>(xs), list,
+                                                                           reinterpret_cast<float4 *>(dst), count4, F4, shift,
+                                                                           &mine->push_cnt[q], flag, flag_base + (uint32_t)c + 1u);
+                }
                 DT_TRY(cudaPeekAtLastError());
                 ++d->launches;
             }
