@@ -169,14 +169,15 @@ __global__ void __launch_bounds__(128, 16) halo_push_kernel(const float4 *__rest
     }
 }
 
-// The same push with the rows STAGED THROUGH SHARED MEMORY BY THE TMA ENGINE: one warp per CTA keeps a ring of kPushBufs
-// batches (<= 8 KB each) in flight -- every lane issues one 1-D bulk copy (cp.async.bulk, global -> shared) for one
-// wanted row onto the batch's mbarrier; when the batch has landed ONE bulk copy (shared -> global) writes it to the
-// receiver's contiguous slots over NVLink.  32 threads, ~20 registers and kPushBufs x 8 KB of shared memory per CTA: it
-// runs in what the aggregation CTAs leave free on an SM, and its bytes in flight are bounded by shared memory instead of
-// registers -- the register version above slows down by a third as soon as the aggregation kernel saturates the
-// memory system next to it (387 instead of 615 GB/s on the RMAT-26 exchange), because 4 loads per thread no longer
-// cover the loaded latency.
+// EXPERIMENT, off by default (GNNAGG_PUSH_TMA=1 selects it): the same push with the rows STAGED THROUGH SHARED MEMORY BY
+// THE TMA ENGINE.  One warp per CTA keeps a ring of kPushBufs batches (<= 8 KB each) in flight -- every lane issues one
+// 1-D bulk copy (cp.async.bulk, global -> shared) for one wanted row onto the batch's mbarrier; when the batch has
+// landed ONE bulk copy (shared -> global) writes it to the receiver's contiguous slots over NVLink.  32 threads, 28
+// registers, bytes in flight bounded by shared memory instead of registers.  Measured on 8 B200s it LOSES to the register
+// version (profiles/r2_sweep_n8_push_v3_tma.jsonl vs r2_sweep_n8_push_v2_light.jsonl: reddit-shape step 4.20 vs 3.48 ms,
+// RMAT-26 exchange alone 569 vs 615 GB/s): its 48 KB of shared memory per CTA changes the SM's L1 / shared-memory
+// split, and the SM drains before kernels with different splits can share it -- the push stops running BESIDE the
+// aggregation, which was the point.  Kept selectable as the evidence for that conclusion.
 constexpr int kPushBufs = 6;        // ring depth
 constexpr int kPushAhead = 4;       // batches of loads in flight per warp
 constexpr int kPushBatchBytes = 8192;
@@ -451,7 +452,7 @@ struct gnnagg_dist {
     uint32_t epoch = 0;
     int sm_count = 148;
     int prepared_feat = 0;
-    int push_tma = 1;           // 1: rows staged through shared memory by bulk copies (halo_push_tma_kernel); 0: register version
+    int push_tma = 0;           // 1: rows staged through shared memory by bulk copies (halo_push_tma_kernel); 0: register version
     int same_device_ranks = 1;  // ranks (including this one) living on this rank's device: > 1 only in single-GPU tests
     int64_t launches = 0;
 };
