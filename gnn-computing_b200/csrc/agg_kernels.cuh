@@ -50,6 +50,8 @@ struct AggParams {
     int bulk_ok;                         // idx/val 16-byte aligned -> TMA staging allowed
     int num_fine_items;                  // entries of item_row
     int accumulate;                      // GCN un-scheduled: Y += A*X instead of Y = A*X
+    const int *__restrict__ out_row;     // un-scheduled GCN over a COMPACTED sub-CSR (locality slices): row r of the CSR is
+                                         // output row out_row[r]; NULL: identity.  Every output row occurs at most once.
     // row-range launch (un-scheduled only): rows [row_lo, row_hi) = edges [edge_lo, edge_hi); the whole graph is
     // (0, num_rows, 0, num_edges).  Items keep their global numbering, a range just clips them.
     int row_lo, row_hi, edge_lo, edge_hi;
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
                 if (MODE == kModeGAT && vl == 0 && cb == 0) p.carry_den[item] = den;
                 carry_in = false;
             } else {
-                float *y = p.Y + (size_t)row * F + col;
+                float *y = p.Y + (size_t)((MODE == kModeGCN && p.out_row) ? __ldg(p.out_row + row) : row) * F + col;
                 if (MODE == kModeGAT) {
                     // complete row: normalise here (aggr_gat.h:163); empty row -> 0 (documented)
                     const float inv = (den != 0.f) ? __fdividef(1.f, den) : 0.f;
@@ -422,7 +424,8 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
             if (act1) stg_f4(c + LPR * 4, acc1);
             if (MODE == kModeGAT && vl == 0 && cb == 0) p.carry_den[item] = den;
         } else {
-            float *y = p.Y + (size_t)row * F + col;  // row starts here and continues: raw partial
+            // row starts here and continues: raw partial
+            float *y = p.Y + (size_t)((MODE == kModeGCN && p.out_row) ? __ldg(p.out_row + row) : row) * F + col;
             if (MODE == kModeGCN && p.accumulate) {
                 if (act0) acc0 = add4(acc0, *reinterpret_cast<const float4 *>(y));
                 if (act1) acc1 = add4(acc1, *reinterpret_cast<const float4 *>(y + LPR * 4));
@@ -468,7 +471,7 @@ __device__ __forceinline__ void fixup_sum(const AggParams &p, int row, int64_t i
         }
         for (; b <= b1; b += step) acc = add4(acc, *reinterpret_cast<const float4 *>(p.carry + (size_t)b * F + col));
         if (finish) {
-            float *y = p.Y + (size_t)row * F + col;
+            float *y = p.Y + (size_t)((MODE == kModeGCN && p.out_row) ? __ldg(p.out_row + row) : row) * F + col;
             acc = add4(*reinterpret_cast<const float4 *>(y), acc);
             if (MODE == kModeGAT) acc = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
             stg_f4(y, acc);

@@ -130,6 +130,8 @@ struct gnnagg_aggregator {
     // `loc` borrows this aggregator's CSR and owns the slices.
     int loc_slices = 0;  // 0 = automatic, 1 = off, 2..kMaxSlices forced
     gnnagg_aggregator *loc = nullptr;
+    // a slice compacted to its non-empty rows: d_ptr = c_ptr (owned), row r of it is output row out_row[r] (owned)
+    int *c_ptr = nullptr, *out_row = nullptr;
     cudaStream_t in_stream = nullptr;
     cudaEvent_t in_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t in_free = nullptr;
@@ -388,6 +390,7 @@ static int gcn_run_core(gnnagg_aggregator *a, const float *X, float *Y, int F, i
     if (int rc = ensure(a->carry, a->carry_cap, (size_t)cdiv(a->m, EB) * F)) return rc;
     p.num_fine_items = a->num_items;
     p.accumulate = accumulate;
+    p.out_row = a->out_row;
     p.ptr = a->d_ptr;
     p.idx = a->d_idx;
     p.val = a->d_val;
@@ -546,7 +549,7 @@ static int mlp_run_core(gnnagg_aggregator *a, const float *P, float *Y, int F, i
 static void free_slices(gnnagg_aggregator *a);
 
 // builds the source slices on first use and (re)mirrors the edge values into slice order
-static int ensure_slices(gnnagg_aggregator *a, int want, cudaStream_t st)
+static int ensure_slices(gnnagg_aggregator *a, int want, cudaStream_t st, bool compact = false)
 {
     if (a->num_slices != want) {
         free_slices(a);
@@ -568,6 +571,17 @@ static int ensure_slices(gnnagg_aggregator *a, int want, cudaStream_t st)
             s->n = a->n;
             s->m = a->sl_cnt[c];
             s->warp_edges = a->warp_edges ? a->warp_edges : (a->m < kSmallGraphEdges ? 128 : kWarpEdges);  // as the whole graph
+            if (compact && c > 0) {
+                // slices behind the first only ADD to rows that have edges in them: keep those rows only (slice 0 stays
+                // complete: it is the pass that writes every row, zeros included)
+                int rows = 0;
+                if (int rc = compact_rows_device(s->d_ptr, a->n, &s->c_ptr, &s->out_row, &rows, st)) {
+                    free_slices(a);
+                    return rc;
+                }
+                s->d_ptr = s->c_ptr;
+                s->n = rows;
+            }
             if (int rc = build_item_rows(s, s->d_ptr, s->n, s->m, &s->d_item_row, &s->num_items, st)) {
                 free_slices(a);
                 return rc;
@@ -621,7 +635,7 @@ static int gcn_run_sliced(gnnagg_aggregator *a, const float *X, float *Y, int F,
     a->loc->warp_edges = a->warp_edges;
     a->loc->d_val = a->d_val;
     const int64_t before_build = a->loc->launches;
-    if (int rc = ensure_slices(a->loc, S, st)) return rc;
+    if (int rc = ensure_slices(a->loc, S, st, true)) return rc;
     a->launches += a->loc->launches - before_build;
     PROF_RECORD(a, 1, st);
     for (int c = 0; c < S; ++c) {
@@ -711,6 +725,8 @@ static void free_slices(gnnagg_aggregator *a)
         if (!a->slice[c]) continue;
         cudaFree(a->slice[c]->d_item_row);
         cudaFree(a->slice[c]->carry);
+        cudaFree(a->slice[c]->c_ptr);
+        cudaFree(a->slice[c]->out_row);
         free_long_rows(a->slice[c]);
         delete a->slice[c];
         a->slice[c] = nullptr;

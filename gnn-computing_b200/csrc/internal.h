@@ -35,6 +35,9 @@ int source_slices_build_device(const int *d_ptr, const int *d_idx, const int *d_
                                int num_slices, int width, int **sl_ptr, int **sl_idx, int **sl_perm, int *edge_off,
                                int *edge_cnt, cudaStream_t st, const int *d_edge_keys = nullptr);
 
+// non-empty rows of a sub-CSR and their row pointers (sched_device.cu); outputs are cudaMalloc'ed
+int compact_rows_device(const int *d_ptr, int n, int **c_ptr, int **c_row, int *n_out, cudaStream_t st);
+
 // item_row table of a CSR (row containing edge k*128), cudaMalloc'ed into *out (capi.cu)
 int build_item_rows_device(const int *d_ptr, int rows, int edges, int **out, int *items, cudaStream_t st);
 

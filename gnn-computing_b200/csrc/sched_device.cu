@@ -390,4 +390,61 @@ fail:
     return GNNAGG_ERR_CUDA;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Compaction of a sub-CSR to its non-empty rows (locality slices of the device-resident path, capi.cu): a source
+// slice of a low-degree graph leaves most rows without an edge, and walking them costs more than the slice's
+// edges.  Outputs (cudaMalloc'ed, owned by the caller): *c_row [*n_out] the rows that have edges, ascending, and
+// *c_ptr [*n_out + 1] their row pointers -- the (ptr, target) pair of a schedule whose groups are whole rows
+// (graph_schedule.h:54-57 emits exactly these (slice, row) groups), so every output row occurs at most once.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) row_flag_kernel(const int *__restrict__ ptr, int n, char *__restrict__ flag)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) flag[r] = ptr[r + 1] > ptr[r];
+}
+
+__global__ void __launch_bounds__(256) compact_ptr_kernel(const int *__restrict__ ptr, const int *__restrict__ rows, int count, int n,
+                                                          int *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = ptr[rows[i]];
+    if (i == count) out[count] = ptr[n];
+}
+
+int compact_rows_device(const int *d_ptr, int n, int **c_ptr, int **c_row, int *n_out, cudaStream_t st)
+{
+    *c_ptr = *c_row = nullptr;
+    *n_out = 0;
+    char *flag = nullptr;
+    int *count_d = nullptr;
+    void *tmp = nullptr;
+    size_t need = 0;
+    int count = 0;
+    cub::CountingInputIterator<int> ids(0);
+    SD_TRY(cudaMalloc((void **)&flag, (size_t)(n > 0 ? n : 1)));
+    SD_TRY(cudaMalloc((void **)&count_d, sizeof(int)));
+    SD_TRY(cudaMalloc((void **)c_row, (size_t)(n > 0 ? n : 1) * sizeof(int)));
+    if (n > 0) {
+        row_flag_kernel<<<blocks(n), 256, 0, st>>>(d_ptr, n, flag);
+        SD_TRY(cub::DeviceSelect::Flagged(nullptr, need, ids, flag, *c_row, count_d, n, st));
+        SD_TRY(cudaMalloc(&tmp, need ? need : 1));
+        SD_TRY(cub::DeviceSelect::Flagged(tmp, need, ids, flag, *c_row, count_d, n, st));
+        SD_TRY(cudaMemcpyAsync(&count, count_d, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SD_TRY(cudaStreamSynchronize(st));
+    }
+    SD_TRY(cudaMalloc((void **)c_ptr, ((size_t)count + 1) * sizeof(int)));
+    compact_ptr_kernel<<<blocks((int64_t)count + 1), 256, 0, st>>>(d_ptr, *c_row, count, n, *c_ptr);
+    SD_TRY(cudaGetLastError());
+    SD_TRY(cudaStreamSynchronize(st));
+    *n_out = count;
+    cudaFree(flag), cudaFree(count_d), cudaFree(tmp);
+    return GNNAGG_OK;
+fail:
+    cudaFree(flag), cudaFree(count_d), cudaFree(tmp);
+    cudaFree(*c_ptr), cudaFree(*c_row);
+    *c_ptr = *c_row = nullptr;
+    return GNNAGG_ERR_CUDA;
+}
+
 }  // namespace gnnagg

@@ -6,6 +6,7 @@ import pytest
 import torch
 
 from conftest import rel_gate
+from gnnagg import synth
 from gpu_util import GRAPHS, dev, make_graph, rand_inputs
 
 pytestmark = pytest.mark.gpu
@@ -240,3 +241,29 @@ def test_naive_spmm_and_validators(gn, orc, cuda):
     assert orc.validate_reordered(ans.cpu().numpy(), permuted.cpu().numpy(), rows) == 0
     permuted[rows[2], 1] += 0.5
     assert gn.validate_reordered(ans, permuted, dev(rows)) == 1
+
+
+@pytest.mark.parametrize("slices", [2, 5, 16])
+@pytest.mark.parametrize("F", [32, 256])
+def test_locality_slices_match_oracle(gn, orc, cuda, slices, F):
+    """gnnagg_set_locality_slices: the un-scheduled aggregation source slice by source slice (first slice complete,
+    the others compacted to their non-empty rows and accumulated) -- deterministic, within the parity gate"""
+    ptr, idx = synth.small_random_csr(4000, 9.0, 77, empty_frac=0.3, hub=30000)
+    n, m = len(ptr) - 1, len(idx)
+    X, val = rand_inputs(n, m, F, 5)
+    want, scale = orc.spmm_f64(ptr, idx, val, X)
+    agg = gn.Aggregator(dev(ptr), dev(idx), dev(val))
+    agg.set_locality_slices(slices)
+    Y = agg.gcn_run(dev(X), torch.full((n, F), float("nan"), device=cuda))
+    assert rel_gate(Y.cpu().numpy(), want, scale, 1e-5)[0] == 0
+    assert torch.equal(Y, agg.gcn_run(dev(X), torch.full((n, F), float("nan"), device=cuda)))   # bit-reproducible
+    # accumulate on top of an existing Y, and the fused layer, go through the same slices
+    Y2 = agg.gcn_run_acc(dev(X), Y.clone(), accumulate=True)
+    assert rel_gate(Y2.cpu().numpy(), 2 * want, 2 * scale, 1e-5)[0] == 0
+    if F == 32:
+        W = np.random.default_rng(1).standard_normal((F, 64)).astype(np.float32) / 6
+        _, h64, hs = orc.gcn_layer_f64(ptr, idx, val, X, W)
+        H = agg.gcn_layer(dev(X), dev(W), torch.empty((n, 64), device=cuda))
+        assert rel_gate(H.cpu().numpy(), h64, hs, 1e-5)[0] == 0
+    agg.set_locality_slices(1)
+    assert rel_gate(agg.gcn_run(dev(X), torch.empty((n, F), device=cuda)).cpu().numpy(), want, scale, 1e-5)[0] == 0
