@@ -202,9 +202,12 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
                 if (MODE == kModeGCN && p.accumulate) {  // each row is stored by exactly one item: plain RMW is safe
                     // a lane whose partial sum is exactly zero has nothing to add: rows without edges in this sub-CSR
                     // (most rows of a source slice of a low-degree graph) cost no traffic on Y
+                    // The add itself is a 128-bit reduction (RED.E.ADD.F32x4): nobody else touches this row during the
+                    // launch, so the result is as deterministic as load-add-store, but the warp does not wait for Y to come
+                    // back from memory at the end of every (short) row.
                     const bool z0 = !act0 || is_zero4(acc0), z1 = !act1 || is_zero4(acc1);
-                    if (!z0) stg_f4(y, add4(acc0, *reinterpret_cast<const float4 *>(y)));
-                    if (!z1) stg_f4(y + LPR * 4, add4(acc1, *reinterpret_cast<const float4 *>(y + LPR * 4)));
+                    if (!z0) red_add_f4(y, acc0);
+                    if (!z1) red_add_f4(y + LPR * 4, acc1);
                 } else {
                     if (act0) stg_f4(y, acc0);
                     if (act1) stg_f4(y + LPR * 4, acc1);
@@ -427,11 +430,12 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
             // row starts here and continues: raw partial
             float *y = p.Y + (size_t)((MODE == kModeGCN && p.out_row) ? __ldg(p.out_row + row) : row) * F + col;
             if (MODE == kModeGCN && p.accumulate) {
-                if (act0) acc0 = add4(acc0, *reinterpret_cast<const float4 *>(y));
-                if (act1) acc1 = add4(acc1, *reinterpret_cast<const float4 *>(y + LPR * 4));
+                if (act0) red_add_f4(y, acc0);
+                if (act1) red_add_f4(y + LPR * 4, acc1);
+            } else {
+                if (act0) stg_f4(y, acc0);
+                if (act1) stg_f4(y + LPR * 4, acc1);
             }
-            if (act0) stg_f4(y, acc0);
-            if (act1) stg_f4(y + LPR * 4, acc1);
             if (MODE == kModeGAT && vl == 0 && cb == 0) p.den_row[row] = den;
         }
     }
@@ -472,9 +476,13 @@ __device__ __forceinline__ void fixup_sum(const AggParams &p, int row, int64_t i
         for (; b <= b1; b += step) acc = add4(acc, *reinterpret_cast<const float4 *>(p.carry + (size_t)b * F + col));
         if (finish) {
             float *y = p.Y + (size_t)((MODE == kModeGCN && p.out_row) ? __ldg(p.out_row + row) : row) * F + col;
-            acc = add4(*reinterpret_cast<const float4 *>(y), acc);
-            if (MODE == kModeGAT) acc = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
-            stg_f4(y, acc);
+            if (MODE == kModeGCN) {
+                red_add_f4(y, acc);  // one add per element and launch: deterministic, and no wait for Y
+            } else {
+                acc = add4(*reinterpret_cast<const float4 *>(y), acc);
+                if (MODE == kModeGAT) acc = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+                stg_f4(y, acc);
+            }
         } else {
             stg_f4(p.carry + (size_t)item * F + col, acc);  // chunk head now holds the chunk sum
         }
