@@ -60,8 +60,8 @@ constexpr int kMaxSlices = 16;
 // kLocalitySliceL2Multiples x L2, average degree at least kLocalityMinDegree
 constexpr double kLocalityMinL2Multiples = 8.0;
 constexpr double kLocalitySliceL2Multiples = 2.5;
-constexpr double kLocalityMinDegree = 128.0;
-constexpr int kLocalityMaxAuto = 8;
+constexpr double kLocalityMinDegree = 20.0;
+constexpr int kLocalityMaxAuto = 4;
 
 struct gnnagg_aggregator {
     // borrowed graph

@@ -382,10 +382,12 @@ int gnnagg_set_host_pipeline(gnnagg_aggregator *a, int slices);
  * (graph_schedule.h:17-89: process the edges source range by source range so that the gathered rows stay in cache)
  * without its float atomics: the CSR is split once, on the GPU, into `slices` sub-CSRs by source range and the
  * deterministic kernel accumulates them one after the other; lanes whose partial sum is zero skip the pass over Y.
- *   0  automatic (default): only when X is >= 8x the L2 AND the average degree is >= 128 -- every slice walks all
- *      rows, so short rows make the passes cost more than the locality returns (products-shape, 25 edges per row,
- *      F=256: 4.43 ms un-sliced, 5.78 / 7.88 / 12.4 ms with 4 / 8 / 16 slices); none of the BASELINE.json shapes
- *      qualifies on one GPU
+ *   0  automatic (default): when X is >= 8x the L2 and the average degree is >= 20: ceil(X bytes / 2.5 L2) slices, at
+ *      most 4.  The first slice covers every row (it writes the zeros of empty rows too); the others are compacted to
+ *      the rows that have edges in them and ADD with 128-bit reductions (one add per element and launch: deterministic).
+ *      Products-shape (25 edges per row, F=256, X = 20x L2): 4.48 ms un-sliced, 4.27 / 4.29 / 4.82 ms with 2 / 4 / 8
+ *      slices -- the gain is bounded because every slice still costs a pass over the rows it touches; the reddit /
+ *      proteins / arxiv shapes (X within a few L2 sizes) run un-sliced
  *   1  off;  2..16  forced.   Square graphs (sources in [0, num_v)); out-of-range sources fall into the last slice.
  * Results are deterministic for a given setting; slices change the fp32 summation order (slice by slice). */
 int gnnagg_set_locality_slices(gnnagg_aggregator *a, int slices);

@@ -8,7 +8,7 @@ R=${1:-r1}
 OUT=gpurun_out
 mkdir -p $OUT
 NCU="ncu --clock-control none"
-BENCH="python bench.py --steps 2 --warmup 3 --cpu-seconds 0"
+BENCH="python bench.py --steps 2 --warmup 3 --cpu-seconds 0 --c5 0 --ref-kernels 0"
 
 # launch list of the bench command (per-launch times are cold-cache and serialised)
 # (only the library's kernels: the first thousands of launches of the process are torch element-wise kernels of the
