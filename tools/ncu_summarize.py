@@ -21,6 +21,7 @@ METRICS = [
     "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers",
     "launch__occupancy_limit_shared_mem", "smsp__inst_executed.sum",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "dram__throughput.avg.pct_of_peak_sustained_elapsed",
 ]
 # capture name -> (title, key in ncu_summary.json or None)
 CAPTURES = {
@@ -107,6 +108,8 @@ def main():
                              "l1_hit_pct": num(k["l1tex__t_sector_hit_rate.pct"]), "l2_hit_pct": num(k["lts__t_sector_hit_rate.pct"]),
                              "l1tex_throughput_pct": num(k["l1tex__throughput.avg.pct_of_peak_sustained_elapsed"]),
                              "lts_throughput_pct": num(k["lts__throughput.avg.pct_of_peak_sustained_elapsed"]),
+                             "dram_throughput_pct": (num(k["dram__throughput.avg.pct_of_peak_sustained_elapsed"])
+                                                     if "dram__throughput.avg.pct_of_peak_sustained_elapsed" in k else None),
                              "dram_GBps": round((rd + wr) / num(k["gpu__time_duration.sum"]) / 1e6, 1),
                              "instructions": num(k["smsp__inst_executed.sum"]),
                              "source": "profiles/%s_prof_%s.raw.csv" % (rnd, name)}

@@ -22,8 +22,8 @@ full agg        'agg_kernel'                3 ""
 timeout 900 $NCU --set full --import-source on -k regex:agg_fixup -s 6 -c 2 -f -o $OUT/${R}_prof_fixup $BENCH > $OUT/${R}_prof_fixup.log 2>&1
 full dense      'dense_tf32x3_ws'           3 ""
 full agg_uniform 'agg_kernel'               3 "--sources uniform"
-full agg_products 'agg_kernel'              3 "--workload products_gcn_layer_256"
-full dense_stream 'dense_tf32x3_ws'         3 "--workload products_gcn_layer_256"
+full agg_products 'agg_kernel'              3 "--workload products_gcn_layer_256 --locality-slices 1"
+full dense_stream 'dense_tf32x3_ws'         3 "--workload products_gcn_layer_256 --locality-slices 1"
 full agg_proteins 'agg_kernel'              3 "--workload proteins_gcn_layer_64"
 full agg_arxiv  'agg_kernel'                3 "--workload arxiv_gcn_layer_32"
 timeout 900 $NCU --set full --import-source on -k regex:agg_kernel -s 2 -c 1 -f -o $OUT/${R}_prof_gat python tools/gat_loop.py 4 > $OUT/${R}_prof_gat.log 2>&1
