@@ -14,6 +14,7 @@
 //   * warp-specialised roles connected by mbarriers only (dense_tf32x3_ws_kernel below): 4 producer warps, one MMA
 //     lane issuing 12 tcgen05.mma per stage (4 k-steps x 3 products), tcgen05.commit frees the stage, 4 epilogue
 //     warps read TMEM with tcgen05.ld (32 lanes x 32 bit x 16 columns) and store rows straight to global memory.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <mutex>
@@ -99,40 +100,59 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r)
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Warp-specialised kernel.  Roles never meet at a CTA barrier inside the loop; they hand stages to each other
-// through mbarriers:
-//   warps 4-11 producers : A chunk (128 rows x 32 floats) global -> registers -> hi/lo -> ring stage; arrive on
-//                          full_a[stage].  Each thread keeps FOUR chunks of loads in flight (4 x 4 float4 registers
-//                          with fixed roles per unrolled step: the loads issued in step c are first read in step c+4),
-//                          64 KB per SM -- the round-1 kernel had 4 producer warps and 32 KB in flight and ran at the
-//                          speed that much latency hiding allows (2.3 TB/s)
-//   warp  12   MMA       : one lane waits full_a (and full_w), issues the 12 tcgen05.mma of the chunk into accumulator
-//                          buffer tile&1, tcgen05.commit -> empty[stage]; after the last chunk commit -> acc_full[buffer]
-//   warp  13   W loader  : streamed W: bulk copies of the two W chunks of a stage as soon as the stage is empty;
-//                          resident W: one set of bulk copies at the start
-//   warps 0-3  epilogue  : wait acc_full[buffer], tcgen05.ld their 32 TMEM lanes 32 columns at a time, TRANSPOSE the
-//                          32 x 32 block through a padded shared-memory tile and store 4 rows x 128 B per instruction
-//                          (the round-1 epilogue stored 16 B from 32 different rows per instruction: twice the L2 write
-//                          requests, half a sector each); arrive on acc_empty[buffer]
-// The accumulator is double-buffered in TMEM (2 x N columns <= 512), so the epilogue of tile t overlaps the main loop
-// of tile t+1 and A loads never stop.  W is split once per call into global memory (split_w_kernel: hi/lo in the
-// canonical chunk layout) instead of once per CTA.  RESIDENT (2*K*N*4 <= 128 KB): every CTA pulls all of it into
-// shared memory with bulk copies while the producers already fill the ring; otherwise the two W chunks of a stage
-// arrive by bulk copy per stage.  Ring depth S (2..4) = whatever fits beside W and the epilogue tiles.
+// Warp-specialised kernel, A fed by the TMA engine.
+//
+// Round 1/2a versions loaded A with LDG into registers, split it there and stored hi and lo into shared memory.  ncu
+// showed what bound them: l1tex__data_pipe_lsu_wavefronts at 78-89 % of peak -- every 128-bit global load that misses
+// costs ~23 cycles of the LSU data pipe (one fill wavefront per sector), 4x what the tile's shared-memory traffic
+// costs -- while DRAM ran at 2.4-3.1 TB/s and the tensor pipe at 23-44 % (profiles/r2_ncu_summary.md).  So A no longer
+// goes through the LSU at all:
+//   * the raw fp32 tile (128 rows x 32 floats) arrives by ONE 2-D bulk tensor copy per stage
+//     (cp.async.bulk.tensor, CU_TENSOR_MAP_SWIZZLE_128B): it lands in exactly the 128-byte-swizzled K-major layout a
+//     tcgen05 shared-memory descriptor can name, and rows beyond M are zero-filled by the engine;
+//   * kind::tf32 reads the top 19 bits of each fp32 word, i.e. the raw tile IS the `hi` operand (hi = a truncated to
+//     tf32); only lo = a - trunc(a) has to be produced -- 4 converter warps read the raw tile and write the lo tile at
+//     the same swizzled offset (LDS.128 + 4 LOP + 4 FADD + STS.128 per 16 bytes; half the stores of the old split);
+//   * A*B ~= lo*Bhi + a*Blo + a*Bhi as before (W is still pre-split with round-to-nearest by split_w_kernel).
+//     With a truncated instead of rounded, |lo| < 2^-10 |a|; the dropped lo*Blo term and the tf32 truncation of lo
+//     are both below 2^-20 |a b| per product, inside the 1e-5 gate with the same tests as before.
+// Roles (mbarriers only inside the loop):
+//   warp  9    loader    : waits empty[stage], arms full_raw[stage] with the byte count and issues the tensor copy of the
+//                          A chunk (+ the two bulk copies of the stage's W chunks when W is streamed)
+//   warps 4-7  converters: wait full_raw, write the lo tile, fence.proxy.async, arrive on full_lo[stage]
+//   warp  8    MMA       : one lane waits full_lo, issues the 12 tcgen05.mma of the chunk into accumulator buffer
+//                          tile&1, tcgen05.commit -> empty[stage]; after the last chunk commit -> acc_full[buffer]
+//   warps 0-3  epilogue  : wait acc_full[buffer], tcgen05.ld 32 TMEM lanes x 32 columns, transpose the block through a
+//                          padded shared-memory tile, store 4 rows x 128 B per instruction; arrive on acc_empty[buffer]
+// The accumulator is double-buffered in TMEM (2 x N columns <= 512).  RESIDENT (2*K*N*4 <= 128 KB): W hi/lo sit in
+// shared memory for the life of the CTA; otherwise the stage's W chunks are streamed from L2.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kWsThreads = 448;
-constexpr int kProducerThreads = 256;
+constexpr int kWsThreads = 320;
+constexpr int kConverterThreads = 128;
 constexpr int kMaxStages = 4;
 constexpr int kEpiRowBytes = (32 + 4) * 4;                 // 32 floats + 16 B of padding: conflict-free both ways
 constexpr int kEpiBytes = 4 * 32 * kEpiRowBytes;           // one 32 x 32 tile per epilogue warp
 
+// 128-byte-swizzled K-major operand (what the tensor copy writes): 8-row x 128-byte atoms, 1024 bytes apart
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr)
+{
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void *tmap, int c0, int c1, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
+                 : "memory");
+}
+
 template <bool RESIDENT>
 __global__ void __launch_bounds__(kWsThreads, 1)
-dense_tf32x3_ws_kernel(const float *__restrict__ A, const float *__restrict__ Whi, const float *__restrict__ Wlo,
+dense_tf32x3_ws_kernel(const __grid_constant__ CUtensorMap tmapA, const float *__restrict__ Whi, const float *__restrict__ Wlo,
                        float *__restrict__ C, int64_t M, int N, int K, int acc_cols, int S)
 {
-    extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t s_full_a[kMaxStages], s_full_w[kMaxStages], s_empty[kMaxStages], s_acc_full[2], s_acc_empty[2],
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t s_full_raw[kMaxStages], s_full_lo[kMaxStages], s_empty[kMaxStages], s_acc_full[2], s_acc_empty[2],
         s_w_ready;
     __shared__ uint32_t s_tmem;
 
@@ -140,13 +160,13 @@ dense_tf32x3_ws_kernel(const float *__restrict__ A, const float *__restrict__ Wh
     const int chunks = K / kChunkK;
     const uint32_t b_chunk = (uint32_t)N * 128u;  // bytes of one 32-wide K chunk of Whi (or Wlo)
     const uint32_t w_bytes = RESIDENT ? 2u * (uint32_t)chunks * b_chunk : 0u;
-    const uint32_t stage_bytes = RESIDENT ? 2u * kStageBytes : 2u * kStageBytes + 2u * b_chunk;  // [Ahi | Alo | (Bhi | Blo)]
-    uint8_t *const ring = smem + w_bytes;
+    const uint32_t stage_bytes = RESIDENT ? 2u * kStageBytes : 2u * kStageBytes + 2u * b_chunk;  // [A raw | A lo | (Bhi | Blo)]
+    uint8_t *const ring = smem + w_bytes;        // 1024-byte aligned: w_bytes and stage_bytes are multiples of 8 KB
     uint8_t *const epi = ring + (uint32_t)S * stage_bytes;
-    const uint32_t sbo = (kChunkK / 4) * 128;  // 1024 B between 8-row core-matrix groups, both operands
+    const uint32_t sbo = (kChunkK / 4) * 128;    // W operands: 1024 B between 8-row core-matrix groups (no swizzle)
     const int64_t tiles = (M + kTileM - 1) / kTileM;
 
-    if (warp == 12) {
+    if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
                      "r"((uint32_t)(2 * acc_cols))
                      : "memory");
@@ -154,8 +174,8 @@ dense_tf32x3_ws_kernel(const float *__restrict__ A, const float *__restrict__ Wh
     }
     if (tid == 0) {
         for (int i = 0; i < S; ++i) {
-            mbar_init(smem_u32(&s_full_a[i]), kProducerThreads);
-            mbar_init(smem_u32(&s_full_w[i]), 1);
+            mbar_init(smem_u32(&s_full_raw[i]), 1);
+            mbar_init(smem_u32(&s_full_lo[i]), kConverterThreads);
             mbar_init(smem_u32(&s_empty[i]), 1);
         }
         for (int i = 0; i < 2; ++i) {
@@ -170,73 +190,68 @@ dense_tf32x3_ws_kernel(const float *__restrict__ A, const float *__restrict__ Wh
     tc_fence_after();
     const uint32_t tmem = s_tmem;
 
-    if (warp >= 4 && warp < 12) {
-        // ---------------------------------------------------------------- producers
+    if (warp == 9) {
+        // ---------------------------------------------------------------- loader (one lane)
+        if (lane == 0) {
+            if (RESIDENT) {
+                // all of W (pre-split, chunk layout) into shared memory once: 2 * chunks bulk copies on one mbarrier
+                const uint32_t ready = smem_u32(&s_w_ready);
+                mbar_expect_tx(ready, w_bytes);
+                for (int kc = 0; kc < chunks; ++kc) {
+                    bulk_g2s(smem_u32(smem) + (uint32_t)kc * b_chunk, Whi + (size_t)kc * N * 32, b_chunk, ready);
+                    bulk_g2s(smem_u32(smem) + (uint32_t)(chunks + kc) * b_chunk, Wlo + (size_t)kc * N * 32, b_chunk, ready);
+                }
+            }
+            uint32_t stage = 0, round = 0;
+            for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                for (int kc = 0; kc < chunks; ++kc) {
+                    if (round > 0) mbar_wait(smem_u32(&s_empty[stage]), (round - 1) & 1);  // MMAs of the previous use retired
+                    const uint32_t full = smem_u32(&s_full_raw[stage]);
+                    const uint32_t a_raw = smem_u32(ring + stage * stage_bytes);
+                    mbar_expect_tx(full, RESIDENT ? (uint32_t)kStageBytes : (uint32_t)kStageBytes + 2u * b_chunk);
+                    tma_load_2d(a_raw, &tmapA, kc * kChunkK, (int)(tile * kTileM), full);
+                    if (!RESIDENT) {
+                        const uint32_t dst = a_raw + 2u * kStageBytes;
+                        bulk_g2s(dst, Whi + (size_t)kc * N * 32, b_chunk, full);
+                        bulk_g2s(dst + b_chunk, Wlo + (size_t)kc * N * 32, b_chunk, full);
+                    }
+                    if (++stage == (uint32_t)S) {
+                        stage = 0;
+                        ++round;
+                    }
+                }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ---------------------------------------------------------------- converters: lo = a - trunc_tf32(a)
         const int t = tid - 128;
-        // element u = p * 256 + t of a stage: row = (u >> 6) * 8 + (u & 7), 16-byte K piece kq = (u >> 3) & 7.
-        // Eight consecutive lanes cover the 8 rows of one core matrix (conflict-free 128-byte shared-memory phases);
-        // a warp-wide load touches 8 rows x 64 B, whole sectors.
-        auto fetch = [&](int64_t tile, int kc, float4 (&v)[4]) {
-#pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                const int u = p * kProducerThreads + t;
-                const int r8 = u & 7, kq = (u >> 3) & 7, rb = u >> 6;
-                const int64_t row = tile * kTileM + rb * 8 + r8;
-                v[p] = (tile < tiles && row < M) ? ldg_f4(A + (size_t)row * K + kc * kChunkK + kq * 4)
-                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        };
-        float4 b0[4], b1[4], b2[4], b3[4];
-        int64_t ftile = blockIdx.x;
-        int fkc = 0;
-        auto fetch_next = [&](float4 (&v)[4]) {
-            fetch(ftile, fkc, v);
-            if (++fkc == chunks) {
-                fkc = 0;
-                ftile += gridDim.x;
-            }
-        };
-        const int64_t my_tiles = (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+        const int64_t my_tiles = tiles > blockIdx.x ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
         const uint32_t total = (uint32_t)(my_tiles * chunks);
-        uint32_t c = 0, stage = 0, round = 0;  // round = c / S
-        auto step = [&](float4 (&buf)[4]) {
-            if (round > 0) mbar_wait(smem_u32(&s_empty[stage]), (round - 1) & 1);  // MMAs of the previous use retired
-            uint8_t *aHi = ring + stage * stage_bytes, *aLo = aHi + kStageBytes;
+        uint32_t stage = 0, par = 0;
+        for (uint32_t c = 0; c < total; ++c) {
+            mbar_wait(smem_u32(&s_full_raw[stage]), par);
+            const uint8_t *raw = ring + stage * stage_bytes;
+            uint8_t *lo = ring + stage * stage_bytes + kStageBytes;
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                const int u = p * kProducerThreads + t;
-                const int r8 = u & 7, kq = (u >> 3) & 7, rb = u >> 6;
-                const float4 v = buf[p];
-                const float4 h = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
-                const float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-                const uint32_t off = (uint32_t)rb * sbo + (uint32_t)kq * 128u + (uint32_t)r8 * 16u;
-                *reinterpret_cast<float4 *>(aHi + off) = h;
-                *reinterpret_cast<float4 *>(aLo + off) = l;
+            for (int p = 0; p < 8; ++p) {
+                // element-wise on the swizzled tile: offset in = offset out; 8 consecutive threads = one 128-byte row
+                const uint32_t off = (uint32_t)(p * kConverterThreads + t) * 16u;
+                const float4 v = *reinterpret_cast<const float4 *>(raw + off);
+                float4 l;
+                l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+                l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+                l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                *reinterpret_cast<float4 *>(lo + off) = l;
             }
             fence_proxy_async();  // generic-proxy stores visible to the tensor core's async proxy
-            mbar_arrive(smem_u32(&s_full_a[stage]));
-            fetch_next(buf);      // refill this buffer: first read four steps from now
-            ++c;
+            mbar_arrive(smem_u32(&s_full_lo[stage]));
             if (++stage == (uint32_t)S) {
                 stage = 0;
-                ++round;
+                par ^= 1u;
             }
-        };
-        fetch_next(b0);
-        fetch_next(b1);
-        fetch_next(b2);
-        fetch_next(b3);
-        for (;;) {
-            if (c >= total) break;
-            step(b0);
-            if (c >= total) break;
-            step(b1);
-            if (c >= total) break;
-            step(b2);
-            if (c >= total) break;
-            step(b3);
         }
-    } else if (warp == 12) {
+    } else if (warp == 8) {
         // ---------------------------------------------------------------- MMA issue (one lane)
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
@@ -248,15 +263,15 @@ dense_tf32x3_ws_kernel(const float *__restrict__ A, const float *__restrict__ Wh
                 tc_fence_after();
                 const uint32_t d_tmem = tmem + buf * (uint32_t)acc_cols;
                 for (int kc = 0; kc < chunks; ++kc) {
-                    mbar_wait(smem_u32(&s_full_a[stage]), par);
-                    if (!RESIDENT) mbar_wait(smem_u32(&s_full_w[stage]), par);
+                    mbar_wait(smem_u32(&s_full_raw[stage]), par);  // the tensor copy (and the streamed W chunks) landed
+                    mbar_wait(smem_u32(&s_full_lo[stage]), par);   // the lo tile is written
                     tc_fence_after();
                     const uint32_t a_hi = smem_u32(ring + stage * stage_bytes), a_lo = a_hi + kStageBytes;
                     const uint32_t b_hi = RESIDENT ? smem_u32(smem) + (uint32_t)kc * b_chunk : a_lo + kStageBytes;
                     const uint32_t b_lo = RESIDENT ? b_hi + (uint32_t)chunks * b_chunk : b_hi + b_chunk;
 #pragma unroll
-                    for (int j = 0; j < kChunkK / 8; ++j) {  // one MMA consumes K = 8 tf32 = two 16-byte chunks
-                        const uint64_t dah = smem_desc(a_hi + j * 256, 128, sbo), dal = smem_desc(a_lo + j * 256, 128, sbo);
+                    for (int j = 0; j < kChunkK / 8; ++j) {  // one MMA consumes K = 8 tf32 = 32 bytes of every row
+                        const uint64_t dah = smem_desc_sw128(a_hi + j * 32), dal = smem_desc_sw128(a_lo + j * 32);
                         const uint64_t dbh = smem_desc(b_hi + j * 256, 128, sbo), dbl = smem_desc(b_lo + j * 256, 128, sbo);
                         tc_mma_tf32(d_tmem, dal, dbh, idesc, (kc | j) ? 1u : 0u);  // small terms first
                         tc_mma_tf32(d_tmem, dah, dbl, idesc, 1u);
@@ -269,34 +284,6 @@ dense_tf32x3_ws_kernel(const float *__restrict__ A, const float *__restrict__ Wh
                     }
                 }
                 tc_commit(smem_u32(&s_acc_full[buf]));
-            }
-        }
-    } else if (warp == 13) {
-        // ---------------------------------------------------------------- W loader
-        if (RESIDENT && lane == 0) {
-            // all of W (pre-split, chunk layout) into shared memory once: 2 * chunks bulk copies on one mbarrier
-            const uint32_t ready = smem_u32(&s_w_ready);
-            mbar_expect_tx(ready, w_bytes);
-            for (int kc = 0; kc < chunks; ++kc) {
-                bulk_g2s(smem_u32(smem) + (uint32_t)kc * b_chunk, Whi + (size_t)kc * N * 32, b_chunk, ready);
-                bulk_g2s(smem_u32(smem) + (uint32_t)(chunks + kc) * b_chunk, Wlo + (size_t)kc * N * 32, b_chunk, ready);
-            }
-        }
-        if (!RESIDENT && lane == 0) {
-            uint32_t stage = 0, round = 0;
-            for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-                for (int kc = 0; kc < chunks; ++kc) {
-                    if (round > 0) mbar_wait(smem_u32(&s_empty[stage]), (round - 1) & 1);
-                    const uint32_t full = smem_u32(&s_full_w[stage]);
-                    const uint32_t dst = smem_u32(ring + stage * stage_bytes) + 2u * kStageBytes;
-                    mbar_expect_tx(full, 2u * b_chunk);
-                    bulk_g2s(dst, Whi + (size_t)kc * N * 32, b_chunk, full);
-                    bulk_g2s(dst + b_chunk, Wlo + (size_t)kc * N * 32, b_chunk, full);
-                    if (++stage == (uint32_t)S) {
-                        stage = 0;
-                        ++round;
-                    }
-                }
             }
         }
     } else {
@@ -335,8 +322,49 @@ dense_tf32x3_ws_kernel(const float *__restrict__ A, const float *__restrict__ Wh
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 12)
+    if (warp == 8)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)(2 * acc_cols)) : "memory");
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point: libgnnagg.so does not link libcuda, so it still
+// loads on a machine without a GPU (tests/test_abi.py)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled()
+{
+    static std::mutex lock;
+    static EncodeTiledFn fn = nullptr;
+    std::lock_guard<std::mutex> guard(lock);
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// A [M, K] fp32 row-major, box = 32 floats x 128 rows, 128-byte swizzle, rows beyond M read as zero
+static int make_a_tensor_map(CUtensorMap *map, const float *A, int64_t M, int K)
+{
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return set_error(GNNAGG_ERR_CUDA, "dense combination: cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)M};
+    const cuuint64_t gstride[1] = {(cuuint64_t)K * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)kChunkK, (cuuint32_t)kTileM};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(A), gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[128];
+        snprintf(buf, sizeof buf, "dense combination: cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return set_error(GNNAGG_ERR_CUDA, buf);
+    }
+    return GNNAGG_OK;
 }
 
 // Stream-ordered pool for the W split of the streamed kernel.  The device's default pool hands freed memory back to
@@ -390,8 +418,9 @@ void dense_preload()
     if (cudaGetDevice(&dev) == cudaSuccess) {
         split_pool(dev);
         // opt in to the largest dynamic shared memory either variant can ask for, now rather than at the first launch
-        ensure_dynamic_smem(dense_tf32x3_ws_kernel<false>, 0, dev, 227 * 1024 - 1024);
-        ensure_dynamic_smem(dense_tf32x3_ws_kernel<true>, 1, dev, 227 * 1024 - 1024);
+        ensure_dynamic_smem(dense_tf32x3_ws_kernel<false>, 0, dev, 227 * 1024 - 2048);
+        ensure_dynamic_smem(dense_tf32x3_ws_kernel<true>, 1, dev, 227 * 1024 - 2048);
+        encode_tiled();
     }
 }
 
@@ -418,22 +447,27 @@ int dense_nn_launch(const float *A, const float *B, float *C, int64_t M, int N, 
         return set_error(GNNAGG_ERR_CUDA, "dense combination: cannot allocate the W split");
     float *whi = wsplit, *wlo = wsplit + (size_t)K * N;
     split_w_kernel<<<(K * N + 255) / 256, 256, 0, st>>>(B, whi, wlo, K, N);
+    CUtensorMap tmapA;
+    if (int rc = make_a_tensor_map(&tmapA, A, M, K)) {
+        cudaFreeAsync(wsplit, st);
+        return rc;
+    }
     cudaError_t e = cudaSuccess;
-    constexpr size_t kSmemBudget = 227 * 1024 - 1024;  // opt-in limit minus the static barriers
+    constexpr size_t kSmemBudget = 227 * 1024 - 2048;  // opt-in limit minus the static barriers and the 1 KB alignment slack
     if (N * K > kMaxNK) {  // W does not fit in shared memory next to the A ring: stream it stage by stage
         const size_t stage = (size_t)2 * kStageBytes + (size_t)2 * N * 128;
         int S = (int)((kSmemBudget - kEpiBytes) / stage);
         S = S > kMaxStages ? kMaxStages : S;
         const size_t smem_s = (size_t)S * stage + kEpiBytes;
         e = ensure_dynamic_smem(dense_tf32x3_ws_kernel<false>, 0, dev, smem_s);
-        if (e == cudaSuccess) dense_tf32x3_ws_kernel<false><<<grid, kWsThreads, smem_s, st>>>(A, whi, wlo, C, M, N, K, acc_cols, S);
+        if (e == cudaSuccess) dense_tf32x3_ws_kernel<false><<<grid, kWsThreads, smem_s, st>>>(tmapA, whi, wlo, C, M, N, K, acc_cols, S);
     } else {
         const size_t wres = (size_t)2 * N * K * 4;  // W hi/lo resident
         int S = (int)((kSmemBudget - kEpiBytes - wres) / ((size_t)2 * kStageBytes));
         S = S > kMaxStages ? kMaxStages : S;
         const size_t smem = wres + (size_t)S * 2 * kStageBytes + kEpiBytes;
         e = ensure_dynamic_smem(dense_tf32x3_ws_kernel<true>, 1, dev, smem);
-        if (e == cudaSuccess) dense_tf32x3_ws_kernel<true><<<grid, kWsThreads, smem, st>>>(A, whi, wlo, C, M, N, K, acc_cols, S);
+        if (e == cudaSuccess) dense_tf32x3_ws_kernel<true><<<grid, kWsThreads, smem, st>>>(tmapA, whi, wlo, C, M, N, K, acc_cols, S);
     }
     if (e == cudaSuccess) e = cudaPeekAtLastError();
     cudaFreeAsync(wsplit, st);
