@@ -127,9 +127,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r)
 // The accumulator is double-buffered in TMEM (2 x N columns <= 512).  RESIDENT (2*K*N*4 <= 128 KB): W hi/lo sit in
 // shared memory for the life of the CTA; otherwise the stage's W chunks are streamed from L2.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kWsThreads = 320;
+constexpr int kWsThreads = 352;
 constexpr int kConverterThreads = 128;
-constexpr int kMaxStages = 4;
+constexpr int kMaxRaw = 4;                                 // depth of the raw-tile ring (tensor copies in flight)
+constexpr int kLoStages = 2;                               // depth of the lo (+ streamed W) ring
 constexpr int kEpiRowBytes = (32 + 4) * 4;                 // 32 floats + 16 B of padding: conflict-free both ways
 constexpr int kEpiBytes = 4 * 32 * kEpiRowBytes;           // one 32 x 32 tile per epilogue warp
 
@@ -146,25 +147,31 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void *tmap, int 
                  : "memory");
 }
 
+// Two rings, because what has to be deep and what has to be wide differ: the RAW ring (RR x 16 KB, the tensor copies in
+// flight -- HBM latency is hidden by its depth) and the LO ring (2 x [lo tile 16 KB + the stage's W chunks when W is
+// streamed]).  Chunk c uses raw slot c % RR and lo slot c % 2.
 template <bool RESIDENT>
 __global__ void __launch_bounds__(kWsThreads, 1)
 dense_tf32x3_ws_kernel(const __grid_constant__ CUtensorMap tmapA, const float *__restrict__ Whi, const float *__restrict__ Wlo,
-                       float *__restrict__ C, int64_t M, int N, int K, int acc_cols, int S)
+                       float *__restrict__ C, int64_t M, int N, int K, int acc_cols, int RR)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t s_full_raw[kMaxStages], s_full_lo[kMaxStages], s_empty[kMaxStages], s_acc_full[2], s_acc_empty[2],
-        s_w_ready;
+    __shared__ __align__(8) uint64_t s_full_raw[kMaxRaw], s_empty_raw[kMaxRaw], s_full_lo[kLoStages], s_full_w[kLoStages],
+        s_empty_lo[kLoStages], s_acc_full[2], s_acc_empty[2], s_w_ready;
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int chunks = K / kChunkK;
     const uint32_t b_chunk = (uint32_t)N * 128u;  // bytes of one 32-wide K chunk of Whi (or Wlo)
     const uint32_t w_bytes = RESIDENT ? 2u * (uint32_t)chunks * b_chunk : 0u;
-    const uint32_t stage_bytes = RESIDENT ? 2u * kStageBytes : 2u * kStageBytes + 2u * b_chunk;  // [A raw | A lo | (Bhi | Blo)]
-    uint8_t *const ring = smem + w_bytes;        // 1024-byte aligned: w_bytes and stage_bytes are multiples of 8 KB
-    uint8_t *const epi = ring + (uint32_t)S * stage_bytes;
-    const uint32_t sbo = (kChunkK / 4) * 128;    // W operands: 1024 B between 8-row core-matrix groups (no swizzle)
+    const uint32_t lo_stage = RESIDENT ? (uint32_t)kStageBytes : (uint32_t)kStageBytes + 2u * b_chunk;  // [A lo | (Bhi | Blo)]
+    uint8_t *const raw_ring = smem + w_bytes;     // 1024-byte aligned: every piece is a multiple of 8 KB
+    uint8_t *const lo_ring = raw_ring + (uint32_t)RR * kStageBytes;
+    uint8_t *const epi = lo_ring + (uint32_t)kLoStages * lo_stage;
+    const uint32_t sbo = (kChunkK / 4) * 128;     // W operands: 1024 B between 8-row core-matrix groups (no swizzle)
     const int64_t tiles = (M + kTileM - 1) / kTileM;
+    const int64_t my_tiles = tiles > blockIdx.x ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint32_t total = (uint32_t)(my_tiles * chunks);  // chunks this CTA processes
 
     if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
@@ -173,10 +180,14 @@ dense_tf32x3_ws_kernel(const __grid_constant__ CUtensorMap tmapA, const float *_
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        for (int i = 0; i < S; ++i) {
+        for (int i = 0; i < RR; ++i) {
             mbar_init(smem_u32(&s_full_raw[i]), 1);
+            mbar_init(smem_u32(&s_empty_raw[i]), 1);
+        }
+        for (int i = 0; i < kLoStages; ++i) {
             mbar_init(smem_u32(&s_full_lo[i]), kConverterThreads);
-            mbar_init(smem_u32(&s_empty[i]), 1);
+            mbar_init(smem_u32(&s_full_w[i]), 1);
+            mbar_init(smem_u32(&s_empty_lo[i]), 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&s_acc_full[i]), 1);
@@ -191,7 +202,24 @@ dense_tf32x3_ws_kernel(const __grid_constant__ CUtensorMap tmapA, const float *_
     const uint32_t tmem = s_tmem;
 
     if (warp == 9) {
-        // ---------------------------------------------------------------- loader (one lane)
+        // ---------------------------------------------------------------- A loader (one lane): tensor copies, RR deep
+        if (lane == 0) {
+            uint32_t slot = 0, round = 0;
+            for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                for (int kc = 0; kc < chunks; ++kc) {
+                    if (round > 0) mbar_wait(smem_u32(&s_empty_raw[slot]), (round - 1) & 1);  // MMAs of the previous use retired
+                    const uint32_t full = smem_u32(&s_full_raw[slot]);
+                    mbar_expect_tx(full, (uint32_t)kStageBytes);
+                    tma_load_2d(smem_u32(raw_ring + slot * kStageBytes), &tmapA, kc * kChunkK, (int)(tile * kTileM), full);
+                    if (++slot == (uint32_t)RR) {
+                        slot = 0;
+                        ++round;
+                    }
+                }
+            }
+        }
+    } else if (warp == 10) {
+        // ---------------------------------------------------------------- W loader (one lane)
         if (lane == 0) {
             if (RESIDENT) {
                 // all of W (pre-split, chunk layout) into shared memory once: 2 * chunks bulk copies on one mbarrier
@@ -201,54 +229,47 @@ dense_tf32x3_ws_kernel(const __grid_constant__ CUtensorMap tmapA, const float *_
                     bulk_g2s(smem_u32(smem) + (uint32_t)kc * b_chunk, Whi + (size_t)kc * N * 32, b_chunk, ready);
                     bulk_g2s(smem_u32(smem) + (uint32_t)(chunks + kc) * b_chunk, Wlo + (size_t)kc * N * 32, b_chunk, ready);
                 }
-            }
-            uint32_t stage = 0, round = 0;
-            for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-                for (int kc = 0; kc < chunks; ++kc) {
-                    if (round > 0) mbar_wait(smem_u32(&s_empty[stage]), (round - 1) & 1);  // MMAs of the previous use retired
-                    const uint32_t full = smem_u32(&s_full_raw[stage]);
-                    const uint32_t a_raw = smem_u32(ring + stage * stage_bytes);
-                    mbar_expect_tx(full, RESIDENT ? (uint32_t)kStageBytes : (uint32_t)kStageBytes + 2u * b_chunk);
-                    tma_load_2d(a_raw, &tmapA, kc * kChunkK, (int)(tile * kTileM), full);
-                    if (!RESIDENT) {
-                        const uint32_t dst = a_raw + 2u * kStageBytes;
-                        bulk_g2s(dst, Whi + (size_t)kc * N * 32, b_chunk, full);
-                        bulk_g2s(dst + b_chunk, Wlo + (size_t)kc * N * 32, b_chunk, full);
-                    }
-                    if (++stage == (uint32_t)S) {
-                        stage = 0;
-                        ++round;
-                    }
+            } else {
+                // the two W chunks of every K chunk into the lo-ring slot, as soon as the MMAs that read the slot retired
+                for (uint32_t c = 0; c < total; ++c) {
+                    const uint32_t l = c % kLoStages, round = c / kLoStages;
+                    const int kc = (int)(c % (uint32_t)chunks);
+                    if (round > 0) mbar_wait(smem_u32(&s_empty_lo[l]), (round - 1) & 1);
+                    const uint32_t full = smem_u32(&s_full_w[l]);
+                    const uint32_t dst = smem_u32(lo_ring + l * lo_stage) + (uint32_t)kStageBytes;
+                    mbar_expect_tx(full, 2u * b_chunk);
+                    bulk_g2s(dst, Whi + (size_t)kc * N * 32, b_chunk, full);
+                    bulk_g2s(dst + b_chunk, Wlo + (size_t)kc * N * 32, b_chunk, full);
                 }
             }
         }
     } else if (warp >= 4 && warp < 8) {
         // ---------------------------------------------------------------- converters: lo = a - trunc_tf32(a)
         const int t = tid - 128;
-        const int64_t my_tiles = tiles > blockIdx.x ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-        const uint32_t total = (uint32_t)(my_tiles * chunks);
-        uint32_t stage = 0, par = 0;
+        uint32_t slot = 0, par_raw = 0;
         for (uint32_t c = 0; c < total; ++c) {
-            mbar_wait(smem_u32(&s_full_raw[stage]), par);
-            const uint8_t *raw = ring + stage * stage_bytes;
-            uint8_t *lo = ring + stage * stage_bytes + kStageBytes;
+            const uint32_t l = c % kLoStages, round_l = c / kLoStages;
+            mbar_wait(smem_u32(&s_full_raw[slot]), par_raw);
+            if (round_l > 0) mbar_wait(smem_u32(&s_empty_lo[l]), (round_l - 1) & 1);  // MMAs that read this lo slot retired
+            const uint8_t *raw = raw_ring + slot * kStageBytes;
+            uint8_t *lo = lo_ring + l * lo_stage;
 #pragma unroll
             for (int p = 0; p < 8; ++p) {
                 // element-wise on the swizzled tile: offset in = offset out; 8 consecutive threads = one 128-byte row
                 const uint32_t off = (uint32_t)(p * kConverterThreads + t) * 16u;
                 const float4 v = *reinterpret_cast<const float4 *>(raw + off);
-                float4 l;
-                l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-                l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-                l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-                l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-                *reinterpret_cast<float4 *>(lo + off) = l;
+                float4 r;
+                r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+                r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+                r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                *reinterpret_cast<float4 *>(lo + off) = r;
             }
             fence_proxy_async();  // generic-proxy stores visible to the tensor core's async proxy
-            mbar_arrive(smem_u32(&s_full_lo[stage]));
-            if (++stage == (uint32_t)S) {
-                stage = 0;
-                par ^= 1u;
+            mbar_arrive(smem_u32(&s_full_lo[l]));
+            if (++slot == (uint32_t)RR) {
+                slot = 0;
+                par_raw ^= 1u;
             }
         }
     } else if (warp == 8) {
@@ -256,17 +277,19 @@ dense_tf32x3_ws_kernel(const __grid_constant__ CUtensorMap tmapA, const float *_
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
             if (RESIDENT) mbar_wait(smem_u32(&s_w_ready), 0);
-            uint32_t stage = 0, par = 0, t = 0;
+            uint32_t slot = 0, par_raw = 0, c = 0, t = 0;
             for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++t) {
                 const uint32_t buf = t & 1;
                 if (t >= 2) mbar_wait(smem_u32(&s_acc_empty[buf]), ((t >> 1) - 1) & 1);  // epilogue drained this buffer
                 tc_fence_after();
                 const uint32_t d_tmem = tmem + buf * (uint32_t)acc_cols;
-                for (int kc = 0; kc < chunks; ++kc) {
-                    mbar_wait(smem_u32(&s_full_raw[stage]), par);  // the tensor copy (and the streamed W chunks) landed
-                    mbar_wait(smem_u32(&s_full_lo[stage]), par);   // the lo tile is written
+                for (int kc = 0; kc < chunks; ++kc, ++c) {
+                    const uint32_t l = c % kLoStages, par_l = (c / kLoStages) & 1;
+                    mbar_wait(smem_u32(&s_full_raw[slot]), par_raw);  // the tensor copy landed
+                    mbar_wait(smem_u32(&s_full_lo[l]), par_l);        // the lo tile is written
+                    if (!RESIDENT) mbar_wait(smem_u32(&s_full_w[l]), par_l);
                     tc_fence_after();
-                    const uint32_t a_hi = smem_u32(ring + stage * stage_bytes), a_lo = a_hi + kStageBytes;
+                    const uint32_t a_hi = smem_u32(raw_ring + slot * kStageBytes), a_lo = smem_u32(lo_ring + l * lo_stage);
                     const uint32_t b_hi = RESIDENT ? smem_u32(smem) + (uint32_t)kc * b_chunk : a_lo + kStageBytes;
                     const uint32_t b_lo = RESIDENT ? b_hi + (uint32_t)chunks * b_chunk : b_hi + b_chunk;
 #pragma unroll
@@ -277,16 +300,17 @@ dense_tf32x3_ws_kernel(const __grid_constant__ CUtensorMap tmapA, const float *_
                         tc_mma_tf32(d_tmem, dah, dbl, idesc, 1u);
                         tc_mma_tf32(d_tmem, dah, dbh, idesc, 1u);
                     }
-                    tc_commit(smem_u32(&s_empty[stage]));
-                    if (++stage == (uint32_t)S) {
-                        stage = 0;
-                        par ^= 1u;
+                    tc_commit(smem_u32(&s_empty_raw[slot]));  // both rings are released by the same MMAs
+                    tc_commit(smem_u32(&s_empty_lo[l]));
+                    if (++slot == (uint32_t)RR) {
+                        slot = 0;
+                        par_raw ^= 1u;
                     }
                 }
                 tc_commit(smem_u32(&s_acc_full[buf]));
             }
         }
-    } else {
+    } else if (warp < 4) {
         // ---------------------------------------------------------------- warps 0-3: epilogue
         uint8_t *const my_tile = epi + warp * (32 * kEpiRowBytes);
         uint32_t t = 0;
@@ -418,8 +442,8 @@ void dense_preload()
     if (cudaGetDevice(&dev) == cudaSuccess) {
         split_pool(dev);
         // opt in to the largest dynamic shared memory either variant can ask for, now rather than at the first launch
-        ensure_dynamic_smem(dense_tf32x3_ws_kernel<false>, 0, dev, 227 * 1024 - 2048);
-        ensure_dynamic_smem(dense_tf32x3_ws_kernel<true>, 1, dev, 227 * 1024 - 2048);
+        ensure_dynamic_smem(dense_tf32x3_ws_kernel<false>, 0, dev, 227 * 1024 - 1024);
+        ensure_dynamic_smem(dense_tf32x3_ws_kernel<true>, 1, dev, 227 * 1024 - 1024);
         encode_tiled();
     }
 }
@@ -453,21 +477,23 @@ int dense_nn_launch(const float *A, const float *B, float *C, int64_t M, int N, 
         return rc;
     }
     cudaError_t e = cudaSuccess;
-    constexpr size_t kSmemBudget = 227 * 1024 - 2048;  // opt-in limit minus the static barriers and the 1 KB alignment slack
-    if (N * K > kMaxNK) {  // W does not fit in shared memory next to the A ring: stream it stage by stage
-        const size_t stage = (size_t)2 * kStageBytes + (size_t)2 * N * 128;
-        int S = (int)((kSmemBudget - kEpiBytes) / stage);
-        S = S > kMaxStages ? kMaxStages : S;
-        const size_t smem_s = (size_t)S * stage + kEpiBytes;
+    // static shared memory rounds up to 1 KB (the dynamic part is 1024-byte aligned); everything else goes to the rings
+    constexpr size_t kSmemBudget = 227 * 1024 - 1024;
+    if (N * K > kMaxNK) {  // W does not fit in shared memory next to the rings: stream it, two chunks per lo-ring slot
+        const size_t fixed = (size_t)kLoStages * (kStageBytes + (size_t)2 * N * 128) + kEpiBytes;
+        int RR = (int)((kSmemBudget - fixed) / kStageBytes);
+        RR = RR > kMaxRaw ? kMaxRaw : RR;
+        if (RR < 1) return set_error(GNNAGG_ERR_ARG, "dense combination: feat_out too large for the shared-memory rings");
+        const size_t smem_s = fixed + (size_t)RR * kStageBytes;
         e = ensure_dynamic_smem(dense_tf32x3_ws_kernel<false>, 0, dev, smem_s);
-        if (e == cudaSuccess) dense_tf32x3_ws_kernel<false><<<grid, kWsThreads, smem_s, st>>>(tmapA, whi, wlo, C, M, N, K, acc_cols, S);
+        if (e == cudaSuccess) dense_tf32x3_ws_kernel<false><<<grid, kWsThreads, smem_s, st>>>(tmapA, whi, wlo, C, M, N, K, acc_cols, RR);
     } else {
-        const size_t wres = (size_t)2 * N * K * 4;  // W hi/lo resident
-        int S = (int)((kSmemBudget - kEpiBytes - wres) / ((size_t)2 * kStageBytes));
-        S = S > kMaxStages ? kMaxStages : S;
-        const size_t smem = wres + (size_t)S * 2 * kStageBytes + kEpiBytes;
+        const size_t fixed = (size_t)2 * N * K * 4 + (size_t)kLoStages * kStageBytes + kEpiBytes;  // W hi/lo resident
+        int RR = (int)((kSmemBudget - fixed) / kStageBytes);
+        RR = RR > kMaxRaw ? kMaxRaw : RR;
+        const size_t smem = fixed + (size_t)RR * kStageBytes;
         e = ensure_dynamic_smem(dense_tf32x3_ws_kernel<true>, 1, dev, smem);
-        if (e == cudaSuccess) dense_tf32x3_ws_kernel<true><<<grid, kWsThreads, smem, st>>>(tmapA, whi, wlo, C, M, N, K, acc_cols, S);
+        if (e == cudaSuccess) dense_tf32x3_ws_kernel<true><<<grid, kWsThreads, smem, st>>>(tmapA, whi, wlo, C, M, N, K, acc_cols, RR);
     }
     if (e == cudaSuccess) e = cudaPeekAtLastError();
     cudaFreeAsync(wsplit, st);
