@@ -733,10 +733,24 @@ int gnnagg_dist_set_graph(gnnagg_dist *d, const int *d_ptr, const int *d_idx, co
     d->rounds = K;
     for (int s = 0; s < kMaxStages; ++s) d->stage_mask[s] = 0;
     d->stage_of[d->rank] = 0;
+    // groups grow geometrically (7 owners in 3 stages: 1 + 2 + 4): the first remote stage must not wait long after the
+    // local one, and the later, larger ones amortise their launches; every group holds at least one owner
+    int stage_end[kMaxStages + 1] = {0};  // stage s covers arrival positions [stage_end[s-1], stage_end[s])
+    for (int s = 1; s <= R; ++s) {
+        int e = (int)((double)((1 << s) - 1) / (double)((1 << R) - 1) * (W - 1) + 0.5);
+        if (e < s) e = s;
+        if (e > W - 1 - (R - s)) e = W - 1 - (R - s);
+        stage_end[s] = s == R ? W - 1 : e;
+    }
     for (int k = 0; k < W - 1; ++k) {
         const int p = (d->rank + 1 + k) % W;
-        d->stage_of[p] = R == 0 ? 0 : 1 + (int)((int64_t)k * R / (W - 1));
-        d->stage_mask[d->stage_of[p]] |= 1u << p;
+        int stage = 0;
+        if (R > 0) {
+            stage = 1;
+            while (stage < R && k >= stage_end[stage]) ++stage;
+        }
+        d->stage_of[p] = stage;
+        d->stage_mask[stage] |= 1u << p;
     }
     Bounds b;
     memset(&b, 0, sizeof b);

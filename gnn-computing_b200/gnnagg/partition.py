@@ -503,6 +503,18 @@ class LocalDist:
         self.handles = []
 
 
+def stage_ends(world, R):
+    """[R+1] arrival positions at which the owner groups of the stage mode end (dist.cu): geometric growth -- 7 owners in
+    3 stages are cut 1 + 2 + 4 -- with at least one owner per group"""
+    ends = [0] * (R + 1)
+    for s in range(1, R + 1):
+        e = int(((1 << s) - 1) / float((1 << R) - 1) * (world - 1) + 0.5)
+        e = max(e, s)
+        e = min(e, world - 1 - (R - s))
+        ends[s] = world - 1 if s == R else e
+    return ends
+
+
 def peer_plan(idx, bounds, rank, remote_stages, ptr=None):
     """numpy restatement of the index bookkeeping of gnnagg_dist_set_graph (csrc/dist.cu), for tests and for
     reasoning about traffic without a GPU.  remote_stages = R > 0: stages by owner; 0: one pass; < 0: row pipelining
@@ -512,7 +524,7 @@ def peer_plan(idx, bounds, rank, remote_stages, ptr=None):
       recv_tab    [rounds, world+1] first slot of every owner's rows of a round; recv_tab[c][world] = end of round c
       recv_local  recv_rows as local row numbers inside their owner's shard (the rows that owner pushes)
       stage_of    [world] stage of every owner: 0 = this rank (and everybody when R <= 0), 1..R = groups of the owners
-                  taken in the order rank+1, rank+2, ... (mod world)
+                  taken in the order rank+1, rank+2, ... (mod world), group sizes growing geometrically (stage_ends)
       recv_order  the world-1 remote owners in the order their rows arrive (owner p pushes to p-1, p-2, ...)
       chunk_rows  [rounds+1] row chunk boundaries
       idx_new     per edge: local row of the own shard, or rows_own + receive slot (one buffer: shard, then slots)
@@ -547,8 +559,9 @@ def peer_plan(idx, bounds, rank, remote_stages, ptr=None):
         recv_tab[c] = lo + np.searchsorted(sel, bounds, side="left")
     order = [(rank + 1 + k) % W for k in range(W - 1)]
     stage_of = np.zeros(W, np.int64)
+    ends = stage_ends(W, R)
     for k, p in enumerate(order):
-        stage_of[p] = 0 if R == 0 else 1 + (k * R) // (W - 1)
+        stage_of[p] = 0 if R == 0 else 1 + int(np.searchsorted(ends[1:], k, side="right"))
     owner_e = np.clip(np.searchsorted(bounds, g, side="right") - 1, 0, W - 1)
     slot_of = np.empty(len(U), np.int64)
     by_id = np.argsort(U, kind="stable")
