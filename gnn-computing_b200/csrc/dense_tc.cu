@@ -448,11 +448,58 @@ void dense_preload()
     }
 }
 
+// Shapes the tensor-core kernel does not take (K or N not a multiple of 32, or above 256): a plain fp32 tiled GEMM,
+// 64 x 64 tile per CTA, 4 x 4 outputs per thread, K in steps of 16 through shared memory; sums in K order (fp32 FMA).
+// matmul_NN of the reference (dense.h:4-23, cuBLAS) takes any size; the configs of BASELINE.json never come here.
+__global__ void __launch_bounds__(256) dense_simt_kernel(const float *__restrict__ A, const float *__restrict__ B, float *__restrict__ C,
+                                                         int64_t M, int N, int K)
+{
+    __shared__ float sA[16][64 + 1], sB[16][64];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int64_t row0 = (int64_t)blockIdx.y * 64;
+    const int col0 = blockIdx.x * 64;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+            const int r = i >> 4, k = i & 15;
+            sA[k][r] = (row0 + r < M && k0 + k < K) ? __ldg(A + (size_t)(row0 + r) * K + k0 + k) : 0.f;
+            const int kb = i >> 6, c = i & 63;
+            sB[kb][c] = (k0 + kb < K && col0 + c < N) ? __ldg(B + (size_t)(k0 + kb) * N + col0 + c) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = sA[k][ty * 4 + i], b[i] = sB[k][tx * 4 + i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (row0 + ty * 4 + i < M && col0 + tx * 4 + j < N) C[(size_t)(row0 + ty * 4 + i) * N + col0 + tx * 4 + j] = acc[i][j];
+}
+
 int dense_nn_launch(const float *A, const float *B, float *C, int64_t M, int N, int K, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
-    if (N < 32 || K < 32 || N > 256 || K > 256 || (N % 32) || (K % 32))
-        return set_error(GNNAGG_ERR_ARG, "dense combination: feat_in and feat_out must be multiples of 32 in [32,256]");
+    if (N < 1 || K < 1) return set_error(GNNAGG_ERR_ARG, "dense combination: feat_in and feat_out must be positive");
+    if (N < 32 || K < 32 || N > 256 || K > 256 || (N % 32) || (K % 32)) {
+        if (M <= 0) return GNNAGG_OK;
+        const dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 63) / 64));
+        if (grid.y > 65535u * 16u) return set_error(GNNAGG_ERR_ARG, "dense combination: too many rows for the generic kernel");
+        for (int64_t r0 = 0; r0 < M; r0 += (int64_t)65535 * 64) {  // gridDim.y limit
+            const int64_t rows = M - r0 < (int64_t)65535 * 64 ? M - r0 : (int64_t)65535 * 64;
+            dense_simt_kernel<<<dim3(grid.x, (unsigned)((rows + 63) / 64)), 256, 0, st>>>(A + (size_t)r0 * K, B, C + (size_t)r0 * N, rows, N, K);
+        }
+        return cudaPeekAtLastError() == cudaSuccess ? GNNAGG_OK : set_error(GNNAGG_ERR_CUDA, "dense combination: launch failed");
+    }
     if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(C)) & 15)
         return set_error(GNNAGG_ERR_ARG, "dense combination: A and C must be 16-byte aligned");
     int dev = 0, sms = 0;

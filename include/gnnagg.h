@@ -184,7 +184,8 @@ int gnnagg_csr2edgelist(gnnagg_aggregator *a, int *d_edgelist /* 2*num_e */, voi
  * replaces Aggregator_GCN::run_with_nn + aggr_gcn_nn (aggr_gcn.h:304-359,491-499) and the
  * un-fused aggr_gcn_target + matmul_NN baseline (dense.h:4-23, Figure10/main_b.cu:89-90).
  * AX may be NULL (not materialised for the caller).  Outputs are overwritten (the reference
- * accumulates into never-zeroed buffers).  feat_in, feat_out multiples of 32 <= 256.
+ * accumulates into never-zeroed buffers).  feat_in, feat_out multiples of 32 up to 256 run on the tensor
+ * cores; any other size goes through a plain fp32 kernel (matmul_NN takes any size, dense.h:4-23).
  * The combination runs on tcgen05 tensor cores in 3xTF32 (fp32-level accuracy). */
 int gnnagg_gcn_layer(gnnagg_aggregator *a, const float *X, const float *W, float *H, float *AX, int feat_in,
                      int feat_out, int scheduled, void *stream);

@@ -24,12 +24,17 @@ def test_dense_nn_parity(gn, orc, cuda, M, K, N):
     assert bad == 0, worst
 
 
-def test_dense_nn_rejects_unsupported_shapes(gn, cuda):
-    A = torch.zeros((8, 48), device=cuda)
-    with pytest.raises(gn.GnnaggError):
-        gn.dense_nn(A, torch.zeros((48, 32), device=cuda), torch.zeros((8, 32), device=cuda))  # K % 32
-    with pytest.raises(gn.GnnaggError):
-        gn.dense_nn(torch.zeros((8, 32), device=cuda), torch.zeros((32, 512), device=cuda), torch.zeros((8, 512), device=cuda))
+@pytest.mark.parametrize("M,K,N", [(8, 48, 32), (1000, 100, 7), (333, 16, 16), (257, 320, 64), (1, 1, 1), (5000, 40, 300)])
+def test_dense_nn_generic_shapes(gn, orc, cuda, M, K, N):
+    """shapes the tensor-core kernel does not take (K or N not a multiple of 32, or above 256) go through the plain fp32
+    kernel, as any size goes through cuBLAS in the reference's matmul_NN (dense.h:4-23)"""
+    rng = np.random.default_rng(M + K + N)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    W = (rng.standard_normal((K, N)) / np.sqrt(K)).astype(np.float32)
+    C = gn.dense_nn(dev(A), dev(W), torch.full((M, N), float("nan"), device=cuda))
+    h64, scale = orc.dense_f64(A, W)
+    bad, worst = rel_gate(C.cpu().numpy(), h64, scale, TOL)
+    assert bad == 0, worst
 
 
 @pytest.mark.parametrize("fin,fout", [(128, 128), (32, 32), (64, 32), (256, 128)])
