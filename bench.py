@@ -714,7 +714,7 @@ def main():
                     roofline["compulsory_bytes"] = comp
                     roofline["traffic_over_compulsory"] = round(s["dram_bytes_per_launch"] / comp, 3)
                     roofline["frac_dram"] = round(s["dram_bytes_per_launch"] / (agg_ms * 1e-3) / 1e9 / peak, 4)
-                units = {k: s[k] for k in ("l1tex_throughput_pct", "lts_throughput_pct", "dram_throughput_pct") if k in s}
+                units = {k: s[k] for k in ("l1tex_throughput_pct", "lts_throughput_pct", "dram_throughput_pct") if s.get(k) is not None}
                 if units:
                     top = max(units, key=units.get)
                     roofline["binding_unit"] = {"unit": top.split("_")[0], "pct_of_peak": units[top]}
