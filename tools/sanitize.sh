@@ -1,4 +1,5 @@
 #!/bin/bash
+# (multi-rank dist tests are left out: the sanitizer serialises kernels, and kernels of different ranks wait for each other)
 # compute-sanitizer passes over the GPU parity tests on small graphs (the reference has
 # latent shared-memory hazards -- missing __syncwarp, shared slots written by several warps; these runs show ours has none).
 #   tools/sanitize.sh [memcheck|racecheck|synccheck|initcheck]   -> gpurun_out/sanitize_<tool>.log
@@ -7,8 +8,8 @@ tool="${1:-memcheck}"
 mkdir -p gpurun_out
 timeout 1500 compute-sanitizer --tool "$tool" --error-exitcode 66 --target-processes application-only \
   python -m pytest tests/test_gpu_gcn.py tests/test_gpu_gat.py tests/test_gpu_layer.py tests/test_gpu_mlp.py tests/test_gpu_backward.py \
-  tests/test_gpu_sampler.py -m gpu -q -x -p no:cacheprovider \
-  -k "(unscheduled and (tiny or hub or exact_items)) or scheduled or sddmm and tiny or dense_nn_parity or mlp_parity and tiny or host_entry or (backward and (tiny or hub or bighub) and not timing) or transpose_bit_exact or (sampler_matches_oracle and (hub or tiny))" \
+  tests/test_gpu_sampler.py tests/test_gpu_dist.py -m gpu -q -x -p no:cacheprovider \
+  -k "(unscheduled and (tiny or hub or exact_items)) or scheduled or sddmm and tiny or dense_nn_parity or dense_nn_generic or mlp_parity and tiny or host_entry or host_buffer_entry or locality_slices or (local_ranks_match and 1-1) or (backward and (tiny or hub or bighub) and not timing) or transpose_bit_exact or (sampler_matches_oracle and (hub or tiny))" \
   > "gpurun_out/sanitize_${tool}.log" 2>&1
 echo "exit=$?" >> "gpurun_out/sanitize_${tool}.log"
 tail -15 "gpurun_out/sanitize_${tool}.log"
