@@ -153,7 +153,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void *tmap, int 
 template <bool RESIDENT>
 __global__ void __launch_bounds__(kWsThreads, 1)
 dense_tf32x3_ws_kernel(const __grid_constant__ CUtensorMap tmapA, const float *__restrict__ Whi, const float *__restrict__ Wlo,
-                       float *__restrict__ C, int64_t M, int N, int K, int acc_cols, int RR)
+                       float *__restrict__ C, int64_t M, int N, int K, int acc_cols, int RR, int LS)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_full_raw[kMaxRaw], s_empty_raw[kMaxRaw], s_full_lo[kLoStages], s_full_w[kLoStages],
@@ -167,7 +167,7 @@ dense_tf32x3_ws_kernel(const __grid_constant__ CUtensorMap tmapA, const float *_
     const uint32_t lo_stage = RESIDENT ? (uint32_t)kStageBytes : (uint32_t)kStageBytes + 2u * b_chunk;  // [A lo | (Bhi | Blo)]
     uint8_t *const raw_ring = smem + w_bytes;     // 1024-byte aligned: every piece is a multiple of 8 KB
     uint8_t *const lo_ring = raw_ring + (uint32_t)RR * kStageBytes;
-    uint8_t *const epi = lo_ring + (uint32_t)kLoStages * lo_stage;
+    uint8_t *const epi = lo_ring + (uint32_t)LS * lo_stage;
     const uint32_t sbo = (kChunkK / 4) * 128;     // W operands: 1024 B between 8-row core-matrix groups (no swizzle)
     const int64_t tiles = (M + kTileM - 1) / kTileM;
     const int64_t my_tiles = tiles > blockIdx.x ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -184,7 +184,7 @@ dense_tf32x3_ws_kernel(const __grid_constant__ CUtensorMap tmapA, const float *_
             mbar_init(smem_u32(&s_full_raw[i]), 1);
             mbar_init(smem_u32(&s_empty_raw[i]), 1);
         }
-        for (int i = 0; i < kLoStages; ++i) {
+        for (int i = 0; i < LS; ++i) {
             mbar_init(smem_u32(&s_full_lo[i]), kConverterThreads);
             mbar_init(smem_u32(&s_full_w[i]), 1);
             mbar_init(smem_u32(&s_empty_lo[i]), 1);
@@ -232,7 +232,7 @@ dense_tf32x3_ws_kernel(const __grid_constant__ CUtensorMap tmapA, const float *_
             } else {
                 // the two W chunks of every K chunk into the lo-ring slot, as soon as the MMAs that read the slot retired
                 for (uint32_t c = 0; c < total; ++c) {
-                    const uint32_t l = c % kLoStages, round = c / kLoStages;
+                    const uint32_t l = c % (uint32_t)LS, round = c / (uint32_t)LS;
                     const int kc = (int)(c % (uint32_t)chunks);
                     if (round > 0) mbar_wait(smem_u32(&s_empty_lo[l]), (round - 1) & 1);
                     const uint32_t full = smem_u32(&s_full_w[l]);
@@ -248,7 +248,7 @@ dense_tf32x3_ws_kernel(const __grid_constant__ CUtensorMap tmapA, const float *_
         const int t = tid - 128;
         uint32_t slot = 0, par_raw = 0;
         for (uint32_t c = 0; c < total; ++c) {
-            const uint32_t l = c % kLoStages, round_l = c / kLoStages;
+            const uint32_t l = c % (uint32_t)LS, round_l = c / (uint32_t)LS;
             mbar_wait(smem_u32(&s_full_raw[slot]), par_raw);
             if (round_l > 0) mbar_wait(smem_u32(&s_empty_lo[l]), (round_l - 1) & 1);  // MMAs that read this lo slot retired
             const uint8_t *raw = raw_ring + slot * kStageBytes;
@@ -284,7 +284,7 @@ dense_tf32x3_ws_kernel(const __grid_constant__ CUtensorMap tmapA, const float *_
                 tc_fence_after();
                 const uint32_t d_tmem = tmem + buf * (uint32_t)acc_cols;
                 for (int kc = 0; kc < chunks; ++kc, ++c) {
-                    const uint32_t l = c % kLoStages, par_l = (c / kLoStages) & 1;
+                    const uint32_t l = c % (uint32_t)LS, par_l = (c / (uint32_t)LS) & 1;
                     mbar_wait(smem_u32(&s_full_raw[slot]), par_raw);  // the tensor copy landed
                     mbar_wait(smem_u32(&s_full_lo[l]), par_l);        // the lo tile is written
                     if (!RESIDENT) mbar_wait(smem_u32(&s_full_w[l]), par_l);
@@ -533,14 +533,17 @@ int dense_nn_launch(const float *A, const float *B, float *C, int64_t M, int N, 
         if (RR < 1) return set_error(GNNAGG_ERR_ARG, "dense combination: feat_out too large for the shared-memory rings");
         const size_t smem_s = fixed + (size_t)RR * kStageBytes;
         e = ensure_dynamic_smem(dense_tf32x3_ws_kernel<false>, 0, dev, smem_s);
-        if (e == cudaSuccess) dense_tf32x3_ws_kernel<false><<<grid, kWsThreads, smem_s, st>>>(tmapA, whi, wlo, C, M, N, K, acc_cols, RR);
+        if (e == cudaSuccess) dense_tf32x3_ws_kernel<false><<<grid, kWsThreads, smem_s, st>>>(tmapA, whi, wlo, C, M, N, K, acc_cols, RR, kLoStages);
     } else {
-        const size_t fixed = (size_t)2 * N * K * 4 + (size_t)kLoStages * kStageBytes + kEpiBytes;  // W hi/lo resident
+        // (one lo slot and a fourth raw slot instead was measured: 0.074 ms against 0.0615 ms on C2 -- the converter <-> MMA
+        // hand-over then serialises; two lo slots stay)
+        const int LS = kLoStages;
+        const size_t fixed = (size_t)2 * N * K * 4 + (size_t)LS * kStageBytes + kEpiBytes;  // W hi/lo resident
         int RR = (int)((kSmemBudget - fixed) / kStageBytes);
         RR = RR > kMaxRaw ? kMaxRaw : RR;
         const size_t smem = fixed + (size_t)RR * kStageBytes;
         e = ensure_dynamic_smem(dense_tf32x3_ws_kernel<true>, 1, dev, smem);
-        if (e == cudaSuccess) dense_tf32x3_ws_kernel<true><<<grid, kWsThreads, smem, st>>>(tmapA, whi, wlo, C, M, N, K, acc_cols, RR);
+        if (e == cudaSuccess) dense_tf32x3_ws_kernel<true><<<grid, kWsThreads, smem, st>>>(tmapA, whi, wlo, C, M, N, K, acc_cols, RR, LS);
     }
     if (e == cudaSuccess) e = cudaPeekAtLastError();
     cudaFreeAsync(wsplit, st);
