@@ -133,13 +133,26 @@ __global__ void __launch_bounds__(32) halo_consumed_kernel(PeerTable peers, int 
 // into what three aggregation CTAs (3 x 256 threads x 80 registers) leave free on an SM; the first version (256 threads,
 // 8 loads in flight per thread, 2 CTAs per SM) displaced one aggregation CTA per SM for as long as the exchange ran.
 // Posted writes need no latency hiding; U loads per thread cover the local gather latency.
-template <int U>
+template <int U, bool PREFETCH>
 __global__ void __launch_bounds__(128, 16) halo_push_kernel(const float4 *__restrict__ X, const int *__restrict__ rows,
                                                             float4 *__restrict__ dst, int64_t count4, int F4, int f4_shift,
                                                             uint32_t *done_cnt, uint32_t *arrived_flag, uint32_t value)
 {
     const int64_t stride = (int64_t)gridDim.x * 128 * U;
     for (int64_t base = (int64_t)blockIdx.x * 128 * U + threadIdx.x; base < count4; base += stride) {
+        if (PREFETCH) {
+            // the rows of the NEXT iteration are pulled into L2 now: prefetches hold no registers, so the kernel has twice
+            // its load depth in flight where the memory system is busy with the aggregation's gathers
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t e = base + stride + (int64_t)u * 128;
+                if (e < count4 && (e & 7) == 0) {  // one prefetch per 128-byte line
+                    const int64_t r = (f4_shift >= 0) ? (e >> f4_shift) : (e / F4);
+                    const int c = (int)(e - r * F4);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(X + (int64_t)__ldg(rows + r) * F4 + c));
+                }
+            }
+        }
         float4 v[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -452,6 +465,7 @@ struct gnnagg_dist {
     uint32_t epoch = 0;
     int sm_count = 148;
     int prepared_feat = 0;
+    int push_prefetch = 0;      // 1: the register push kernel prefetches the next iteration's rows into L2
     int push_tma = 0;           // 1: rows staged through shared memory by bulk copies (halo_push_tma_kernel); 0: register version
     int same_device_ranks = 1;  // ranks (including this one) living on this rank's device: > 1 only in single-GPU tests
     int64_t launches = 0;
@@ -529,7 +543,9 @@ int gnnagg_dist_create_rank(int rank, int world, const int64_t *shard_bounds, in
         if (cudaFuncGetAttributes(&attr, halo_begin_kernel) != cudaSuccess) cudaGetLastError();
         if (cudaFuncGetAttributes(&attr, halo_wait_kernel) != cudaSuccess) cudaGetLastError();
         if (cudaFuncGetAttributes(&attr, halo_consumed_kernel) != cudaSuccess) cudaGetLastError();
-        if (cudaFuncGetAttributes(&attr, halo_push_kernel<4>) != cudaSuccess) cudaGetLastError();
+        if (cudaFuncGetAttributes(&attr, halo_push_kernel<4, false>) != cudaSuccess) cudaGetLastError();
+        if (cudaFuncGetAttributes(&attr, halo_push_kernel<4, true>) != cudaSuccess) cudaGetLastError();
+        if (const char *env = getenv("GNNAGG_PUSH_PREFETCH")) d->push_prefetch = atoi(env) != 0;
         if (cudaFuncGetAttributes(&attr, halo_push_tma_kernel) != cudaSuccess) cudaGetLastError();
         if (cudaFuncSetAttribute(halo_push_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPushBufs * kPushBatchBytes) != cudaSuccess)
             cudaGetLastError();
@@ -1079,10 +1095,14 @@ static int dist_run(gnnagg_dist *d, int buf, float *Y, const float *W, float *H,
                     g2 = g2 < 1 ? 1 : (g2 > cap2 ? cap2 : g2);
                     halo_push_tma_kernel<<<(unsigned)g2, 32, kPushBufs * kPushBatchBytes, d->comm>>>(
                         xs, list, dst, d->send_cnt[q][c], feat_in, rpb, &mine->push_cnt[q], flag, flag_base + (uint32_t)c + 1u);
+                } else if (d->push_prefetch) {
+                    halo_push_kernel<4, true><<<(unsigned)grid, 128, 0, d->comm>>>(reinterpret_cast<const float4 *>(xs), list,
+                                                                                 reinterpret_cast<float4 *>(dst), count4, F4, shift,
+                                                                                 &mine->push_cnt[q], flag, flag_base + (uint32_t)c + 1u);
                 } else {
-                    halo_push_kernel<4><<<(unsigned)grid, 128, 0, d->comm>>>(reinterpret_cast<const float4 *>(xs), list,
-                                                                           reinterpret_cast<float4 *>(dst), count4, F4, shift,
-                                                                           &mine->push_cnt[q], flag, flag_base + (uint32_t)c + 1u);
+                    halo_push_kernel<4, false><<<(unsigned)grid, 128, 0, d->comm>>>(reinterpret_cast<const float4 *>(xs), list,
+                                                                                  reinterpret_cast<float4 *>(dst), count4, F4, shift,
+                                                                                  &mine->push_cnt[q], flag, flag_base + (uint32_t)c + 1u);
                 }
                 DT_TRY(cudaPeekAtLastError());
                 ++d->launches;
