@@ -417,16 +417,17 @@ int compact_rows_device(const int *d_ptr, int n, int **c_ptr, int **c_row, int *
     *c_ptr = *c_row = nullptr;
     *n_out = 0;
     char *flag = nullptr;
-    int *count_d = nullptr;
+    int *count_d = nullptr, *ids = nullptr;
     void *tmp = nullptr;
     size_t need = 0;
     int count = 0;
-    cub::CountingInputIterator<int> ids(0);
     SD_TRY(cudaMalloc((void **)&flag, (size_t)(n > 0 ? n : 1)));
+    SD_TRY(cudaMalloc((void **)&ids, (size_t)(n > 0 ? n : 1) * sizeof(int)));
     SD_TRY(cudaMalloc((void **)&count_d, sizeof(int)));
     SD_TRY(cudaMalloc((void **)c_row, (size_t)(n > 0 ? n : 1) * sizeof(int)));
     if (n > 0) {
         row_flag_kernel<<<blocks(n), 256, 0, st>>>(d_ptr, n, flag);
+        iota_kernel<<<blocks(n), 256, 0, st>>>(ids, n);
         SD_TRY(cub::DeviceSelect::Flagged(nullptr, need, ids, flag, *c_row, count_d, n, st));
         SD_TRY(cudaMalloc(&tmp, need ? need : 1));
         SD_TRY(cub::DeviceSelect::Flagged(tmp, need, ids, flag, *c_row, count_d, n, st));
@@ -438,10 +439,10 @@ int compact_rows_device(const int *d_ptr, int n, int **c_ptr, int **c_row, int *
     SD_TRY(cudaGetLastError());
     SD_TRY(cudaStreamSynchronize(st));
     *n_out = count;
-    cudaFree(flag), cudaFree(count_d), cudaFree(tmp);
+    cudaFree(flag), cudaFree(count_d), cudaFree(ids), cudaFree(tmp);
     return GNNAGG_OK;
 fail:
-    cudaFree(flag), cudaFree(count_d), cudaFree(tmp);
+    cudaFree(flag), cudaFree(count_d), cudaFree(ids), cudaFree(tmp);
     cudaFree(*c_ptr), cudaFree(*c_row);
     *c_ptr = *c_row = nullptr;
     return GNNAGG_ERR_CUDA;
