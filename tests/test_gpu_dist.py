@@ -164,3 +164,61 @@ def test_multi_process_equals_single_gpu():
     assert r.returncode == 0
     lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
     assert lines and all(l["ok"] for l in lines)
+
+
+def test_narrower_feature_width_than_feat_cap_and_wide_rows(gn, orc, cuda):
+    """feat < feat_cap re-uses the same peer-visible buffers with a tighter row stride (every rank is prepared for the new
+    width before the first step: a process that drives several ranks must do that, gnnagg_dist_prepare); F = 256 takes
+    the two-register-chunk kernel variant"""
+    rng = np.random.default_rng(41)
+    bounds = [0, 500, 1300, 2000]
+    n, cap = bounds[-1], 256
+    ptr, idx = synth.small_random_csr(n, 15.0, 17, hub=7000)
+    val = rng.standard_normal(len(idx)).astype(np.float32)
+    ld = partition.LocalDist(bounds, cap, devices=[0, 0, 0])
+    streams = [torch.cuda.Stream(device=cuda) for _ in range(3)]
+    try:
+        for r in range(3):
+            lp, li, lv = partition.local_block(ptr, idx, val, bounds, r)
+            ld.set_graph(r, torch.from_numpy(lp).to(cuda), torch.from_numpy(li).to(cuda), torch.from_numpy(lv).to(cuda), 2)
+        ld.connect()
+        for F in (256, 64):
+            X = rng.standard_normal((n, F)).astype(np.float32)
+            want, scale = orc.spmm_f64(ptr, idx, val, X)
+            for r in range(3):
+                gn.check(gn.lib().gnnagg_dist_prepare(ld.ranks[r].h, F, None))
+                ld.ranks[r].x(0, F).copy_(torch.from_numpy(np.ascontiguousarray(X[bounds[r]:bounds[r + 1]])).to(cuda))
+            torch.cuda.synchronize()
+            Y = [torch.empty((bounds[r + 1] - bounds[r], F), device=cuda) for r in range(3)]
+            for r in range(3):
+                with torch.cuda.stream(streams[r]):
+                    ld.ranks[r].gcn_run(Y[r], 0, F)
+            torch.cuda.synchronize()
+            for r in range(3):
+                ld.ranks[r].check()
+            got = torch.cat(Y).cpu().numpy().astype(np.float64)
+            assert np.all(np.abs(got - want) <= 1e-5 * scale + 1e-30), F
+    finally:
+        ld.close()
+
+
+def test_state_errors_are_reported_not_crashed(gn, cuda):
+    import ctypes as C
+
+    L = gn.lib()
+    bounds = (C.c_int64 * 3)(0, 8, 16)
+    h = C.c_void_p()
+    assert L.gnnagg_dist_create_rank(0, 2, bounds, 32, C.byref(h)) == 0
+    blob = C.create_string_buffer(256)
+    assert L.gnnagg_dist_export(h, blob) == -4                         # no graph yet
+    assert L.gnnagg_dist_gcn_run(h, 0, None, 32, 0, None) != 0         # neither graph nor peers
+    assert L.gnnagg_dist_x(h, 0) is None
+    ptr = torch.zeros(9, dtype=torch.int32, device=cuda)
+    assert L.gnnagg_dist_set_graph(h, C.c_void_p(ptr.data_ptr()), None, None, 0, 1, None) == 0
+    assert L.gnnagg_dist_set_graph(h, C.c_void_p(ptr.data_ptr()), None, None, 0, 1, None) == -4   # once per handle
+    Y = torch.empty((8, 32), device=cuda)
+    assert L.gnnagg_dist_gcn_run(h, 0, C.c_void_p(Y.data_ptr()), 32, 0, None) == -4              # peers not connected
+    assert b"connect" in L.gnnagg_last_error()
+    assert L.gnnagg_dist_gcn_run(h, 0, C.c_void_p(Y.data_ptr()), 48, 0, None) != 0               # feat > feat_cap
+    assert L.gnnagg_dist_create_rank(0, 17, bounds, 32, C.byref(C.c_void_p())) == -1              # world > 16
+    assert L.gnnagg_dist_destroy(h) == 0
