@@ -182,6 +182,57 @@ __global__ void __launch_bounds__(128, 16) halo_push_kernel(const float4 *__rest
     }
 }
 
+// the same loop without the register diet: 256 threads, U = 8 loads in flight per thread (GNNAGG_PUSH_HEAVY=1; it displaces
+// aggregation CTAs instead of running beside them)
+template <int U>
+__global__ void __launch_bounds__(256) halo_push_heavy_kernel(const float4 *__restrict__ X, const int *__restrict__ rows,
+                                                            float4 *__restrict__ dst, int64_t count4, int F4, int f4_shift,
+                                                            uint32_t *done_cnt, uint32_t *arrived_flag, uint32_t value)
+{
+    const int64_t stride = (int64_t)gridDim.x * 256 * U;
+    for (int64_t base = (int64_t)blockIdx.x * 256 * U + threadIdx.x; base < count4; base += stride) {
+        if (false) {
+            // the rows of the NEXT iteration are pulled into L2 now: prefetches hold no registers, so the kernel has twice
+            // its load depth in flight where the memory system is busy with the aggregation's gathers
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t e = base + stride + (int64_t)u * 256;
+                if (e < count4 && (e & 7) == 0) {  // one prefetch per 128-byte line
+                    const int64_t r = (f4_shift >= 0) ? (e >> f4_shift) : (e / F4);
+                    const int c = (int)(e - r * F4);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(X + (int64_t)__ldg(rows + r) * F4 + c));
+                }
+            }
+        }
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t e = base + (int64_t)u * 256;
+            if (e < count4) {
+                const int64_t r = (f4_shift >= 0) ? (e >> f4_shift) : (e / F4);
+                const int c = (int)(e - r * F4);
+                v[u] = __ldg(X + (int64_t)__ldg(rows + r) * F4 + c);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t e = base + (int64_t)u * 256;
+            if (e < count4) dst[e] = v[u];
+        }
+    }
+    // every thread's stores are ordered before this CTA's count, the count before the flag (system scope)
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t before = atomicAdd(done_cnt, 1u);
+        if (before == gridDim.x - 1) {
+            atomicExch(done_cnt, 0u);  // ready for the next launch towards this receiver (stream-ordered after this one)
+            __threadfence_system();
+            st_release_sys(arrived_flag, value);
+        }
+    }
+}
+
 // EXPERIMENT, off by default (GNNAGG_PUSH_TMA=1 selects it): the same push with the rows STAGED THROUGH SHARED MEMORY BY
 // THE TMA ENGINE.  One warp per CTA keeps a ring of kPushBufs batches (<= 8 KB each) in flight -- every lane issues one
 // 1-D bulk copy (cp.async.bulk, global -> shared) for one wanted row onto the batch's mbarrier; when the batch has
@@ -465,6 +516,7 @@ struct gnnagg_dist {
     uint32_t epoch = 0;
     int sm_count = 148;
     int prepared_feat = 0;
+    int push_heavy = 0;         // k > 0: 256-thread / 8-loads push kernel with up to k CTAs per SM (experiment)
     int push_prefetch = 0;      // 1: the register push kernel prefetches the next iteration's rows into L2
     int push_tma = 0;           // 1: rows staged through shared memory by bulk copies (halo_push_tma_kernel); 0: register version
     int same_device_ranks = 1;  // ranks (including this one) living on this rank's device: > 1 only in single-GPU tests
@@ -546,6 +598,8 @@ int gnnagg_dist_create_rank(int rank, int world, const int64_t *shard_bounds, in
         if (cudaFuncGetAttributes(&attr, halo_push_kernel<4, false>) != cudaSuccess) cudaGetLastError();
         if (cudaFuncGetAttributes(&attr, halo_push_kernel<4, true>) != cudaSuccess) cudaGetLastError();
         if (const char *env = getenv("GNNAGG_PUSH_PREFETCH")) d->push_prefetch = atoi(env) != 0;
+        if (cudaFuncGetAttributes(&attr, halo_push_heavy_kernel<8>) != cudaSuccess) cudaGetLastError();
+        if (const char *env = getenv("GNNAGG_PUSH_HEAVY")) d->push_heavy = atoi(env);
         if (cudaFuncGetAttributes(&attr, halo_push_tma_kernel) != cudaSuccess) cudaGetLastError();
         if (cudaFuncSetAttribute(halo_push_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPushBufs * kPushBatchBytes) != cudaSuccess)
             cudaGetLastError();
@@ -1095,6 +1149,13 @@ static int dist_run(gnnagg_dist *d, int buf, float *Y, const float *W, float *H,
                     g2 = g2 < 1 ? 1 : (g2 > cap2 ? cap2 : g2);
                     halo_push_tma_kernel<<<(unsigned)g2, 32, kPushBufs * kPushBatchBytes, d->comm>>>(
                         xs, list, dst, d->send_cnt[q][c], feat_in, rpb, &mine->push_cnt[q], flag, flag_base + (uint32_t)c + 1u);
+                } else if (d->push_heavy) {
+                    int64_t gh = (count4 + 256 * 8 - 1) / (256 * 8);
+                    const int64_t caph = d->same_device_ranks > 1 ? std::max(4, d->sm_count / (2 * d->same_device_ranks)) : (int64_t)d->push_heavy * d->sm_count;
+                    gh = gh < 1 ? 1 : (gh > caph ? caph : gh);
+                    halo_push_heavy_kernel<8><<<(unsigned)gh, 256, 0, d->comm>>>(reinterpret_cast<const float4 *>(xs), list,
+                                                                               reinterpret_cast<float4 *>(dst), count4, F4, shift,
+                                                                               &mine->push_cnt[q], flag, flag_base + (uint32_t)c + 1u);
                 } else if (d->push_prefetch) {
                     halo_push_kernel<4, true><<<(unsigned)grid, 128, 0, d->comm>>>(reinterpret_cast<const float4 *>(xs), list,
                                                                                  reinterpret_cast<float4 *>(dst), count4, F4, shift,
