@@ -145,7 +145,7 @@ def auto_stages(shape, N):
     if N <= 1:
         return 0
     if shape in RMAT_SCALES:            # 16 edges per output row: an extra pass over Y per owner group costs more than it
-        return -8                       # hides (8 GPUs: 9.2 vs 8.65 ms) -> row pipelining, 8 row chunks of the one CSR
+        return -4                       # hides (8 GPUs: 9.2 vs 8.65 ms) -> row pipelining, 4 row chunks of the one CSR (8.05 ms; 8 chunks: 8.5-8.8)
     return min(N - 1, 3)                # 490 edges per output row: Y passes are cheap, overlap by owner groups pays
 
 
@@ -648,7 +648,7 @@ def main():
     # optional: remote-stage sweep on the headline workload (builder's tuning runs; one JSON line per setting)
     if args.sweep and N > 1 and wl.ph is not None:
         for st in [int(s) for s in args.sweep.split(",")]:
-            w2 = wl if st == wl.ph.num_stages - 1 else Workload(args, args.workload, N, rank, dev, dist, stages=st)
+            w2 = wl if st == wl.stages else Workload(args, args.workload, N, rank, dev, dist, stages=st)
             if w2.ph is None:
                 continue
             r = measure(w2, timed, max(5, args.steps // 2), 3, e2e=False)
