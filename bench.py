@@ -240,6 +240,8 @@ class Workload:
                     "peer memory: every owner pushes the rows its peers' blocks reference (rank 0 receives %d distinct remote rows = "
                     "%.1f%% of X) straight into their receive slots with 128-bit stores over NVLink (cudaIpc mappings, no NCCL in "
                     "the step); %s" % (self.ph.num_recv, 100.0 * (self.ph.num_recv + 0.0) / self.src_n,
+                                       ("row pipelining: %d edge-balanced row chunks of the one CSR, chunk c starts when round c "
+                                        "of the pushes (the rows it needs first) has landed" % min(-self.stages, 16)) if self.stages < 0 else
                                        "one aggregation pass after all arrivals" if self.ph.num_stages == 1 else
                                        "stage 0 = local sources, %d remote stage(s) accumulated as their owners land" % (self.ph.num_stages - 1)))
                 return
@@ -502,7 +504,7 @@ def c5_block(args, N, rank, dev, dist, timed, steps, warmup):
             d["exposed_exchange_ms"] = round(r["ms"] - r["compute_ms"], 4)
             if wl.ph is not None:
                 ex_bytes = wl.ph.num_send * wl.fin * 4
-                d["remote_stages"] = wl.ph.num_stages - 1
+                d["remote_stages"] = wl.stages if wl.stages < 0 else wl.ph.num_stages - 1
                 d["bytes_exchanged_per_rank"] = ex_bytes
                 d["exchange_ms"] = round(r["exchange_ms"], 4)
                 d["nvlink_GBps_per_rank"] = round(ex_bytes / (r["exchange_ms"] * 1e-3) / 1e9, 1) if r["exchange_ms"] > 0 else None
@@ -776,7 +778,7 @@ def main():
             hal = {"kind": wl.halo, "exposed_ms": round(ms - r["compute_ms"], 4)}
             if wl.ph is not None:
                 ex_bytes = wl.ph.num_send * fin * 4
-                hal.update({"remote_stages": wl.ph.num_stages - 1, "stage_edges": wl.ph.stage_edges,
+                hal.update({"remote_stages": wl.stages if wl.stages < 0 else wl.ph.num_stages - 1, "stage_edges": wl.ph.stage_edges,
                             "bytes_per_rank": ex_bytes, "exchange_ms": round(r["exchange_ms"], 4),
                             "nvlink_GBps_per_rank": round(ex_bytes / (r["exchange_ms"] * 1e-3) / 1e9, 1),
                             "nvlink_frac_of_770": round(ex_bytes / (r["exchange_ms"] * 1e-3) / 1e9 / NVLINK_PEAK_GBS, 3),
