@@ -760,8 +760,9 @@ def main():
                 "edges_feat_per_s": round(N * m * fin / (ms * 1e-3), 1),
                 "clocks": clocks,
                 "e2e": {"value": round(e2e_value, 1), "unit": "GB/s", "ms_per_step": round(ms_e2e, 4),
-                        "h2d_bytes_per_step": 4 * n * fin + (4 * fin * fout if (N == 1 and not agg_only) else 0),
-                        "d2h_bytes_per_step": 4 * n * (fout or fin),
+                        # whole job: every rank copies its X shard (and W) in and its H shard out
+                        "h2d_bytes_per_step": N * (4 * n * fin + (4 * fin * fout if not agg_only else 0)),
+                        "d2h_bytes_per_step": N * 4 * n * (fout or fin),
                         "api": ("gnnagg_gcn_run_host (pinned host X -> Y)" if agg_only else "gnnagg_gcn_layer_host (pinned host X, W -> H)") if N == 1 else
                                "gnnagg_dist_gcn_layer_host: pinned H2D of the X shard into the peer-visible buffer + the step (halo pushes + "
                                "staged aggregation + combination) with the copy back of the H shard overlapping the last stage"},
