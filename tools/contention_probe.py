@@ -66,19 +66,28 @@ def main():
             ts.append(a.elapsed_time(b))
         return sorted(ts)[len(ts) // 2]
 
+    side_ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+
     def both():
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
+            side_ev[0].record()
             exchange()
+            side_ev[1].record()
         agg.gcn_run(X, Y)
         torch.cuda.current_stream().wait_stream(side)
 
+    if len(sys.argv) > 3:
+        agg.set_warp_edges(int(sys.argv[3]))     # 128: the small-graph variant, half the gathers in flight per warp
     t_agg = timeit(lambda: agg.gcn_run(X, Y))
     t_ex = timeit(exchange)
     t_both = timeit(both)
+    torch.cuda.synchronize()
+    t_ex_under = side_ev[0].elapsed_time(side_ev[1])   # how long the stand-in takes while the aggregation runs (last repetition)
     print(json.dumps({"probe": "local contention between aggregation and exchange stand-in", "shape": shape, "ranks": N, "rows": n,
                       "edges": m, "F": F, "recv_rows": R, "exchange_bytes_each_way": R * F * 4,
-                      "agg_alone_ms": round(t_agg, 3), "exchange_standin_alone_ms": round(t_ex, 3), "both_ms": round(t_both, 3),
+                      "agg_alone_ms": round(t_agg, 3), "exchange_standin_alone_ms": round(t_ex, 3), "both_ms": round(t_both, 3), "exchange_standin_while_aggregating_ms": round(t_ex_under, 3),
+                      "warp_edges": int(sys.argv[3]) if len(sys.argv) > 3 else 512,
                       "sum_ms": round(t_agg + t_ex, 3), "overlap_gain_ms": round(t_agg + t_ex - t_both, 3)}))
 
 
