@@ -34,6 +34,7 @@ CAPTURES = {
     "agg_proteins": ("aggregation kernel, proteins-shaped R-MAT, F=64", "proteins_gcn_layer_64"),
     "agg_arxiv": ("aggregation kernel, arxiv-shaped R-MAT, F=32", "arxiv_gcn_layer_32"),
     "gat": ("fused GAT aggregation, proteins-shaped R-MAT, F=64", None),
+    "agg_rmat26": ("aggregation kernel, R-MAT scale 26 (67 M vertices / 1.07 G edges), F=64, one GPU", "rmat26_gcn_agg_64"),
 }
 UNIT_SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12,
               "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}

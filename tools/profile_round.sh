@@ -26,6 +26,7 @@ full agg_products 'agg_kernel'              3 "--workload products_gcn_layer_256
 full dense_stream 'dense_tf32x3_ws'         3 "--workload products_gcn_layer_256 --locality-slices 1"
 full agg_proteins 'agg_kernel'              3 "--workload proteins_gcn_layer_64"
 full agg_arxiv  'agg_kernel'                3 "--workload arxiv_gcn_layer_32"
+full agg_rmat26 'agg_kernel'                3 "--workload rmat26_gcn_agg_64"
 timeout 900 $NCU --set full --import-source on -k regex:agg_kernel -s 2 -c 1 -f -o $OUT/${R}_prof_gat python tools/gat_loop.py 4 > $OUT/${R}_prof_gat.log 2>&1
 # gpurun brings back at most 64 MiB: keep the raw pages of every capture, the full report (with
 # source) only for the two kernels worth reading line by line
