@@ -521,6 +521,16 @@ def c5_block(args, N, rank, dev, dist, timed, steps, warmup):
         else:
             d["kernel_ms"] = round(r["prof"].get("agg", 0.0), 4)
             d["note"] = "single-GPU base of the strong-scaling series"
+            try:  # HBM fraction of the kernel from the committed ncu capture of this workload (profiles/ncu_summary.json)
+                sm = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json"))).get(C5_WORKLOAD, {})
+                peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
+                if sm.get("dram_bytes_per_launch") and d["kernel_ms"] > 0:
+                    d["roofline"] = {"bound": "hbm", "traffic": sm["dram_bytes_per_launch"], "peak": peak, "unit": "GB/s",
+                                     "frac_dram": round(sm["dram_bytes_per_launch"] / (d["kernel_ms"] * 1e-3) / 1e9 / peak, 4),
+                                     "l2_hit_pct": sm.get("l2_hit_pct"), "source": sm.get("source"),
+                                     "compulsory_bytes": compulsory_bytes(wl.n, wl.m, wl.fin)}
+            except Exception:
+                pass
         if len(stage_list) > 1 and rank == 0:
             print(json.dumps({"c5_sweep": d}), flush=True)
         if best is None or d["ms_per_step"] < best["ms_per_step"]:
