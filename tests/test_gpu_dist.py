@@ -222,3 +222,44 @@ def test_state_errors_are_reported_not_crashed(gn, cuda):
     assert L.gnnagg_dist_gcn_run(h, 0, C.c_void_p(Y.data_ptr()), 48, 0, None) != 0               # feat > feat_cap
     assert L.gnnagg_dist_create_rank(0, 17, bounds, 32, C.byref(C.c_void_p())) == -1              # world > 16
     assert L.gnnagg_dist_destroy(h) == 0
+
+
+def test_two_layers_through_the_two_shard_buffers(gn, orc, cuda):
+    """a 2-layer GCN across ranks without any copy between the layers: layer 1 writes H1 = (A X) W1 straight into the
+    OTHER peer-visible shard buffer, layer 2 pushes its halo out of that buffer.  Exercises consecutive epochs, the
+    write-after-read protection of the receive slots and both buffers."""
+    rng = np.random.default_rng(23)
+    bounds = [0, 900, 2100, 3000]
+    n, F = bounds[-1], 64
+    ptr, idx = synth.small_random_csr(n, 18.0, 29, hub=8000)
+    val = (rng.random(len(idx)).astype(np.float32) + 0.1) / 20
+    X = rng.standard_normal((n, F)).astype(np.float32)
+    W1 = (rng.standard_normal((F, F)) / 8).astype(np.float32)
+    W2 = (rng.standard_normal((F, F)) / 8).astype(np.float32)
+    _, h1_64, _ = orc.gcn_layer_f64(ptr, idx, val, X, W1)
+    ld = partition.LocalDist(bounds, F, devices=[0, 0, 0])
+    streams = [torch.cuda.Stream(device=cuda) for _ in range(3)]
+    try:
+        for r in range(3):
+            lp, li, lv = partition.local_block(ptr, idx, val, bounds, r)
+            ld.set_graph(r, torch.from_numpy(lp).to(cuda), torch.from_numpy(li).to(cuda), torch.from_numpy(lv).to(cuda), 2)
+        ld.connect()
+        dW1, dW2 = torch.from_numpy(W1).to(cuda), torch.from_numpy(W2).to(cuda)
+        H2 = [torch.empty((bounds[r + 1] - bounds[r], F), device=cuda) for r in range(3)]
+        for rep in range(3):  # repeated: the buffers are rewritten while peers may still be behind
+            for r in range(3):
+                with torch.cuda.stream(streams[r]):
+                    ld.ranks[r].x(0, F).copy_(torch.from_numpy(np.ascontiguousarray(X[bounds[r]:bounds[r + 1]])).to(cuda), non_blocking=True)
+                    ld.ranks[r].gcn_layer(dW1, ld.ranks[r].x(1, F), buf=0)       # H1 lands in buffer 1 of every rank
+                    ld.ranks[r].gcn_layer(dW2, H2[r], buf=1)                      # layer 2 reads buffer 1
+        torch.cuda.synchronize()
+        for r in range(3):
+            ld.ranks[r].check()
+        h1 = torch.cat([ld.ranks[r].x(1, F) for r in range(3)]).cpu().numpy()
+        got = torch.cat(H2).cpu().numpy().astype(np.float64)
+    finally:
+        ld.close()
+    # layer 2 of the oracle starts from the GPU's own H1 (fp32), so that only layer 2's error is gated
+    _, h2_64, h2_scale = orc.gcn_layer_f64(ptr, idx, val, np.ascontiguousarray(h1), W2)
+    assert np.all(np.abs(h1.astype(np.float64) - h1_64) <= 1e-4 * np.abs(h1_64).max())
+    assert np.all(np.abs(got - h2_64) <= 1e-5 * h2_scale + 1e-30)
