@@ -40,9 +40,14 @@ struct AggParams {
     float *__restrict__ carry;           // [num_items, F] partials of rows entering an item
     float *__restrict__ den_row;         // GAT: [n] denominator of rows that start in an item and leave it
     float *__restrict__ carry_den;       // GAT: [num_items]
-    float *__restrict__ newval;          // GAT scheduled: un-normalised edge weights (aggr_gat.h:192); GAT backward: alpha_e
-    const float2 *__restrict__ bwd_c;    // GAT backward: per row (1 / D_v, c_v = <Y[v], dY[v]>)
-    float *__restrict__ bwd_ds;          // GAT backward: ds_e (gradient of the pre-activation of edge e)
+    float *__restrict__ newval;          // GAT scheduled: un-normalised edge weights (aggr_gat.h:192); SDDMM: the dot products
+    // GAT backward (two traversals, see kModeGATBWD / kModeGATBWD2 below)
+    const float2 *__restrict__ bwd_c;    // per destination row (1 / D_v, c_v = <Y[v], dY[v]>); pass 1 reads .y, pass 2 reads .x
+    float2 *__restrict__ bwd_wt;         // per edge (w_e, t_e): un-normalised weight and w_e (g_e - c_v) lrelu'(s_e)
+    float2 *__restrict__ bwd_part;       // pass 1: [n] (sum w, sum t) over the edges of row v inside the item where v starts
+    float2 *__restrict__ bwd_carry;      // pass 1: [num_items] the same sums of the row that ENTERS an item
+    float *__restrict__ rsum;            // pass 2: row sums of ds go to rsum[row * rsum_stride] (source half of d att)
+    int rsum_stride;
     int num_rows;
     int num_edges;
     int F;
@@ -57,13 +62,20 @@ struct AggParams {
     int row_lo, row_hi, edge_lo, edge_hi;
 };
 
-// kModeGATBWD: the SDDMM traversal with X2 = dY whose per-edge epilogue turns g_e = <X[u], dY[v]> into the
-// softmax-normalised weight alpha_e and the pre-activation gradient ds_e (edge pass of aggr_gat_fine_bwd,
-// aggr_gat.h:266-290): att (or val = un-normalised weights), den_row = D_v and bwd_c are inputs.
-enum { kModeGCN = 0, kModeGAT = 1, kModeMLP = 2, kModeSDDMM = 3, kModeGATBWD = 4 };
+// The GAT backward (aggr_gat_fine_bwd, aggr_gat.h:222-294) is two traversals with one row-parallel kernel between them:
+// kModeGATBWD  (pass 1, the CSR): the SDDMM traversal with X2 = dY.  Its per-edge epilogue turns g_e = <X[u], dY[v]>
+//   into (w_e, t_e) with w_e the UN-normalised softmax weight and t_e = w_e (g_e - c_v) lrelu'(s_e) (:266-290 before
+//   the division by D_v), and sums both per row on the way (item/carry scheme, deterministic): D_v is not an input.
+//   gat_bwd_rowfinal_kernel then closes the rows: 1 / D_v and d att[2v] = (sum t) / D_v.
+// kModeGATBWD2 (pass 2, the TRANSPOSED CSR, rows = sources u): the aggregation dX[u] = sum_e alpha_e dY[v] whose
+//   weight is formed on the fly, alpha_e = w_e / D_v with (w, t) fetched through t_perm (staged like GCN edge values),
+//   and whose row scalar -- the GAT denominator slot -- is sum_e t_e / D_v = d att[2u+1].
+enum { kModeGCN = 0, kModeGAT = 1, kModeMLP = 2, kModeSDDMM = 3, kModeGATBWD = 4, kModeGATBWD2 = 5 };
 __host__ __device__ constexpr bool mode_emits_edges(int mode) { return mode == kModeSDDMM || mode == kModeGATBWD; }  // per-edge outputs, no row sums
 __host__ __device__ constexpr bool mode_has_dst(int mode) { return mode == kModeMLP || mode_emits_edges(mode); }  // keeps P[dst,:] in registers
 __host__ __device__ constexpr bool mode_stages_val(int mode) { return mode == kModeGCN; }
+// the edge weight is computed per batch by lanes vl < U and shared by shuffle; a scalar per row travels with the sums
+__host__ __device__ constexpr bool mode_gat_like(int mode) { return mode == kModeGAT || mode == kModeGATBWD2; }
 
 // row that contains edge e0 (start of an item): direct lookup when items are aligned with the
 // item_row table, bounded binary search otherwise (the small-graph variant uses 32..128-edge items)
@@ -89,6 +101,8 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
     __shared__ __align__(16) int s_stage[kCtaWarps][2][kWarpEdges];
     __shared__ __align__(8) uint64_t s_bar[kCtaWarps];
 
+    // the two passes of the GAT backward read what the kernel in front of them wrote and are launched with launch_dep
+    if (MODE == kModeGATBWD || MODE == kModeGATBWD2) griddep_wait();
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int64_t gwarp = (int64_t)(p.edge_lo / kWarpEdges) + (int64_t)blockIdx.x * kCtaWarps + warp;
@@ -104,7 +118,8 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
     {
         const int nb = p.bulk_ok ? (wcnt & ~3) : 0;  // bulk copies need 16-byte multiples
         // edge values travel with idx for GCN, and for the GAT backward when the weights are handed in (no table)
-        const bool stage_val = (MODE == kModeGCN) || (MODE == kModeGATBWD && p.att == nullptr);
+        // and for its second pass, whose "values" are the positions t_perm of the edges in CSR order
+        const bool stage_val = (MODE == kModeGCN) || (MODE == kModeGATBWD && p.att == nullptr) || (MODE == kModeGATBWD2);
         const uint32_t bar = smem_u32(&s_bar[warp]);
         if (nb > 0) {
             if (lane == 0) {
@@ -161,6 +176,9 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
         float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
         float den = 0.f;
         // MLP: projected feature of the destination row, P[dst, col..] (aggr_nn.h:26 `cached`, after projection)
+        // (Fetching it one row ahead, and carrying the row terms of the GAT backward in registers beside it, was measured
+        // on the arxiv shape and lost: 0.162 against 0.154 ms for the whole backward -- the walk is bound by how many
+        // warps an SM holds, 3 CTAs per SM cost another 0.015 ms, and the extra registers are not free.)
         float4 pd0 = make_float4(0.f, 0.f, 0.f, 0.f), pd1 = pd0;
         auto load_dst = [&](int r) {
             const float *q = p.P + (size_t)(SCHED ? __ldg(p.target + r) : r) * F + col;
@@ -189,7 +207,7 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
                 float *c = p.carry + (size_t)item * F + col;
                 if (act0) stg_f4(c, acc0);
                 if (act1) stg_f4(c + LPR * 4, acc1);
-                if (MODE == kModeGAT && vl == 0 && cb == 0) p.carry_den[item] = den;
+                if (mode_gat_like(MODE) && vl == 0 && cb == 0) p.carry_den[item] = den;
                 carry_in = false;
             } else {
                 float *y = p.Y + (size_t)((MODE == kModeGCN && p.out_row) ? __ldg(p.out_row + row) : row) * F + col;
@@ -199,6 +217,7 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
                     acc0 = make_float4(acc0.x * inv, acc0.y * inv, acc0.z * inv, acc0.w * inv);
                     acc1 = make_float4(acc1.x * inv, acc1.y * inv, acc1.z * inv, acc1.w * inv);
                 }
+                if (MODE == kModeGATBWD2 && vl == 0 && cb == 0) p.rsum[(size_t)row * p.rsum_stride] = den;  // complete row
                 if (MODE == kModeGCN && p.accumulate) {  // each row is stored by exactly one item: plain RMW is safe
                     // a lane whose partial sum is exactly zero has nothing to add: rows without edges in this sub-CSR
                     // (most rows of a source slice of a low-degree graph) cost no traffic on Y
@@ -241,6 +260,39 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
         // per-edge combination of the gathered row (u is a compile-time constant after unrolling)
         float dd[U];  // SDDMM: this lane's partial dot products of the batch
         int drow[U];  // GAT backward: destination row of every edge of the batch (uniform over the virtual warp)
+        // GAT backward, pass 1: (sum w, sum t) of row `srow`.  Every writer lane keeps the part of its own edges; the
+        // virtual warp adds the parts up (fixed butterfly order) only when the row changes or the item ends.  The row
+        // that enters the item leaves the sums in bwd_carry[item], a row that starts here in bwd_part[row].
+        float s_w = 0.f, s_t = 0.f;
+        int srow = -1;
+        bool s_carry = carry_in;
+        auto sum_flush = [&]() {
+            if (srow >= 0) {
+                float tw = s_w, tt = s_t;
+#pragma unroll
+                for (int off = LPR / 2; off >= 1; off >>= 1) {
+                    tw += __shfl_xor_sync(vw_mask, tw, off, LPR);
+                    tt += __shfl_xor_sync(vw_mask, tt, off, LPR);
+                }
+                if (vl == 0) {
+                    if (s_carry)
+                        p.bwd_carry[item] = make_float2(tw, tt);
+                    else
+                        p.bwd_part[srow] = make_float2(tw, tt);
+                }
+                s_carry = false;
+            }
+            s_w = s_t = 0.f;
+        };
+        // GAT backward, pass 2: (alpha_e, ds_e) of the staged edge k: (w, t) through the staged position of the edge in
+        // CSR order, times 1 / D_v of its destination v = the column index of the transposed CSR
+        auto edge_terms = [&](const int k, float &alpha, float &ds) {
+            const int pe = __float_as_int(my_val[k]);
+            const float2 wt = __ldg(reinterpret_cast<const float2 *>(p.bwd_wt) + pe);
+            const float inv = __ldg(&p.bwd_c[my_idx[k]].x);
+            alpha = wt.x * inv;
+            ds = wt.y * inv;
+        };
         auto combine = [&](const int u, const float wu, const float4 &a0, const float4 &a1) {
             if (MODE == kModeMLP) {
                 relu_add4(acc0, pd0, a0);
@@ -254,43 +306,67 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
             }
         };
         // SDDMM: totals of the batch's dot products (reduce-scatter over the virtual warp) -> out[e .. e+nb)
-        auto sddmm_emit = [&](const int nb) {
+        // same_row: all nb edges of the batch belong to the current `row` (no row ended inside the batch)
+        auto sddmm_emit = [&](const int nb, const bool same_row) {
             const int id = vl / (LPR / U);
             const bool writer = (vl % (LPR / U)) == 0 && id < nb;
             // GAT backward: everything the epilogue needs besides g_e is fetched before the shuffles
             float sv = 0.f, a_v = 0.f;
             float2 ri = make_float2(0.f, 0.f);
             if (MODE == kModeGATBWD && writer && cb + CHUNK >= F) {
-                int v = drow[0];
-#pragma unroll
-                for (int u = 1; u < U; ++u)
-                    if (id == u) v = drow[u];
                 sv = (p.att != nullptr) ? __ldg(p.att + 2 * (size_t)my_idx[e + id - wbase] + 1)  // source attention term
                                         : my_val[e + id - wbase];                                  // handed-in weight
+                int v = row;  // row of this writer's edge: the current one unless a row ended inside the batch
+                if (!same_row) {
+                    v = drow[0];
+#pragma unroll
+                    for (int u = 1; u < U; ++u)
+                        if (id == u) v = drow[u];
+                }
                 ri = __ldg(p.bwd_c + v);
                 if (p.att != nullptr) a_v = __ldg(p.att + 2 * (size_t)v);
             }
             VwReduceScatter<LPR, LPR / 2, U>::run(dd, vl, vw_mask);
+            float mw = 0.f, mt = 0.f;  // GAT backward: (w, t) of this writer's edge
             if (writer) {
                 if (MODE == kModeSDDMM) {
                     float *o = p.newval + e + id;
                     *o = (cb == 0) ? dd[0] : *o + dd[0];  // wide rows: column chunks accumulate
                 } else {
-                    float *o = p.bwd_ds + e + id;
-                    const float g = (cb == 0) ? dd[0] : *o + dd[0];
+                    float2 *o = p.bwd_wt + e + id;
+                    const float g = (cb == 0) ? dd[0] : o->y + dd[0];
                     if (cb + CHUNK < F) {
-                        *o = g;  // more column chunks to come
+                        o->y = g;  // more column chunks to come
                     } else {
-                        float w = sv;         // handed in: newval of aggr_gat_fine; s > 0 <=> w > 1
+                        mw = sv;              // handed in: newval of aggr_gat_fine; s > 0 <=> w > 1
                         bool pos = sv > 1.f;
                         if (p.att != nullptr) {
                             const float sc = a_v + sv;
                             pos = sc > 0.f;
-                            w = __expf(fmaxf(sc, sc * p.slope));  // aggr_gat.h:190
+                            mw = __expf(fmaxf(sc, sc * p.slope));  // aggr_gat.h:190
                         }
-                        const float alpha = w * ri.x;
-                        p.newval[e + id] = alpha;
-                        *o = alpha * (g - ri.y) * (pos ? 1.f : p.slope);  // :287-289
+                        mt = mw * (g - ri.y) * (pos ? 1.f : p.slope);  // :287-289, times D_v
+                        *o = make_float2(mw, mt);
+                    }
+                }
+            }
+            if (MODE == kModeGATBWD && cb + CHUNK >= F) {
+                if (same_row && row == srow) {
+                    s_w += mw;  // zero on the lanes that hold no edge
+                    s_t += mt;
+                } else {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (u < nb) {
+                            if (drow[u] != srow) {
+                                sum_flush();
+                                srow = drow[u];
+                            }
+                            if (writer && id == u) {
+                                s_w += mw;
+                                s_t += mt;
+                            }
+                        }
                     }
                 }
             }
@@ -306,10 +382,12 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
             for (int u = 0; u < U; ++u) {
                 const int k = min(e + u, e1 - 1) - wbase;
                 src[u] = my_idx[k];
-                w[u] = (mode_has_dst(MODE) || MODE == kModeGAT) ? 0.f : my_val[k];
+                w[u] = (mode_has_dst(MODE) || mode_gat_like(MODE)) ? 0.f : my_val[k];
             }
             float a_src = 0.f;  // GAT: source attention term of edge min(e + vl, e1 - 1), lanes vl < U
             if (MODE == kModeGAT && vl < U) a_src = __ldg(p.att + 2 * (size_t)my_idx[min(e + vl, e1 - 1) - wbase] + 1);
+            float ds_lane = 0.f;  // GAT backward, pass 2: lane vl < U forms (alpha, ds) of that edge; a_src carries alpha
+            if (MODE == kModeGATBWD2 && vl < U) edge_terms(min(e + vl, e1 - 1) - wbase, a_src, ds_lane);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const char *x = xb + (size_t)(uint32_t)src[u] * row_bytes;
@@ -320,9 +398,12 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 float wu = w[u];
-                if (MODE == kModeGAT) wu = __shfl_sync(vw_mask, a_src, u, LPR);  // all lanes of the virtual warp, every u
+                if (mode_gat_like(MODE)) wu = __shfl_sync(vw_mask, a_src, u, LPR);  // all lanes of the virtual warp, every u
+                float du = 0.f;
+                if (MODE == kModeGATBWD2) du = __shfl_sync(vw_mask, ds_lane, u, LPR);
                 if (u < nb) {
                     while (row_end == e + u) flush(false);
+                    if (MODE == kModeGATBWD2) den += du;
                     if (MODE == kModeGAT) {
                         const float sc = a_dst + wu;
                         wu = __expf(fmaxf(sc, sc * p.slope));
@@ -337,7 +418,7 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
             if (MODE == kModeGAT && SCHED && cb == 0 && p.newval != nullptr) {
                 if (vl < nb) p.newval[e + vl] = wout;
             }
-            if (mode_emits_edges(MODE)) sddmm_emit(nb);
+            if (mode_emits_edges(MODE)) sddmm_emit(nb, false);
             e += nb;
         };
 
@@ -354,7 +435,7 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
 #pragma unroll
             for (int q = 0; q < U / 4; ++q) {
                 const int4 i4 = lds_i4(s_base + 4u * (uint32_t)(k + 4 * q));
-                const float4 w4 = (mode_has_dst(MODE) || MODE == kModeGAT)
+                const float4 w4 = (mode_has_dst(MODE) || mode_gat_like(MODE))
                                       ? make_float4(0.f, 0.f, 0.f, 0.f)
                                       : lds_f4(s_base + 4u * (uint32_t)(k + 4 * q + kWarpEdges));
                 src[4 * q] = i4.x, src[4 * q + 1] = i4.y, src[4 * q + 2] = i4.z, src[4 * q + 3] = i4.w;
@@ -362,6 +443,8 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
             }
             float a_src = 0.f;  // GAT: source attention term of edge e + vl (lanes vl < U), in flight with the row gathers
             if (MODE == kModeGAT && vl < U) a_src = __ldg(p.att + 2 * (size_t)my_idx[k + vl] + 1);
+            float ds_lane = 0.f;  // pass 2 of the GAT backward: (alpha, ds) of edge e + vl, a_src carries alpha
+            if (MODE == kModeGATBWD2 && vl < U) edge_terms(k + vl, a_src, ds_lane);
             float4 v0[U], v1[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -370,6 +453,7 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
                 if (NV > 1) v1[u] = __ldg(reinterpret_cast<const float4 *>(x + second));
             }
             float wout = 0.f;
+            const bool whole = row_end - e >= U;  // no row ends inside the batch
             if (MODE == kModeGAT && row_end - e >= U) {
                 // no row ends inside the batch: lane u of the virtual warp evaluates the weight of edge u once
                 // (one MUFU per edge instead of one per edge-lane) and the virtual warp shares it by shuffle
@@ -386,7 +470,15 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
                     if (NV > 1) fma4(acc1, wu, v1[u]);
                 }
                 wout = wgt;
-            } else if (MODE != kModeGAT && row_end - e >= U) {
+            } else if (MODE == kModeGATBWD2 && row_end - e >= U) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    den += __shfl_sync(vw_mask, ds_lane, u, LPR);
+                    const float wu = __shfl_sync(vw_mask, a_src, u, LPR);
+                    fma4(acc0, wu, v0[u]);
+                    if (NV > 1) fma4(acc1, wu, v1[u]);
+                }
+            } else if (!mode_gat_like(MODE) && row_end - e >= U) {
                 // no row ends inside the batch: straight FMA chain
 #pragma unroll
                 for (int u = 0; u < U; ++u) combine(u, w[u], v0[u], v1[u]);
@@ -395,6 +487,10 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
                 for (int u = 0; u < U; ++u) {
                     while (row_end == e + u) flush(false);
                     float wu = w[u];
+                    if (MODE == kModeGATBWD2) {
+                        wu = __shfl_sync(vw_mask, a_src, u, LPR);
+                        den += __shfl_sync(vw_mask, ds_lane, u, LPR);
+                    }
                     if (MODE == kModeGAT) {
                         const float sc = a_dst + __shfl_sync(vw_mask, a_src, u, LPR);
                         wu = __expf(fmaxf(sc, sc * p.slope));  // aggr_gat.h:143
@@ -408,7 +504,7 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
                 // one coalesced store per batch instead of one per edge (U <= LPR always holds)
                 if (vl < U) p.newval[e + vl] = wout;
             }
-            if (mode_emits_edges(MODE)) sddmm_emit(U);
+            if (mode_emits_edges(MODE)) sddmm_emit(U, whole);
             e += U;
         }
 
@@ -417,6 +513,7 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
         // item end
         if (mode_emits_edges(MODE)) {
             // per-edge outputs were written batch by batch
+            if (MODE == kModeGATBWD && cb + CHUNK >= F) sum_flush();
         } else if (row_end == e1) {
             while (row < p.row_hi && row_end == e1) flush(true);  // row closes here (+ trailing empty rows)
         } else if (SCHED) {
@@ -425,7 +522,7 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
             float *c = p.carry + (size_t)item * F + col;  // row spans the whole item
             if (act0) stg_f4(c, acc0);
             if (act1) stg_f4(c + LPR * 4, acc1);
-            if (MODE == kModeGAT && vl == 0 && cb == 0) p.carry_den[item] = den;
+            if (mode_gat_like(MODE) && vl == 0 && cb == 0) p.carry_den[item] = den;
         } else {
             // row starts here and continues: raw partial
             float *y = p.Y + (size_t)((MODE == kModeGCN && p.out_row) ? __ldg(p.out_row + row) : row) * F + col;
@@ -436,7 +533,7 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
                 if (act0) stg_f4(y, acc0);
                 if (act1) stg_f4(y + LPR * 4, acc1);
             }
-            if (MODE == kModeGAT && vl == 0 && cb == 0) p.den_row[row] = den;
+            if (mode_gat_like(MODE) && vl == 0 && cb == 0) p.den_row[row] = den;
         }
     }
 }
@@ -456,11 +553,12 @@ __device__ __forceinline__ void fixup_sum(const AggParams &p, int row, int64_t i
 {
     const int F = p.F;
     float dsum = 0.f, inv = 1.f;
-    if (MODE == kModeGAT) {
+    if (mode_gat_like(MODE)) {
         for (int64_t b = b0; b <= b1; b += step) dsum += p.carry_den[b];
         if (finish) {
             dsum += p.den_row[row];
             inv = (dsum != 0.f) ? __fdividef(1.f, dsum) : 0.f;
+            if (MODE == kModeGATBWD2 && lane == 0) p.rsum[(size_t)row * p.rsum_stride] = dsum;  // a plain row sum
         }
     }
     for (int col = lane * 4; col < F; col += 128) {
@@ -476,7 +574,7 @@ __device__ __forceinline__ void fixup_sum(const AggParams &p, int row, int64_t i
         for (; b <= b1; b += step) acc = add4(acc, *reinterpret_cast<const float4 *>(p.carry + (size_t)b * F + col));
         if (finish) {
             float *y = p.Y + (size_t)((MODE == kModeGCN && p.out_row) ? __ldg(p.out_row + row) : row) * F + col;
-            if (MODE == kModeGCN) {
+            if (MODE == kModeGCN || MODE == kModeGATBWD2) {
                 red_add_f4(y, acc);  // one add per element and launch: deterministic, and no wait for Y
             } else {
                 acc = add4(*reinterpret_cast<const float4 *>(y), acc);
@@ -487,7 +585,7 @@ __device__ __forceinline__ void fixup_sum(const AggParams &p, int row, int64_t i
             stg_f4(p.carry + (size_t)item * F + col, acc);  // chunk head now holds the chunk sum
         }
     }
-    if (MODE == kModeGAT && !finish && lane == 0) p.carry_den[item] = dsum;
+    if (mode_gat_like(MODE) && !finish && lane == 0) p.carry_den[item] = dsum;
 }
 
 // PHASE 1: one warp per item of the launched range.  What an item has to do depends on the graph and the item size
@@ -498,6 +596,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256) agg_fixup_kernel(const AggParams p, int EB, int64_t num_items,
                                                         const int2 *__restrict__ records)
 {
+    griddep_wait();
     // items of the launched edge range only; the first one is clipped at a row start, so nothing enters it
     const int64_t item = (int64_t)(p.edge_lo / EB) + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (item < 1 || item >= num_items || item * EB >= p.edge_hi || item * EB <= p.edge_lo) return;
@@ -534,6 +633,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256) agg_fixup_long_kernel(const AggParams p, int EB, const int *__restrict__ long_rows,
                                                              int num_long)
 {
+    griddep_wait();
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= num_long) return;
     const int row = __ldg(long_rows + w);

@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -50,6 +51,40 @@ static int ensure(T *&p, size_t &cap, size_t need)
 }
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Programmatic dependent launch for the short kernels that follow a traversal (fix-up passes, the row-final kernel and
+// the second pass of the GAT backward): the launch is processed and the grid scheduled while the predecessor's last
+// CTAs drain; the kernel itself waits (griddep_wait) before it reads.  GNNAGG_PDL=0 turns the attribute off.
+static bool pdl_enabled()
+{
+    static const bool on = [] {
+        const char *e = getenv("GNNAGG_PDL");
+        return e ? atoi(e) != 0 : true;
+    }();
+    return on;
+}
+
+template <class... KArgs, class... Args>
+static void launch_dep_smem(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args &&...args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);  // errors surface in the caller's LAUNCH_CHECK
+}
+
+template <class... KArgs, class... Args>
+static void launch_dep(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, Args &&...args)
+{
+    launch_dep_smem(kernel, grid, block, 0, st, static_cast<Args &&>(args)...);
+}
 
 }  // namespace gnnagg
 
@@ -109,8 +144,11 @@ struct gnnagg_aggregator {
     gnnagg_aggregator *tr = nullptr;
     float *t_val = nullptr;    // edge values in transposed order (owned, m floats)
     const float *t_val_of = nullptr;  // which d_val t_val currently mirrors (NULL: none / attention weights)
-    float *bwd_g = nullptr, *bwd_c = nullptr, *bwd_t = nullptr;
-    size_t bwd_g_cap = 0, bwd_c_cap = 0, bwd_t_cap = 0;
+    // GAT backward scratch: per row (1 / D_v, c_v); per edge (w_e, t_e); pass-1 row sums per row / per entered item
+    float2 *bwd_c = nullptr, *bwd_wt = nullptr, *bwd_part = nullptr, *bwd_carry = nullptr;
+    size_t bwd_c_cap = 0, bwd_wt_cap = 0, bwd_part_cap = 0, bwd_carry_cap = 0;
+    float *bwd_t = nullptr;  // large graphs: ds_e in transposed edge order (alpha_e goes to t_val)
+    size_t bwd_t_cap = 0;
     // host-buffer entry points: the result is copied back per row chunk on a second stream while the next chunk computes
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -243,14 +281,20 @@ static void launch_agg_we(const AggParams &p, cudaStream_t st)
     const int F = p.F;
     const int64_t first = (int64_t)(p.edge_lo / WE) * WE;  // warps keep their global 512-edge alignment (TMA staging)
     const unsigned grid = (unsigned)cdiv(p.edge_hi - first, (int64_t)WE * kCtaWarps);
+    auto go = [&](void (*kernel)(const AggParams)) {
+        if (MODE == kModeGATBWD || MODE == kModeGATBWD2)
+            launch_dep(kernel, grid, kCtaThreads, st, p);
+        else
+            kernel<<<grid, kCtaThreads, 0, st>>>(p);
+    };
     if (F <= 32)
-        agg_kernel<8, 1, MODE, SCHED, WE><<<grid, kCtaThreads, 0, st>>>(p);
+        go(agg_kernel<8, 1, MODE, SCHED, WE>);
     else if (F <= 64)
-        agg_kernel<16, 1, MODE, SCHED, WE><<<grid, kCtaThreads, 0, st>>>(p);
+        go(agg_kernel<16, 1, MODE, SCHED, WE>);
     else if (F <= 128)
-        agg_kernel<32, 1, MODE, SCHED, WE><<<grid, kCtaThreads, 0, st>>>(p);
+        go(agg_kernel<32, 1, MODE, SCHED, WE>);
     else
-        agg_kernel<32, 2, MODE, SCHED, WE><<<grid, kCtaThreads, 0, st>>>(p);
+        go(agg_kernel<32, 2, MODE, SCHED, WE>);
 }
 
 // CUDA loads a kernel lazily at its first launch, and that load can wait for the device to go idle.  A process that
@@ -341,10 +385,10 @@ static int launch_agg(gnnagg_aggregator *a, AggParams p, cudaStream_t st)
             const int2 *records = nullptr;
             int num_long = 0;
             if (int rc = long_rows_of(a, p, EB, st, &list, &num_long, &records)) return rc;
-            agg_fixup_kernel<MODE><<<(unsigned)cdiv(range_items, 8), 256, 0, st>>>(p, EB, items, records);
+            launch_dep(agg_fixup_kernel<MODE>, (unsigned)cdiv(range_items, 8), 256, st, p, EB, items, records);
             LAUNCH_CHECK(a);
             if (num_long > 0) {
-                agg_fixup_long_kernel<MODE><<<(unsigned)cdiv(num_long, 8), 256, 0, st>>>(p, EB, list, num_long);
+                launch_dep(agg_fixup_long_kernel<MODE>, (unsigned)cdiv(num_long, 8), 256, st, p, EB, list, num_long);
                 LAUNCH_CHECK(a);
             }
         }
@@ -744,6 +788,7 @@ static void free_transpose(gnnagg_aggregator *a)
         cudaFree(a->tr->d_item_row);
         cudaFree(a->tr->carry);
         cudaFree(a->tr->carry_den);
+        cudaFree(a->tr->den_row);
         free_long_rows(a->tr);
         delete a->tr;
         a->tr = nullptr;
@@ -834,8 +879,10 @@ int gnnagg_destroy(gnnagg_aggregator *a)
         if (a->in_done[i]) cudaEventDestroy(a->in_done[i]);
     if (a->in_free) cudaEventDestroy(a->in_free);
     if (a->in_stream) cudaStreamDestroy(a->in_stream);
-    cudaFree(a->bwd_g);
     cudaFree(a->bwd_c);
+    cudaFree(a->bwd_wt);
+    cudaFree(a->bwd_part);
+    cudaFree(a->bwd_carry);
     cudaFree(a->bwd_t);
     cudaFree(a->d_item_row);
     cudaFree(a->carry);
@@ -1275,38 +1322,38 @@ int gnnagg_gat_backward(gnnagg_aggregator *a, const float *X, const float *att, 
     if (!aligned16(X) || !aligned16(Y) || !aligned16(dY) || !aligned16(dX))
         return set_error(GNNAGG_ERR_ARG, "X, Y, dY and dX must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
+    // every row < n gets its destination half and every row < num_src its source half from the kernels below; only a
+    // rectangular block leaves entries of the [max(n, num_src), 2] table that nobody writes
     const int rows = a->n > a->num_src ? a->n : a->num_src;
-    CUDA_TRY(cudaMemsetAsync(datt, 0, (size_t)rows * 2 * sizeof(float), st));
+    if (a->n != a->num_src || a->m == 0) CUDA_TRY(cudaMemsetAsync(datt, 0, (size_t)rows * 2 * sizeof(float), st));
     if (a->m == 0) {
         CUDA_TRY(cudaMemsetAsync(dX, 0, (size_t)a->num_src * feat * sizeof(float), st));
         return GNNAGG_OK;
     }
-    if (int rc = ensure(a->newval, a->newval_cap, (size_t)a->m)) return rc;
-    if (int rc = ensure(a->bwd_g, a->bwd_g_cap, (size_t)a->m)) return rc;
-    if (int rc = ensure(a->bwd_c, a->bwd_c_cap, (size_t)a->n * 2)) return rc;
-    if (int rc = ensure(a->bwd_t, a->bwd_t_cap, (size_t)a->m)) return rc;
-    if (int rc = ensure(a->den_row, a->den_row_cap, (size_t)a->n)) return rc;
-    // 1. D_v = row sums of the un-normalised weights, computed on the fly from the attention table (or from w)
-    const float *dn = den;
-    if (!dn) {
-        if (int rc = att ? rowsum_impl<kSumWeights>(a, att, a->den_row, st, 1, slope) : rowsum_impl(a, w, a->den_row, st))
-            return rc;
-        dn = a->den_row;
-    }
-    // 2. per row: (1 / D_v, c_v = <Y[v], dY[v]>)
-    gat_bwd_rowinfo_kernel<<<(unsigned)cdiv((int64_t)a->n * 8, 256), 256, 0, st>>>(Y, dY, dn, reinterpret_cast<float2 *>(a->bwd_c),
-                                                                                 a->n, feat);
+    gnnagg_aggregator *t = a->tr;
+    const int EB = item_edges_for(a, feat, a->m);
+    const int EBt = item_edges_for(t, feat, a->m);
+    if (int rc = ensure(a->bwd_c, a->bwd_c_cap, (size_t)a->n)) return rc;
+    if (int rc = ensure(a->bwd_wt, a->bwd_wt_cap, (size_t)a->m)) return rc;
+    if (int rc = ensure(a->bwd_part, a->bwd_part_cap, (size_t)a->n)) return rc;
+    if (int rc = ensure(a->bwd_carry, a->bwd_carry_cap, (size_t)cdiv(a->m, EB) + 1)) return rc;
+    if (int rc = ensure(t->carry, t->carry_cap, (size_t)cdiv(a->m, EBt) * feat)) return rc;
+    if (int rc = ensure(t->carry_den, t->carry_den_cap, (size_t)cdiv(a->m, EBt))) return rc;
+    if (int rc = ensure(t->den_row, t->den_row_cap, (size_t)a->num_src)) return rc;
+    // 1. per destination row: c_v = <Y[v], dY[v]>
+    gat_bwd_rowinfo_kernel<<<(unsigned)cdiv((int64_t)a->n * 8, 256), 256, 0, st>>>(Y, dY, a->bwd_c, a->n, feat);
     LAUNCH_CHECK(a);
-    // 3. the SDDMM traversal g_e = <X[u], dY[v]> with the edge epilogue fused in: alpha_e -> newval, ds_e -> bwd_g
+    // 2. pass 1 over the CSR: g_e = <X[u], dY[v]> (the SDDMM traversal), per edge (w_e, t_e), per row their sums
     {
         AggParams p{};
         p.X = X;
         p.P = dY;
         p.att = att;
         p.val = w;
-        p.bwd_c = reinterpret_cast<const float2 *>(a->bwd_c);
-        p.bwd_ds = a->bwd_g;
-        p.newval = a->newval;
+        p.bwd_c = a->bwd_c;
+        p.bwd_wt = a->bwd_wt;
+        p.bwd_part = a->bwd_part;
+        p.bwd_carry = a->bwd_carry;
         p.F = feat;
         p.slope = slope;
         p.ptr = a->d_ptr;
@@ -1318,18 +1365,51 @@ int gnnagg_gat_backward(gnnagg_aggregator *a, const float *X, const float *att, 
         p.bulk_ok = aligned16(p.idx) && (att || aligned16(w));
         if (int rc = launch_agg<kModeGATBWD, false>(a, p, st)) return rc;
     }
-    // 4. destination half of the attention gradient: row sums of ds
-    if (int rc = rowsum_impl(a, a->bwd_g, datt, st, 2)) return rc;
-    // 5. alpha and ds into the edge order of the transposed CSR (one pass over the permutation)
-    gather2_kernel<<<(unsigned)cdiv(a->m, 256), 256, 0, st>>>(a->newval, a->bwd_g, a->t_perm, a->t_val, a->bwd_t, a->m);
+    // 3. rows closed: 1 / D_v and the destination half of the attention gradient
+    launch_dep(gat_bwd_rowfinal_kernel, (unsigned)cdiv((int64_t)a->n * 8, 256), 256, st, a->d_ptr, a->bwd_part, a->bwd_carry,
+               den, a->bwd_c, datt, a->n, EB);
     LAUNCH_CHECK(a);
-    a->t_val_of = nullptr;
-    // 6. source half = row sums over the transposed CSR;  dX[u] = sum_e alpha_e dY[v] = the aggregation kernel over it
-    const int64_t before = a->tr->launches;
-    int rc = rowsum_impl(a->tr, a->bwd_t, datt + 1, st, 2);
-    if (rc == GNNAGG_OK) rc = gcn_run_core(a->tr, dY, dX, feat, 0, st);
-    a->launches += a->tr->launches - before;
-    return rc;
+    if (a->m >= kSmallGraphEdges) {
+        // 4a. large graphs: (w, t) permuted into transposed order by a streaming kernel, then the source half as a row sum
+        //     and dX as the plain aggregation over the transposed CSR with edge values alpha
+        if (int rc = ensure(a->bwd_t, a->bwd_t_cap, (size_t)a->m)) return rc;
+        launch_dep(gat_bwd_permute_kernel, (unsigned)cdiv(a->m, 256), 256, st, (const float2 *)a->bwd_wt, (const int *)a->t_perm,
+                   (const int *)a->t_idx, (const float2 *)a->bwd_c, a->t_val, a->bwd_t, a->m);
+        LAUNCH_CHECK(a);
+        a->t_val_of = nullptr;  // t_val no longer mirrors the GCN edge values
+        const int64_t before = t->launches;
+        int rc = rowsum_impl(t, a->bwd_t, datt + 1, st, 2);
+        if (rc == GNNAGG_OK) rc = gcn_run_core(t, dY, dX, feat, 0, st);
+        a->launches += t->launches - before;
+        return rc;
+    }
+    // 4b. pass 2 over the transposed CSR: dX[u] = sum_e alpha_e dY[v] and the source half sum_e ds_e, weights formed on
+    //     the fly from (w, t) through t_perm and 1 / D_v ((w, t) of a small graph stays in L2)
+    {
+        AggParams p{};
+        p.X = dY;
+        p.Y = dX;
+        p.val = reinterpret_cast<const float *>(a->t_perm);
+        p.bwd_c = a->bwd_c;
+        p.bwd_wt = a->bwd_wt;
+        p.rsum = datt + 1;
+        p.rsum_stride = 2;
+        p.F = feat;
+        p.ptr = t->d_ptr;
+        p.idx = t->d_idx;
+        p.item_row = t->d_item_row;
+        p.carry = t->carry;
+        p.carry_den = t->carry_den;
+        p.den_row = t->den_row;
+        p.num_rows = t->n;
+        p.num_edges = t->m;
+        p.num_fine_items = t->num_items;
+        p.bulk_ok = aligned16(p.idx) && aligned16(p.val);
+        const int64_t before = t->launches;
+        const int rc = launch_agg<kModeGATBWD2, false>(t, p, st);
+        a->launches += t->launches - before;
+        return rc;
+    }
 }
 
 int gnnagg_sample_subgraph(gnnagg_aggregator *a, int *d_active, int fanout, int layer_num, uint64_t seed, int **d_vertexset,

@@ -89,6 +89,12 @@ __device__ __forceinline__ uint64_t opaque64(uint64_t x)
     return y;
 }
 
+// Programmatic dependent launch: a kernel launched with the programmatic-serialisation attribute (capi.cu: launch_dep)
+// may be scheduled while its predecessor in the stream drains; it must not touch what the predecessor wrote before this
+// returns.  Without the attribute the instruction is a no-op.  Every thread calls it, ahead of any early return, so that
+// the completion of the dependent grid always implies the completion of its predecessor.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- vector loads / stores -------------------------------------------------------------------
 __device__ __forceinline__ float4 ldg_f4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 __device__ __forceinline__ void stg_f4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }

@@ -163,11 +163,10 @@ __global__ void __launch_bounds__(256) rowsum_fixup_kernel(const EdgeParams g, f
         carry[item] = acc;
 }
 
-// Per-row terms of the GAT backward, out[v] = (1 / D_v, c_v = <Y[v,:], dY[v,:]>): 8 lanes per row, float4 per lane
-// (the `res` of aggr_gat_fine_bwd, aggr_gat.h:275-283, and the division by `thediv`, :244).  Rows without edges get 0.
+// Per-row term of the GAT backward that the edge pass needs, out[v] = (0, c_v = <Y[v,:], dY[v,:]>): 8 lanes per row,
+// float4 per lane (the `res` of aggr_gat_fine_bwd, aggr_gat.h:275-283).  The x half is filled by the row-final kernel.
 __global__ void __launch_bounds__(256) gat_bwd_rowinfo_kernel(const float *__restrict__ Y, const float *__restrict__ dY,
-                                                              const float *__restrict__ den, float2 *__restrict__ out,
-                                                              int num_rows, int F)
+                                                              float2 *__restrict__ out, int num_rows, int F)
 {
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     const int sub = threadIdx.x & 7;
@@ -177,22 +176,66 @@ __global__ void __launch_bounds__(256) gat_bwd_rowinfo_kernel(const float *__res
     acc += __shfl_xor_sync(0xffffffffu, acc, 4);
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (row < num_rows && sub == 0) out[row] = make_float2(0.f, acc);
+}
+
+// Closes the rows after pass 1 of the GAT backward (agg_kernel<kModeGATBWD>): adds, in a fixed order, the (sum w, sum t)
+// partials a row left in the item where it starts (part[v]) and in every EB-edge item it enters (carry[]), then
+// rowinfo[v].x = 1 / D_v (the division by `thediv`, aggr_gat.h:244; `den` when the caller hands D_v in) and the
+// destination half of the attention gradient d att[2v] = (sum t) / D_v.  8 lanes per row; rows without edges get 0.
+__global__ void __launch_bounds__(256) gat_bwd_rowfinal_kernel(const int *__restrict__ ptr, const float2 *__restrict__ part,
+                                                               const float2 *__restrict__ carry, const float *__restrict__ den,
+                                                               float2 *__restrict__ rowinfo, float *__restrict__ datt,
+                                                               int num_rows, int EB)
+{
+    griddep_wait();
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int sub = threadIdx.x & 7;
+    float sw = 0.f, st = 0.f;
+    if (row < num_rows) {
+        const int rs = __ldg(ptr + row), re = __ldg(ptr + row + 1);
+        if (re > rs) {
+            const int last = (re - 1) / EB;
+            for (int b = rs / EB + 1 + sub; b <= last; b += 8) {
+                const float2 c = __ldg(carry + b);
+                sw += c.x;
+                st += c.y;
+            }
+            if (sub == 0) {
+                const float2 c = __ldg(part + row);
+                sw += c.x;
+                st += c.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 4; off >= 1; off >>= 1) {
+        sw += __shfl_xor_sync(0xffffffffu, sw, off);
+        st += __shfl_xor_sync(0xffffffffu, st, off);
+    }
     if (row < num_rows && sub == 0) {
-        const float d = __ldg(den + row);
-        out[row] = make_float2(d != 0.f ? __fdividef(1.f, d) : 0.f, acc);
+        const float d = den ? __ldg(den + row) : sw;
+        const float inv = d != 0.f ? __fdividef(1.f, d) : 0.f;
+        rowinfo[row].x = inv;
+        datt[2 * (size_t)row] = st * inv;
     }
 }
 
-// out0[j] = in0[perm[j]], out1[j] = in1[perm[j]]: two edge arrays into another edge order with one read of perm
-__global__ void __launch_bounds__(256) gather2_kernel(const float *__restrict__ in0, const float *__restrict__ in1,
-                                                      const int *__restrict__ perm, float *__restrict__ out0,
-                                                      float *__restrict__ out1, int count)
+// Large graphs, between the two passes of the GAT backward: (w, t) of every edge into transposed edge order and
+// normalised on the way, alpha[j] = w_e / D_v and ds[j] = t_e / D_v with e = perm[j], v = t_idx[j].  As a stream of
+// independent 8-byte gathers this runs at DRAM speed; fetched inside pass 2 (the small-graph variant, where (w, t) is
+// L2 resident) each batch of FMAs would wait for a DRAM round trip.
+__global__ void __launch_bounds__(256) gat_bwd_permute_kernel(const float2 *__restrict__ wt, const int *__restrict__ perm,
+                                                              const int *__restrict__ t_idx, const float2 *__restrict__ rowinfo,
+                                                              float *__restrict__ alpha, float *__restrict__ ds, int count)
 {
+    griddep_wait();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= count) return;
-    const int e = __ldg(perm + j);
-    out0[j] = __ldg(in0 + e);
-    out1[j] = __ldg(in1 + e);
+    const float2 v = __ldg(wt + __ldg(perm + j));
+    const float inv = __ldg(&rowinfo[__ldg(t_idx + j)].x);
+    alpha[j] = v.x * inv;
+    ds[j] = v.y * inv;
 }
 
 // edge-wise GCN aggregation: Y[dst] += X[src]*val[e], one virtual warp per edge and 128-bit

@@ -106,6 +106,54 @@ def test_gat_backward(gn, orc, cuda, gname, F):
     assert torch.equal(dX, dX2) and torch.equal(dA, dA2)  # deterministic: no float atomics
 
 
+def test_gat_backward_wide_rows(gn, orc, cuda):
+    """F > 256: pass 1 walks the feature columns in several chunks and keeps the partial dot products per edge"""
+    F = 320
+    ptr, idx = make_graph("medium", seed=12)
+    n, m = len(ptr) - 1, len(idx)
+    X, _ = rand_inputs(n, m, F, seed=91)
+    dY, _ = rand_inputs(n, m, F, seed=92)
+    att = _att(n, 93)
+    agg = gn.Aggregator(dev(ptr), dev(idx))
+    agg.transpose_build()
+    Xd, dYd, attd = dev(X), dev(dY), dev(att)
+    Y = agg.gat_run(Xd, attd, torch.empty((n, F), device=cuda))
+    dX, dA = agg.gat_backward(Xd, attd, Y, dYd, torch.empty((n, F), device=cuda), torch.empty((n, 2), device=cuda))
+    x64, a64, sx, sa = orc.gat_backward_f64(ptr, idx, att, X, dY)
+    assert rel_gate(dX.cpu().numpy(), x64, sx, TOL_X)[0] == 0
+    assert rel_gate(dA.cpu().numpy(), a64, sa, TOL_A)[0] == 0
+
+
+def test_gat_backward_large_graph_path(gn, orc, cuda):
+    """4.2 M edges: the 512-edge-per-warp kernels, and pass 2 as permute + row sum + plain aggregation (graphs whose
+    per-edge (w, t) array does not stay in L2), against the fp64 oracle on the whole graph"""
+    n, m, F = 150000, 4200000, 32
+    ptr_d, idx_d = synth.rmat_csr(n, m, seed=321, device=cuda)
+    ptr, idx = ptr_d.cpu().numpy(), idx_d.cpu().numpy()
+    X, _ = rand_inputs(n, 1, F, seed=95)
+    dY, _ = rand_inputs(n, 1, F, seed=96)
+    att = _att(n, 97)
+    agg = gn.Aggregator(ptr_d, idx_d)
+    agg.transpose_build()
+    Xd, dYd, attd = dev(X), dev(dY), dev(att)
+    Y = agg.gat_run(Xd, attd, torch.empty((n, F), device=cuda))
+    dX, dA = agg.gat_backward(Xd, attd, Y, dYd, torch.full((n, F), float("nan"), device=cuda),
+                              torch.full((n, 2), float("nan"), device=cuda))
+    x64, a64, sx, sa = orc.gat_backward_f64(ptr, idx, att, X, dY)
+    bad, worst = rel_gate(dX.cpu().numpy(), x64, sx, TOL_X)
+    assert bad == 0, ("dX", worst)
+    bad, worst = rel_gate(dA.cpu().numpy(), a64, sa, TOL_A)
+    assert bad == 0, ("datt", worst)
+    dX2, dA2 = agg.gat_backward(Xd, attd, Y, dYd, torch.empty((n, F), device=cuda), torch.empty((n, 2), device=cuda))
+    assert torch.equal(dX, dX2) and torch.equal(dA, dA2)
+    # the GCN backward still sees its own edge values afterwards (t_val was borrowed for alpha)
+    val = synth.gcn_norm_val(ptr_d, idx_d)
+    agg.set_val(val)
+    dXg = agg.gcn_backward(dYd, torch.empty((n, F), device=cuda))
+    d64, scale = orc.spmm_t_f64(ptr, idx, val.cpu().numpy(), dY, n)
+    assert rel_gate(dXg.cpu().numpy(), d64, scale, 1e-5)[0] == 0
+
+
 @pytest.mark.parametrize("slope", [0.2, 0.0, 1.0])
 def test_gat_backward_from_weights_and_rectangular(gn, orc, cuda, slope):
     """the run_bwd calling convention (w = newval of aggr_gat_fine, den = div; no attention table) and a
