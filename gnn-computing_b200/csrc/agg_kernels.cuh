@@ -86,6 +86,7 @@ __device__ __forceinline__ int item_start_row(const AggParams &p, int e0)
 }
 
 // WE = edges staged per warp: 512 normally, 128 for small graphs (4x more warps, shorter walks)
+// (5 resident CTAs per SM for the small-graph variant -- 48 registers -- measured on the arxiv shape: no change.)
 template <int LPR, int NV, int MODE, bool SCHED, int WE>
 __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(const AggParams p)
 {
@@ -539,7 +540,7 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
 }
 
 // Adds the carried partials of rows that cross item boundaries, in a fixed order (deterministic).
-// One warp per item.  Two passes so that a hub row spanning thousands of items is not summed by a
+// One virtual warp of min(32, F/4) lanes per item (F = 32: four items per warp).  Two passes so that a hub row spanning thousands of items is not summed by a
 // single warp:  PHASE 1 -- every kFixChunk-th carry item of a row ("chunk head") sums its chunk of up
 // to kFixChunk consecutive partials; rows whose whole span fits one chunk are finished here.
 // PHASE 2 -- one warp per long row adds the chunk heads and finishes the row.
@@ -549,7 +550,7 @@ constexpr int kFixChunk = 32;
 // Y[row] (GAT: and normalises), otherwise the total replaces carry[item]
 template <int MODE>
 __device__ __forceinline__ void fixup_sum(const AggParams &p, int row, int64_t item, int64_t b0, int64_t b1, int64_t step,
-                                          bool finish, int lane)
+                                          bool finish, int lane, int lanes = 32)
 {
     const int F = p.F;
     float dsum = 0.f, inv = 1.f;
@@ -561,7 +562,7 @@ __device__ __forceinline__ void fixup_sum(const AggParams &p, int row, int64_t i
             if (MODE == kModeGATBWD2 && lane == 0) p.rsum[(size_t)row * p.rsum_stride] = dsum;  // a plain row sum
         }
     }
-    for (int col = lane * 4; col < F; col += 128) {
+    for (int col = lane * 4; col < F; col += lanes * 4) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         int64_t b = b0;
         for (; b + 3 * step <= b1; b += 4 * step) {
@@ -594,16 +595,16 @@ __device__ __forceinline__ void fixup_sum(const AggParams &p, int row, int64_t i
 // One dependent load instead of the item_row -> ptr[row], ptr[row+1] chain in front of the carry loads.
 template <int MODE>
 __global__ void __launch_bounds__(256) agg_fixup_kernel(const AggParams p, int EB, int64_t num_items,
-                                                        const int2 *__restrict__ records)
+                                                        const int2 *__restrict__ records, int lanes)
 {
     griddep_wait();
     // items of the launched edge range only; the first one is clipped at a row start, so nothing enters it
-    const int64_t item = (int64_t)(p.edge_lo / EB) + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t item = (int64_t)(p.edge_lo / EB) + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / lanes;
     if (item < 1 || item >= num_items || item * EB >= p.edge_hi || item * EB <= p.edge_lo) return;
     const int2 rec = __ldg(records + item);
     if (rec.x < 0) return;  // no row enters this item, or it is not a chunk head
     const int size = rec.y < 0 ? -rec.y : rec.y;
-    fixup_sum<MODE>(p, rec.x, item, item, item + size - 1, 1, rec.y < 0, threadIdx.x & 31);
+    fixup_sum<MODE>(p, rec.x, item, item, item + size - 1, 1, rec.y < 0, threadIdx.x % lanes, lanes);
 }
 
 __global__ void __launch_bounds__(256) fixup_records_kernel(const AggParams p, int EB, int64_t num_items, int2 *__restrict__ records)

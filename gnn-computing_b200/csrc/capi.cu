@@ -385,7 +385,8 @@ static int launch_agg(gnnagg_aggregator *a, AggParams p, cudaStream_t st)
             const int2 *records = nullptr;
             int num_long = 0;
             if (int rc = long_rows_of(a, p, EB, st, &list, &num_long, &records)) return rc;
-            launch_dep(agg_fixup_kernel<MODE>, (unsigned)cdiv(range_items, 8), 256, st, p, EB, items, records);
+            const int lanes = lpr_for(p.F);  // lanes per item: F/4 rounded up to 8, 16 or 32
+            launch_dep(agg_fixup_kernel<MODE>, (unsigned)cdiv(range_items * lanes, 256), 256, st, p, EB, items, records, lanes);
             LAUNCH_CHECK(a);
             if (num_long > 0) {
                 launch_dep(agg_fixup_long_kernel<MODE>, (unsigned)cdiv(num_long, 8), 256, st, p, EB, list, num_long);
