@@ -259,7 +259,14 @@ static int check_feat(int F)
 }
 
 // lanes per virtual warp for a feature width
-static inline int lpr_for(int F) { return F <= 32 ? 8 : (F <= 64 ? 16 : 32); }
+// lanes that cover one feature row with a float4 each: F/4 rounded up to 8, 16 or 32
+static inline int lanes_for(int F) { return F <= 32 ? 8 : (F <= 64 ? 16 : 32); }
+
+// lanes per virtual warp of the aggregation kernels for a feature width (agg_kernel<LPR, NV>).  Virtual warps HALF as
+// wide with two float4 per lane for rows of 33..128 floats -- one broadcast load of the staged idx / val then serves
+// twice as many items, and those loads take 18 % of the L1 data pipe on the reddit shape -- were measured and lost:
+// aggregation 2.27 -> 2.43 ms on reddit F=128, 0.496 -> 0.537 ms on proteins F=64.
+static inline int lpr_for(int F) { return lanes_for(F); }
 
 // graphs below this many edges use the 128-edge-per-warp variant: with 512 there would be fewer than
 // ~2 waves of CTAs on 148 SMs and the kernel would be bound by the length of one warp's walk
@@ -385,7 +392,7 @@ static int launch_agg(gnnagg_aggregator *a, AggParams p, cudaStream_t st)
             const int2 *records = nullptr;
             int num_long = 0;
             if (int rc = long_rows_of(a, p, EB, st, &list, &num_long, &records)) return rc;
-            const int lanes = lpr_for(p.F);  // lanes per item: F/4 rounded up to 8, 16 or 32
+            const int lanes = lanes_for(p.F);
             launch_dep(agg_fixup_kernel<MODE>, (unsigned)cdiv(range_items * lanes, 256), 256, st, p, EB, items, records, lanes);
             LAUNCH_CHECK(a);
             if (num_long > 0) {
@@ -1161,7 +1168,7 @@ int gnnagg_gcn_run_edgewise(gnnagg_aggregator *a, const float *X, float *Y, int 
     CUDA_TRY(cudaMemsetAsync(Y, 0, (size_t)a->n * feat * sizeof(float), st));  // aggr_gcn.h:447
     if (a->m == 0) return GNNAGG_OK;
     const EdgeParams g = edge_params(a);
-    const int lpr = lpr_for(feat);
+    const int lpr = lanes_for(feat);
     const unsigned grid = (unsigned)cdiv(cdiv(a->m, 32 / lpr), 8);
     if (lpr == 8)
         gcn_edgewise_kernel<8><<<grid, 256, 0, st>>>(g, a->d_val, X, Y, feat);
