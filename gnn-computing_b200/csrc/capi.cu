@@ -258,7 +258,6 @@ static int check_feat(int F)
     return GNNAGG_OK;
 }
 
-// lanes per virtual warp for a feature width
 // lanes that cover one feature row with a float4 each: F/4 rounded up to 8, 16 or 32
 static inline int lanes_for(int F) { return F <= 32 ? 8 : (F <= 64 ? 16 : 32); }
 
