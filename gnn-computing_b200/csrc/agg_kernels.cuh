@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
     const int64_t gwarp = (int64_t)(p.edge_lo / kWarpEdges) + (int64_t)blockIdx.x * kCtaWarps + warp;
     const int64_t wbase64 = gwarp * kWarpEdges;
     if (wbase64 >= p.edge_hi) return;  // whole warp idle (warp-uniform)
-    const int wbase = (int)wbase64;
+    // (opaque in the per-edge-output modes: their long batch body otherwise re-derives it from %tid / %ctaid every time)
+    const int wbase = mode_emits_edges(MODE) ? (int)opaque32((uint32_t)wbase64) : (int)wbase64;
     const int wcnt = min(kWarpEdges, p.num_edges - wbase);
 
     // ---------------- stage idx (+val) of this warp's edges ----------------
@@ -258,6 +259,9 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
         const uint32_t s_base = opaque32(smem_u32(my_idx));  // shared address of this warp's staged idx (val: + 4*kWarpEdges)
         const int second = act1 ? LPR * 16 : 0;  // byte offset of the second float4 (NV == 2)
 
+        // per-edge outputs: lane emit_id * (LPR / U) of the virtual warp ends up with the total of edge emit_id of a batch
+        const int emit_id = (int)opaque32((uint32_t)(vl / (LPR / U)));
+        const bool emit_lane = (vl % (LPR / U)) == 0;
         // per-edge combination of the gathered row (u is a compile-time constant after unrolling)
         float dd[U];  // SDDMM: this lane's partial dot products of the batch
         int drow[U];  // GAT backward: destination row of every edge of the batch (uniform over the virtual warp)
@@ -299,7 +303,8 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
                 relu_add4(acc0, pd0, a0);
                 if (NV > 1) relu_add4(acc1, pd1, a1);
             } else if (mode_emits_edges(MODE)) {
-                dd[u] = (act0 ? dot4(pd0, a0) : 0.f) + ((NV > 1 && act1) ? dot4(pd1, a1) : 0.f);
+                // pd0 / pd1 of a lane without columns stay zero (load_dst), so its product vanishes without a predicate
+                dd[u] = (NV > 1) ? dot4(pd0, a0) + dot4(pd1, a1) : dot4(pd0, a0);
                 if (MODE == kModeGATBWD) drow[u] = row;
             } else {
                 fma4(acc0, wu, a0);
@@ -309,8 +314,8 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
         // SDDMM: totals of the batch's dot products (reduce-scatter over the virtual warp) -> out[e .. e+nb)
         // same_row: all nb edges of the batch belong to the current `row` (no row ended inside the batch)
         auto sddmm_emit = [&](const int nb, const bool same_row) {
-            const int id = vl / (LPR / U);
-            const bool writer = (vl % (LPR / U)) == 0 && id < nb;
+            const int id = emit_id;
+            const bool writer = emit_lane && id < nb;
             // GAT backward: everything the epilogue needs besides g_e is fetched before the shuffles
             float sv = 0.f, a_v = 0.f;
             float2 ri = make_float2(0.f, 0.f);
@@ -352,7 +357,11 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
                 }
             }
             if (MODE == kModeGATBWD && cb + CHUNK >= F) {
-                if (same_row && row == srow) {
+                if (same_row) {
+                    if (row != srow) {
+                        sum_flush();
+                        srow = row;
+                    }
                     s_w += mw;  // zero on the lanes that hold no edge
                     s_t += mt;
                 } else {
@@ -480,9 +489,14 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
                     if (NV > 1) fma4(acc1, wu, v1[u]);
                 }
             } else if (!mode_gat_like(MODE) && row_end - e >= U) {
-                // no row ends inside the batch: straight FMA chain
+                // no row ends inside the batch: straight FMA chain (per-edge outputs: the dot products, all of row `row`)
 #pragma unroll
-                for (int u = 0; u < U; ++u) combine(u, w[u], v0[u], v1[u]);
+                for (int u = 0; u < U; ++u) {
+                    if (mode_emits_edges(MODE))
+                        dd[u] = (NV > 1) ? dot4(pd0, v0[u]) + dot4(pd1, v1[u]) : dot4(pd0, v0[u]);
+                    else
+                        combine(u, w[u], v0[u], v1[u]);
+                }
             } else {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
