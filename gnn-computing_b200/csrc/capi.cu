@@ -1322,8 +1322,8 @@ int gnnagg_gcn_backward(gnnagg_aggregator *a, const float *dY, float *dX, int fe
 int gnnagg_gat_backward(gnnagg_aggregator *a, const float *X, const float *att, const float *w, const float *den,
                         const float *Y, const float *dY, float *dX, float *datt, int feat, float slope, void *stream)
 {
-    if (!a || !X || !Y || !dY || !dX || !datt || (!att && !(w && den)))
-        return set_error(GNNAGG_ERR_ARG, "gnnagg_gat_backward: NULL argument (att, or w and den, must be given)");
+    if (!a || !X || !Y || !dY || !dX || !datt || (!att && !w))
+        return set_error(GNNAGG_ERR_ARG, "gnnagg_gat_backward: NULL argument (att or w must be given)");
     if (!a->tr) return set_error(GNNAGG_ERR_STATE, "gnnagg_gat_backward: gnnagg_transpose_build has not run");
     if (int rc = check_feat(feat)) return rc;
     if (!aligned16(X) || !aligned16(Y) || !aligned16(dY) || !aligned16(dX))

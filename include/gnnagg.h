@@ -243,8 +243,9 @@ int gnnagg_sddmm(gnnagg_aggregator *a, const float *X1, const float *X2, float *
  *                           dX[u,:] = sum_e alpha_e dY[v,:]            (:264)
  *                           datt[2v] = sum_e ds_e,  datt[2u+1] = sum_e ds_e   (:287-290; att/datt have max(num_v,num_src) rows)
  *                         Either `att` is given (w, den may be NULL: weights are recomputed), or w[m] (un-normalised
- *                         weights in CSR order, what aggr_gat_fine leaves in newval, :193) and den[num_v] (`div` of
- *                         run_bwd) -- then att may be NULL and the sign of s_e is read from w_e > 1.
+ *                         weights in CSR order, what aggr_gat_fine leaves in newval, :193) -- then att may be NULL and
+ *                         the sign of s_e is read from w_e > 1.  den[num_v] (`div` of run_bwd) is optional: when NULL
+ *                         the row sums D_v are formed on the way (they cost nothing extra), when given it is used as is.
  *                         Outputs are overwritten (the reference accumulates into caller-zeroed arrays). */
 int gnnagg_transpose_build(gnnagg_aggregator *a, int num_src, void *stream);
 int gnnagg_transpose_dev(const gnnagg_aggregator *a, int *num_src, const int **t_ptr, const int **t_idx, const int **t_perm);

@@ -181,6 +181,11 @@ def test_gat_backward_from_weights_and_rectangular(gn, orc, cuda, slope):
                                 torch.empty((num_src, 2), device=cuda), slope=slope, w=w, den=den)
     assert rel_gate(dXw.cpu().numpy(), x64, sx, TOL_X)[0] == 0
     assert rel_gate(dAw.cpu().numpy(), a64, sa, TOL_A)[0] == 0
+    # den is optional: the row sums of w are formed during the first traversal anyway
+    dXn, dAn = agg.gat_backward(Xd, None, Y, dYd, torch.empty((num_src, F), device=cuda),
+                                torch.empty((num_src, 2), device=cuda), slope=slope, w=w)
+    assert rel_gate(dXn.cpu().numpy(), x64, sx, TOL_X)[0] == 0
+    assert rel_gate(dAn.cpu().numpy(), a64, sa, TOL_A)[0] == 0
 
 
 def test_gat_backward_vs_reference_kernel(gn, orc, cuda):
