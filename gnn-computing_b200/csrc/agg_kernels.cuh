@@ -265,11 +265,13 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
         // per-edge combination of the gathered row (u is a compile-time constant after unrolling)
         float dd[U];  // SDDMM: this lane's partial dot products of the batch
         int drow[U];  // GAT backward: destination row of every edge of the batch (uniform over the virtual warp)
+        int my_row = 0;
         // GAT backward, pass 1: (sum w, sum t) of row `srow`.  Every writer lane keeps the part of its own edges; the
         // virtual warp adds the parts up (fixed butterfly order) only when the row changes or the item ends.  The row
         // that enters the item leaves the sums in bwd_carry[item], a row that starts here in bwd_part[row].
         float s_w = 0.f, s_t = 0.f;
         int srow = -1;
+        const int item32 = (int)opaque32((uint32_t)item);  // fewer than 2^31 items; kept instead of re-derived per batch
         bool s_carry = carry_in;
         auto sum_flush = [&]() {
             if (srow >= 0) {
@@ -281,7 +283,7 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
                 }
                 if (vl == 0) {
                     if (s_carry)
-                        p.bwd_carry[item] = make_float2(tw, tt);
+                        p.bwd_carry[item32] = make_float2(tw, tt);
                     else
                         p.bwd_part[srow] = make_float2(tw, tt);
                 }
@@ -305,7 +307,10 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
             } else if (mode_emits_edges(MODE)) {
                 // pd0 / pd1 of a lane without columns stay zero (load_dst), so its product vanishes without a predicate
                 dd[u] = (NV > 1) ? dot4(pd0, a0) + dot4(pd1, a1) : dot4(pd0, a0);
-                if (MODE == kModeGATBWD) drow[u] = row;
+                if (MODE == kModeGATBWD) {
+                    drow[u] = row;
+                    if (emit_id == u) my_row = row;  // the row of the edge this lane will write
+                }
             } else {
                 fma4(acc0, wu, a0);
                 if (NV > 1) fma4(acc1, wu, a1);
@@ -322,13 +327,7 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
             if (MODE == kModeGATBWD && writer && cb + CHUNK >= F) {
                 sv = (p.att != nullptr) ? __ldg(p.att + 2 * (size_t)my_idx[e + id - wbase] + 1)  // source attention term
                                         : my_val[e + id - wbase];                                  // handed-in weight
-                int v = row;  // row of this writer's edge: the current one unless a row ended inside the batch
-                if (!same_row) {
-                    v = drow[0];
-#pragma unroll
-                    for (int u = 1; u < U; ++u)
-                        if (id == u) v = drow[u];
-                }
+                const int v = same_row ? row : my_row;  // row of this writer's edge
                 ri = __ldg(p.bwd_c + v);
                 if (p.att != nullptr) a_v = __ldg(p.att + 2 * (size_t)v);
             }
