@@ -65,12 +65,11 @@ static bool pdl_enabled()
 }
 
 template <class... KArgs, class... Args>
-static void launch_dep_smem(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args &&...args)
+static void launch_dep(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, Args &&...args)
 {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(block);
-    cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -78,12 +77,6 @@ static void launch_dep_smem(void (*kernel)(KArgs...), unsigned grid, unsigned bl
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);  // errors surface in the caller's LAUNCH_CHECK
-}
-
-template <class... KArgs, class... Args>
-static void launch_dep(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, Args &&...args)
-{
-    launch_dep_smem(kernel, grid, block, 0, st, static_cast<Args &&>(args)...);
 }
 
 }  // namespace gnnagg
@@ -1347,6 +1340,9 @@ int gnnagg_gat_backward(gnnagg_aggregator *a, const float *X, const float *att, 
     if (int rc = ensure(t->carry, t->carry_cap, (size_t)cdiv(a->m, EBt) * feat)) return rc;
     if (int rc = ensure(t->carry_den, t->carry_den_cap, (size_t)cdiv(a->m, EBt))) return rc;
     if (int rc = ensure(t->den_row, t->den_row_cap, (size_t)a->num_src)) return rc;
+    const bool large = a->m >= kSmallGraphEdges;  // (w, t) of the graph does not stay in L2: see step 4
+    if (large)
+        if (int rc = ensure(a->bwd_t, a->bwd_t_cap, (size_t)a->m)) return rc;
     // 1. per destination row: c_v = <Y[v], dY[v]>
     gat_bwd_rowinfo_kernel<<<(unsigned)cdiv((int64_t)a->n * 8, 256), 256, 0, st>>>(Y, dY, a->bwd_c, a->n, feat);
     LAUNCH_CHECK(a);
@@ -1376,10 +1372,9 @@ int gnnagg_gat_backward(gnnagg_aggregator *a, const float *X, const float *att, 
     launch_dep(gat_bwd_rowfinal_kernel, (unsigned)cdiv((int64_t)a->n * 8, 256), 256, st, a->d_ptr, a->bwd_part, a->bwd_carry,
                den, a->bwd_c, datt, a->n, EB);
     LAUNCH_CHECK(a);
-    if (a->m >= kSmallGraphEdges) {
+    if (large) {
         // 4a. large graphs: (w, t) permuted into transposed order by a streaming kernel, then the source half as a row sum
         //     and dX as the plain aggregation over the transposed CSR with edge values alpha
-        if (int rc = ensure(a->bwd_t, a->bwd_t_cap, (size_t)a->m)) return rc;
         launch_dep(gat_bwd_permute_kernel, (unsigned)cdiv(a->m, 256), 256, st, (const float2 *)a->bwd_wt, (const int *)a->t_perm,
                    (const int *)a->t_idx, (const float2 *)a->bwd_c, a->t_val, a->bwd_t, a->m);
         LAUNCH_CHECK(a);
