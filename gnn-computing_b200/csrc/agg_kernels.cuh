@@ -157,10 +157,15 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
     // ---------------- the walk: one virtual warp per item ----------------
     const int vw = lane / LPR;
     const int vl = lane % LPR;
-    const unsigned vw_mask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (vw * LPR));  // lanes of this virtual warp
+    // Mask of the shuffles below.  Their sources are always lanes of the caller's own virtual warp (width = LPR), whose
+    // lanes never diverge from each other, so the lanes that currently execute together are a valid mask -- and the
+    // right one: with the static per-virtual-warp mask, two or four virtual warps that run converged (the normal case)
+    // present DIFFERENT mask values to one shfl.sync, which the hardware then executes once per distinct mask behind a
+    // MATCH.ANY check (seen in the SASS of every LPR < 32 variant).  One common mask lets them share the instruction.
+    auto vmask = [&]() -> unsigned { return (LPR == 32) ? 0xffffffffu : __activemask(); };
     const int e0 = max(wbase + vw * EB, p.edge_lo);            // item clipped to the launched edge range
     const int e1 = min(wbase + vw * EB + EB, p.edge_hi);
-    if (e0 >= e1) return;  // below, only shuffles restricted to the lanes of one virtual warp (vw_mask)
+    if (e0 >= e1) return;  // below, only shuffles whose sources lie inside the caller's virtual warp (vmask)
     const int64_t item = gwarp * VPW + vw;
     const int F = p.F;
 
@@ -276,10 +281,11 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
         auto sum_flush = [&]() {
             if (srow >= 0) {
                 float tw = s_w, tt = s_t;
+                const unsigned m = vmask();
 #pragma unroll
                 for (int off = LPR / 2; off >= 1; off >>= 1) {
-                    tw += __shfl_xor_sync(vw_mask, tw, off, LPR);
-                    tt += __shfl_xor_sync(vw_mask, tt, off, LPR);
+                    tw += __shfl_xor_sync(m, tw, off, LPR);
+                    tt += __shfl_xor_sync(m, tt, off, LPR);
                 }
                 if (vl == 0) {
                     if (s_carry)
@@ -331,7 +337,7 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
                 ri = __ldg(p.bwd_c + v);
                 if (p.att != nullptr) a_v = __ldg(p.att + 2 * (size_t)v);
             }
-            VwReduceScatter<LPR, LPR / 2, U>::run(dd, vl, vw_mask);
+            VwReduceScatter<LPR, LPR / 2, U>::run(dd, vl, vmask());
             float mw = 0.f, mt = 0.f;  // GAT backward: (w, t) of this writer's edge
             if (writer) {
                 if (MODE == kModeSDDMM) {
@@ -407,9 +413,10 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 float wu = w[u];
-                if (mode_gat_like(MODE)) wu = __shfl_sync(vw_mask, a_src, u, LPR);  // all lanes of the virtual warp, every u
+                const unsigned m = mode_gat_like(MODE) ? vmask() : 0u;  // fresh: a flush may lie between two of these
+                if (mode_gat_like(MODE)) wu = __shfl_sync(m, a_src, u, LPR);  // all lanes of the virtual warp, every u
                 float du = 0.f;
-                if (MODE == kModeGATBWD2) du = __shfl_sync(vw_mask, ds_lane, u, LPR);
+                if (MODE == kModeGATBWD2) du = __shfl_sync(m, ds_lane, u, LPR);
                 if (u < nb) {
                     while (row_end == e + u) flush(false);
                     if (MODE == kModeGATBWD2) den += du;
@@ -471,19 +478,21 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
                     const float sc = a_dst + a_src;
                     wgt = __expf(fmaxf(sc, sc * p.slope));  // aggr_gat.h:143
                 }
+                const unsigned m = vmask();
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const float wu = __shfl_sync(vw_mask, wgt, u, LPR);
+                    const float wu = __shfl_sync(m, wgt, u, LPR);
                     den += wu;
                     fma4(acc0, wu, v0[u]);
                     if (NV > 1) fma4(acc1, wu, v1[u]);
                 }
                 wout = wgt;
             } else if (MODE == kModeGATBWD2 && row_end - e >= U) {
+                const unsigned m = vmask();
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    den += __shfl_sync(vw_mask, ds_lane, u, LPR);
-                    const float wu = __shfl_sync(vw_mask, a_src, u, LPR);
+                    den += __shfl_sync(m, ds_lane, u, LPR);
+                    const float wu = __shfl_sync(m, a_src, u, LPR);
                     fma4(acc0, wu, v0[u]);
                     if (NV > 1) fma4(acc1, wu, v1[u]);
                 }
@@ -501,12 +510,13 @@ __global__ void __launch_bounds__(kCtaThreads, (WE < 512) ? 4 : 3) agg_kernel(co
                 for (int u = 0; u < U; ++u) {
                     while (row_end == e + u) flush(false);
                     float wu = w[u];
+                    const unsigned m = mode_gat_like(MODE) ? vmask() : 0u;  // fresh: flush() above may have run
                     if (MODE == kModeGATBWD2) {
-                        wu = __shfl_sync(vw_mask, a_src, u, LPR);
-                        den += __shfl_sync(vw_mask, ds_lane, u, LPR);
+                        wu = __shfl_sync(m, a_src, u, LPR);
+                        den += __shfl_sync(m, ds_lane, u, LPR);
                     }
                     if (MODE == kModeGAT) {
-                        const float sc = a_dst + __shfl_sync(vw_mask, a_src, u, LPR);
+                        const float sc = a_dst + __shfl_sync(m, a_src, u, LPR);
                         wu = __expf(fmaxf(sc, sc * p.slope));  // aggr_gat.h:143
                         den += wu;
                         if (SCHED && vl == u % LPR) wout = wu;
